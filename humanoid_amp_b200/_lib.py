@@ -1,0 +1,140 @@
+"""ctypes binding of ``libamp_b200.so`` (C ABI declared in ``include/amp_b200.h``).
+
+There is no CPU fallback and no alternative backend: if the shared object is missing, or a call fails, this module
+raises.  The library is built in-tree by ``python -m humanoid_amp_b200.build`` (``__graft_entry__.build()``).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libamp_b200.so")
+
+AMP_OK, AMP_EINVAL, AMP_ECUDA, AMP_ENODEV, AMP_ERANGE, AMP_ENOMEM = 0, -1, -2, -3, -4, -5
+ABI_VERSION = 1
+
+
+class AmpB200Error(RuntimeError):
+    """A call into libamp_b200.so failed (``code`` is the negative AMP_E* status)."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"[amp_b200 {code}] {message}")
+        self.code = code
+
+
+class LibDesc(C.Structure):
+    """``amp_lib_desc_t``"""
+
+    _fields_ = [
+        ("num_frames", C.c_int64),
+        ("num_dofs", C.c_int32),
+        ("num_bodies", C.c_int32),
+        ("num_trajectories", C.c_int32),
+        ("_pad0", C.c_int32),
+        ("dt", C.c_double),
+        ("traj_starts", C.c_void_p),
+        ("traj_ends", C.c_void_p),
+        ("durations", C.c_void_p),
+        ("dof_positions", C.c_void_p),
+        ("dof_velocities", C.c_void_p),
+        ("body_positions", C.c_void_p),
+        ("body_rotations", C.c_void_p),
+        ("body_linear_velocities", C.c_void_p),
+        ("body_angular_velocities", C.c_void_p),
+        ("dof_indexes", C.c_void_p),
+        ("num_obs_dofs", C.c_int32),
+        ("ref_body_index", C.c_int32),
+        ("key_body_indexes", C.c_void_p),
+        ("num_key_bodies", C.c_int32),
+        ("_pad1", C.c_int32),
+    ]
+
+
+_P, _I32, _I64, _F32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+
+# name -> (restype, argtypes); mirrors include/amp_b200.h one to one (tests/test_abi.py checks the header against this)
+SIGNATURES = {
+    "amp_b200_abi_version": (C.c_int, []),
+    "amp_last_error": (C.c_char_p, []),
+    "amp_set_device": (C.c_int, [C.c_int]),
+    "amp_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
+    "amp_lib_create": (C.c_int, [C.POINTER(LibDesc), _P, C.POINTER(_P)]),
+    "amp_lib_destroy": (C.c_int, [_P]),
+    "amp_lib_obs_width": (C.c_int, [_P]),
+    "amp_lib_poll_flags": (C.c_int, [_P, _P, C.POINTER(C.c_uint32)]),
+    "amp_frame_blend": (C.c_int, [_P, _P, _P, _I64, _P, _P, _P, _P, _P]),
+    "amp_sample_full": (C.c_int, [_P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P]),
+    "amp_lerp": (C.c_int, [_P, _P, _P, _I64, _I64, _P, _P]),
+    "amp_slerp": (C.c_int, [_P, _P, _P, _I64, _I64, _P, _P]),
+    "amp_collect_reference": (C.c_int, [_P, _P, _P, _I64, _I32, _P, _I64, _I64, _I64, _P, _P]),
+    "amp_compute_obs": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _P]),
+    "amp_tangent_normal": (C.c_int, [_P, _I64, _P, _P]),
+    "amp_obs_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _I32, _I32, _P, _P, _I64, _P]),
+    "amp_disc_create": (C.c_int, [_I32, _I32, _I32, _I64, _P, C.POINTER(_P)]),
+    "amp_disc_destroy": (C.c_int, [_P]),
+    "amp_disc_load": (C.c_int, [_P] * 9 + [_P]),
+    "amp_disc_style_reward": (C.c_int, [_P, _P, _I64, _I64, _F32, _P, _P, _P]),
+    "amp_style_reward_from_logits": (C.c_int, [_P, _I64, _F32, _P, _P]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load (once) and type the shared library.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise AmpB200Error(
+            AMP_ENODEV,
+            f"{LIB_PATH} is missing: build the CUDA extension with `python -m humanoid_amp_b200.build` "
+            "(there is no CPU or PyTorch fallback for this path)",
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here means the .so is stale relative to the header
+        fn.restype, fn.argtypes = res, args
+    got = lib.amp_b200_abi_version()
+    if got != ABI_VERSION:
+        raise AmpB200Error(AMP_EINVAL, f"libamp_b200.so has ABI version {got}, the Python shim expects {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def check(status: int) -> None:
+    if status != AMP_OK:
+        msg = load().amp_last_error()
+        raise AmpB200Error(status, msg.decode(errors="replace") if msg else "unknown error")
+
+
+def require_cuda(device) -> torch.device:
+    """The product path runs on a CUDA device only."""
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise AmpB200Error(AMP_ENODEV, f"humanoid_amp_b200 runs on CUDA devices only (got device={device!r}); there is no CPU path")
+    if not torch.cuda.is_available():
+        raise AmpB200Error(AMP_ENODEV, "no CUDA device is available; humanoid_amp_b200 has no CPU fallback")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+def enter(device: torch.device):
+    """Make ``device`` current in the library's runtime and return (lib, cudaStream_t of torch's current stream)."""
+    lib = load()
+    check(lib.amp_set_device(device.index))
+    return lib, C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def ptr(t) -> C.c_void_p:
+    """Device (or host) pointer of a tensor / numpy array, or NULL."""
+    if t is None:
+        return C.c_void_p(0)
+    if isinstance(t, torch.Tensor):
+        return C.c_void_p(t.data_ptr())
+    return C.c_void_p(t.ctypes.data)

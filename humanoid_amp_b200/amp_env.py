@@ -1,0 +1,213 @@
+"""Env-side AMP observation path with the reference's call surface, on hand-written sm_100a kernels.
+
+Mirrors the AMP part of ``G1AmpEnv`` / ``HumanoidAmpEnv`` (``/root/reference/g1_amp_env.py``):
+
+* free functions ``compute_obs`` (``:535-561``) and ``quaternion_to_tangent_and_normal`` (``:489-497``);
+* :class:`AmpEnvPath` -- the state and methods the skrl AMP agent and the env's step/reset touch:
+  ``collect_reference_motions`` (``:445-486``), the history update of ``_get_observations`` (``:176-193``) and the
+  reset-time history fill of ``_reset_strategy_random`` (``:371-419``).
+
+PhysX stepping is out of scope: the simulator state (``robot.data.joint_pos`` ... ``body_ang_vel_w``) is passed in as
+tensors.  There is no CPU path.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .motion_loader import MotionLoader
+from .robots import G1, RobotSpec
+
+
+def _f32c(t: torch.Tensor, device) -> torch.Tensor:
+    return t.to(device=device, dtype=torch.float32).contiguous()
+
+
+def quaternion_to_tangent_and_normal(q: torch.Tensor) -> torch.Tensor:
+    """``(..., 4)`` wxyz -> ``(..., 6)``: the rotated x axis (tangent) and z axis (normal).  Reference ``:489-497``."""
+    dev = _lib.require_cuda(q.device)
+    qc = _f32c(q, dev).view(-1, 4)
+    out = torch.empty((qc.shape[0], 6), dtype=torch.float32, device=dev)
+    lib, stream = _lib.enter(dev)
+    _lib.check(lib.amp_tangent_normal(_lib.ptr(qc), qc.shape[0], _lib.ptr(out), stream))
+    return out.view(*q.shape[:-1], 6)
+
+
+def compute_obs(
+    dof_positions: torch.Tensor,
+    dof_velocities: torch.Tensor,
+    root_positions: torch.Tensor,
+    root_rotations: torch.Tensor,
+    root_linear_velocities: torch.Tensor,
+    root_angular_velocities: torch.Tensor,
+    key_body_positions: torch.Tensor,
+) -> torch.Tensor:
+    """One AMP observation row per sample (reference ``:535-561``):
+
+    ``[dof_pos D | dof_vel D | root_z | tangent 3 | normal 3 | root_lin_vel 3 | root_ang_vel 3 | key_pos - root_pos 3*Kb]``
+    """
+    dev = _lib.require_cuda(dof_positions.device)
+    n, D = dof_positions.shape
+    Kb = key_body_positions.shape[1]
+    args = [
+        _f32c(t, dev)
+        for t in (dof_positions, dof_velocities, root_positions, root_rotations, root_linear_velocities, root_angular_velocities, key_body_positions)
+    ]
+    for t, width in zip(args[2:6], (3, 4, 3, 3)):
+        if t.shape != (n, width):
+            raise RuntimeError(f"expected a ({n}, {width}) tensor, got {tuple(t.shape)}")
+    out = torch.empty((n, 2 * D + 13 + 3 * Kb), dtype=torch.float32, device=dev)
+    lib, stream = _lib.enter(dev)
+    _lib.check(lib.amp_compute_obs(*[_lib.ptr(t) for t in args], n, D, Kb, _lib.ptr(out), stream))
+    return out
+
+
+@dataclass
+class AmpEnvCfg:
+    """The cfg fields the AMP path reads (``g1_amp_env_cfg.py:45-53, 108-109``; ``humanoid_amp_env_cfg.py:35-42``)."""
+
+    motion_file: str
+    num_envs: int = 4096
+    num_amp_observations: int = 2
+    robot: RobotSpec = G1
+
+    @property
+    def amp_observation_space(self) -> int:
+        return self.robot.amp_observation_space
+
+    @property
+    def reference_body(self) -> str:
+        return self.robot.reference_body
+
+
+class AmpEnvPath:
+    """State + methods of the env that lie on the AMP hot path.
+
+    Attribute names follow the reference env (``g1_amp_env.py:35-74``): ``_motion_loader``, ``ref_body_index``,
+    ``key_body_indexes``, ``motion_dof_indexes``, ``motion_ref_body_index``, ``motion_key_body_indexes``,
+    ``amp_observation_size``, ``amp_observation_buffer``, ``extras``.
+    """
+
+    def __init__(self, cfg: AmpEnvCfg, device, motion_loader: Optional[MotionLoader] = None):
+        self.cfg = cfg
+        self.device = _lib.require_cuda(device)
+        self.num_envs = cfg.num_envs
+        self._motion_loader = motion_loader or MotionLoader(motion_file=cfg.motion_file, device=self.device)
+        robot = cfg.robot
+        key_body_names = list(robot.key_body_names)
+        self.ref_body_index = robot.body_names.index(cfg.reference_body)
+        self.key_body_indexes = [robot.body_names.index(n) for n in key_body_names]
+        self.motion_dof_indexes = self._motion_loader.get_dof_index(robot.joint_names)
+        self.motion_ref_body_index = self._motion_loader.get_body_index([cfg.reference_body])[0]
+        self.motion_key_body_indexes = self._motion_loader.get_body_index(key_body_names)
+        self.amp_observation_size = cfg.num_amp_observations * cfg.amp_observation_space
+        self.amp_observation_buffer = torch.zeros(
+            (self.num_envs, cfg.num_amp_observations, cfg.amp_observation_space), device=self.device
+        )
+        self.extras: dict = {}
+        self._handle = self._motion_loader.make_env_handle(
+            self.motion_dof_indexes, self.motion_ref_body_index, self.motion_key_body_indexes
+        )
+        assert self._handle.obs_width == cfg.amp_observation_space
+        self._key_idx_host = np.ascontiguousarray(self.key_body_indexes, dtype=np.int32)
+
+    # ---- reference motions (skrl calls this with one argument) ------------------------------------------------------
+    def collect_reference_motions(self, num_samples: int, current_times=None, motion_ids=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``(num_samples, K*A)`` history-stacked reference observations, slot 0 = newest (reference ``:445-486``).
+
+        ``current_times`` / ``motion_ids``: host numpy (reference behaviour) or CUDA tensors.  ``motion_ids=None`` with
+        given times means clip 0 for every sample (reference ``:462``).  ``out``: optional destination with rows of
+        ``K*A`` contiguous floats (e.g. a slice of a replay memory); a fresh tensor is returned otherwise.
+        """
+        loader = self._motion_loader
+        if current_times is None:
+            motion_ids, current_times = loader.sample_times(num_samples)
+        t = loader._times_to_device(current_times)
+        n = t.numel()
+        ids = loader._ids_to_device(motion_ids, n)
+        K, width = self.cfg.num_amp_observations, self.amp_observation_size
+        if out is None:
+            out = torch.empty((n, width), dtype=torch.float32, device=self.device)
+        self._launch_collect(t, ids, n, out, row_index=None)
+        return out.view(-1, width)
+
+    def _launch_collect(self, t, ids, n, out: torch.Tensor, row_index: Optional[torch.Tensor], start_row: int = 0, capacity_rows: int = 0):
+        width = self.amp_observation_size
+        if out.dtype != torch.float32 or out.device != self.device:
+            raise RuntimeError("destination must be a float32 tensor on the env device")
+        rows = out.reshape(-1, out.shape[-1]) if out.dim() != 2 else out
+        if rows.data_ptr() != out.data_ptr() or rows.stride(-1) != 1 or rows.shape[-1] < width:
+            raise RuntimeError("destination rows must hold K*A contiguous floats")
+        lib, stream = _lib.enter(self.device)
+        _lib.check(
+            lib.amp_collect_reference(
+                self._handle.raw, _lib.ptr(t), _lib.ptr(ids), n, self.cfg.num_amp_observations, _lib.ptr(rows),
+                rows.stride(0), capacity_rows, start_row, _lib.ptr(row_index), stream,
+            )  # fmt: skip
+        )
+
+    def collect_reference_motions_into(self, memory: torch.Tensor, start_row: int, num_samples: int, current_times=None, motion_ids=None) -> int:
+        """Write the rows straight into a ring memory ``(capacity, ..., K*A)`` starting at ``start_row`` and wrapping at
+        the capacity (how skrl's ``RandomMemory.add_samples`` lays rows out); returns the next write index."""
+        loader = self._motion_loader
+        if current_times is None:
+            motion_ids, current_times = loader.sample_times(num_samples)
+        t = loader._times_to_device(current_times)
+        n = t.numel()
+        ids = loader._ids_to_device(motion_ids, n)
+        rows = memory.view(memory.shape[0], -1)
+        self._launch_collect(t, ids, n, rows, None, start_row=start_row, capacity_rows=rows.shape[0])
+        return (start_row + n) % rows.shape[0]
+
+    # ---- per-step update (reference _get_observations :176-193) -----------------------------------------------------
+    def update_amp_observations(self, joint_pos, joint_vel, body_pos_w, body_quat_w, body_lin_vel_w, body_ang_vel_w, policy_obs: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """compute_obs from simulator state, shift the history, write slot 0 -- one kernel, in place.
+
+        Returns ``extras["amp_obs"]``: the ``(num_envs, K*A)`` view of ``amp_observation_buffer``.  ``policy_obs``
+        optionally receives ``obs[:, :-3*Kb]`` (the base actor observation, reference ``:196``).
+        """
+        dev = self.device
+        tensors = [_f32c(t, dev) for t in (joint_pos, joint_vel, body_pos_w, body_quat_w, body_lin_vel_w, body_ang_vel_w)]
+        N, D = tensors[0].shape
+        Bsim = tensors[2].shape[1]
+        if N != self.num_envs or D != self.cfg.robot.num_joints:
+            raise RuntimeError(f"expected joint_pos ({self.num_envs}, {self.cfg.robot.num_joints}), got {(N, D)}")
+        stride = 0
+        if policy_obs is not None:
+            if policy_obs.dtype != torch.float32 or policy_obs.stride(-1) != 1:
+                raise RuntimeError("policy_obs must be float32 with unit inner stride")
+            stride = policy_obs.stride(0)
+        lib, stream = _lib.enter(dev)
+        _lib.check(
+            lib.amp_obs_step(
+                *[_lib.ptr(t) for t in tensors], N, D, Bsim, self.ref_body_index, _lib.ptr(self._key_idx_host),
+                len(self.key_body_indexes), self.cfg.num_amp_observations, _lib.ptr(self.amp_observation_buffer),
+                _lib.ptr(policy_obs), stride, stream,
+            )  # fmt: skip
+        )
+        self.extras = {"amp_obs": self.amp_observation_buffer.view(-1, self.amp_observation_size)}
+        return self.extras["amp_obs"]
+
+    # ---- reset (reference _reset_strategy_random :371-419, AMP part) -------------------------------------------------
+    def reset_amp_history(self, env_ids, times, motion_ids) -> None:
+        """Reset envs receive their reference history: fused collect + scatter into ``amp_observation_buffer[env_ids]``."""
+        loader = self._motion_loader
+        t = loader._times_to_device(times)
+        n = t.numel()
+        ids = loader._ids_to_device(motion_ids, n)
+        rows = torch.as_tensor(env_ids, device=self.device, dtype=torch.int64).contiguous().view(-1)
+        if rows.numel() != n:
+            raise RuntimeError("env_ids and times must have the same length")
+        self._launch_collect(t, ids, n, self.amp_observation_buffer.view(self.num_envs, -1), row_index=rows)
+
+    def poll_flags(self) -> int:
+        lib, stream = _lib.enter(self.device)
+        flags = C.c_uint32(0)
+        _lib.check(lib.amp_lib_poll_flags(self._handle.raw, stream, C.byref(flags)))
+        return flags.value

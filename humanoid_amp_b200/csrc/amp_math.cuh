@@ -1,0 +1,107 @@
+// Device math of the AMP path, written with explicitly rounded intrinsics (__fmul_rn / __dadd_rn ...) so that no
+// multiply-add is ever contracted into an FMA: the reference evaluates every torch / numpy op with its own rounding and
+// two hard thresholds in the slerp make the result sensitive to 1-ulp changes.  The file is also
+// compiled with -fmad=false as a second line of defence.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace amp {
+
+// ---- float64 frame index / blend : reference motions/motion_loader.py:294-305 -------------------------------------
+struct FrameBlend {
+    int64_t i0, i1;  // GLOBAL frame indices (trajectory start + local index)
+    double blend;    // float64 blend as the reference method returns it
+};
+
+// np.clip(x, 0, 1): NaN propagates (np.minimum/np.maximum semantics), unlike fmin/fmax.
+__device__ __forceinline__ double clip01(double x) {
+    x = (x < 0.0) ? 0.0 : x;
+    x = (x > 1.0) ? 1.0 : x;
+    return x;
+}
+
+// phase = clip(t/dur, 0, 1); l0 = rint(phase*span) (half-even); l1 = min(l0+1, span);
+// blend = rint(((t - l0*dt)/dt) * 1e5) / 1e5      (numpy round(decimals=5) == multiply, rint, divide)
+__device__ __forceinline__ FrameBlend frame_blend(double t, double dur, int64_t start, int64_t end, double dt) {
+    const int64_t span = end - start;
+    const double phase = clip01(__ddiv_rn(t, dur));
+    const int64_t l0 = __double2ll_rn(__dmul_rn(phase, (double)span));  // cvt.rni: round-half-even like np.rint
+    const int64_t l1 = (l0 + 1 < span) ? (l0 + 1) : span;
+    double b = __ddiv_rn(__dsub_rn(t, __dmul_rn((double)l0, dt)), dt);
+    b = __ddiv_rn(rint(__dmul_rn(b, 1e5)), 1e5);
+    FrameBlend r;
+    r.i0 = start + l0;
+    r.i1 = start + l1;
+    r.blend = b;
+    return r;
+}
+
+// ---- fp32 lerp : motion_loader.py:215   (1.0 - blend) * a + blend * b ------------------------------------------------
+__device__ __forceinline__ float lerp_w(float one_minus_blend, float blend, float a, float b) {
+    return __fadd_rn(__fmul_rn(one_minus_blend, a), __fmul_rn(blend, b));
+}
+__device__ __forceinline__ float lerp(float blend, float a, float b) {
+    return lerp_w(__fsub_rn(1.0f, blend), blend, a, b);
+}
+
+// ---- shortest-arc slerp, wxyz : motion_loader.py:247-279 -------------------------------------------------------------
+// float4 holds (w, x, y, z) in (.x, .y, .z, .w).
+__device__ __forceinline__ float4 slerp(float4 q0, float4 q1, float blend) {
+    // ((w0*w1 + x0*x1) + y0*y1) + z0*z1, every product and sum rounded on its own (:248-253)
+    float c = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(q0.x, q1.x), __fmul_rn(q0.y, q1.y)), __fmul_rn(q0.z, q1.z)),
+                        __fmul_rn(q0.w, q1.w));
+    if (c < 0.0f) {  // q1[neg_mask] = -q1[neg_mask] (:255-257); NaN compares false, as in torch
+        q1.x = -q1.x; q1.y = -q1.y; q1.z = -q1.z; q1.w = -q1.w;
+    }
+    c = fabsf(c);
+    const float half = acosf(c);                                      // NaN for c > 1, masked below
+    const float s = __fsqrt_rn(__fsub_rn(1.0f, __fmul_rn(c, c)));     // sqrt(1.0 - c*c), unfused (:262)
+    const float ra = __fdiv_rn(sinf(__fmul_rn(__fsub_rn(1.0f, blend), half)), s);
+    const float rb = __fdiv_rn(sinf(__fmul_rn(blend, half)), s);
+    float4 o;
+    o.x = __fadd_rn(__fmul_rn(ra, q0.x), __fmul_rn(rb, q1.x));
+    o.y = __fadd_rn(__fmul_rn(ra, q0.y), __fmul_rn(rb, q1.y));
+    o.z = __fadd_rn(__fmul_rn(ra, q0.z), __fmul_rn(rb, q1.z));
+    o.w = __fadd_rn(__fmul_rn(ra, q0.w), __fmul_rn(rb, q1.w));
+    if (fabsf(s) < 0.001f) {  // midpoint fallback, ignores blend (:275-277); false for NaN s
+        o.x = __fadd_rn(__fmul_rn(0.5f, q0.x), __fmul_rn(0.5f, q1.x));
+        o.y = __fadd_rn(__fmul_rn(0.5f, q0.y), __fmul_rn(0.5f, q1.y));
+        o.z = __fadd_rn(__fmul_rn(0.5f, q0.z), __fmul_rn(0.5f, q1.z));
+        o.w = __fadd_rn(__fmul_rn(0.5f, q0.w), __fmul_rn(0.5f, q1.w));
+    }
+    if (c >= 1.0f) o = q0;  // identity fallback, also masks the NaNs of acos(c > 1) (:278)
+    return o;
+}
+
+// ---- quaternion_to_tangent_and_normal : g1_amp_env.py:489-497 -------------------------------------------------------
+// quat_apply(q, v) = v + w*t + xyz x t with t = 2*(xyz x v), specialised for v = x-hat and v = z-hat keeping the
+// rounding sequence of the generic expression (products rounded separately, then added).
+__device__ __forceinline__ void tangent_normal(float4 q, float tn[6]) {
+    const float w = q.x, x = q.y, y = q.z, z = q.w;
+    const float x2 = __fmul_rn(x, __fmul_rn(2.0f, x));
+    const float y2 = __fmul_rn(y, __fmul_rn(2.0f, y));
+    const float z2 = __fmul_rn(z, __fmul_rn(2.0f, z));
+    const float wx = __fmul_rn(w, __fmul_rn(2.0f, x));
+    const float wy = __fmul_rn(w, __fmul_rn(2.0f, y));
+    const float wz = __fmul_rn(w, __fmul_rn(2.0f, z));
+    const float xy = __fmul_rn(x, __fmul_rn(2.0f, y));
+    const float xz = __fmul_rn(x, __fmul_rn(2.0f, z));
+    const float yz = __fmul_rn(y, __fmul_rn(2.0f, z));
+    tn[0] = __fadd_rn(1.0f, __fsub_rn(-y2, z2));  // tangent = R(q) x-hat
+    tn[1] = __fadd_rn(wz, xy);
+    tn[2] = __fadd_rn(-wy, xz);
+    tn[3] = __fadd_rn(wy, xz);                    // normal = R(q) z-hat
+    tn[4] = __fadd_rn(-wx, yz);
+    tn[5] = __fadd_rn(1.0f, __fsub_rn(-x2, y2));
+}
+
+// ---- skrl AMP style reward : -log(max(1 - 1/(1+exp(-d)), 1e-4)) * scale ------------------------------------------------
+__device__ __forceinline__ float style_reward(float logit, float scale) {
+    const float e = expf(-logit);
+    const float p = __fsub_rn(1.0f, __fdiv_rn(1.0f, __fadd_rn(1.0f, e)));
+    return __fmul_rn(-logf(fmaxf(p, 0.0001f)), scale);
+}
+
+}  // namespace amp

@@ -1,0 +1,658 @@
+// K1 / K2 of the AMP hot path: motion sampling (frame index + blend, lerp, slerp) and AMP-observation building.
+//
+//   amp_frame_blend        <- MotionLoader._compute_frame_blend      (reference motions/motion_loader.py:281-307)
+//   amp_sample_full        <- MotionLoader.sample                    (:368-390)
+//   amp_lerp / amp_slerp   <- MotionLoader._interpolate / _slerp     (:211-215, :242-279)
+//   amp_collect_reference  <- G1AmpEnv.collect_reference_motions     (reference g1_amp_env.py:445-486)
+//   amp_compute_obs        <- compute_obs                            (:535-561)
+//   amp_tangent_normal     <- quaternion_to_tangent_and_normal       (:489-497)
+//   amp_obs_step           <- G1AmpEnv._get_observations, AMP part   (:176-193)
+//
+// All of it is gather / transform / stream-out work bounded by HBM bandwidth, not by math: no tensor cores here.
+// Design for B200: one warp owns a run of consecutive destination frames, consecutive lanes own consecutive
+// observation columns (so every global load and store of a warp is one contiguous 128-byte run), the float64 index
+// math and the root slerp are done once per frame by one lane and staged through shared memory, and the grid is a
+// persistent multiple of the SM count.
+//
+// Compile with -fmad=false (see amp_math.cuh).
+#include <algorithm>
+#include <cstring>
+#include <new>
+
+#include "amp_internal.h"
+#include "amp_math.cuh"
+
+namespace amp {
+
+struct KeyList {
+    int32_t k[kMaxKeyBodies];
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// Packed AMP row table, built once per library.  Row f (R = A rounded up to 4 floats, 16-byte aligned) holds exactly
+// the clip columns compute_obs consumes, already permuted into robot dof order and laid out at the observation's own
+// column offsets so that output column c is interpolated from packed column c:
+//   [0,D)        dof_pos[dof_indexes]          [D,2D)      dof_vel[dof_indexes]
+//   2D           root z                        2D+1..2D+4  root quaternion wxyz   (tangent/normal columns of the obs)
+//   2D+5, 2D+6   root x, y                     2D+7..2D+9  root linear velocity   2D+10..2D+12 root angular velocity
+//   2D+13+3j+a   key body j position, axis a (absolute; the root position is subtracted after interpolation)
+// This folds the column gathers of g1_amp_env.py:478-484 into the staging and cuts the per-frame read from
+// (2*D_clip + 13*B) floats to R floats (G1_dance: 2260 B -> 336 B).
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void pack_rows_kernel(LibView v, const int32_t *__restrict__ dof_idx, int32_t ref, KeyList keys,
+                                 float *__restrict__ packed) {
+    const int64_t total = v.num_frames * (int64_t)v.row_floats;
+    const int D = v.obs_dofs, D2 = 2 * D, B = v.num_bodies;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t f = e / v.row_floats;
+        const int c = (int)(e - f * v.row_floats);
+        float val = 0.0f;
+        if (c < D) {
+            val = v.dof_pos[f * v.num_dofs + dof_idx[c]];
+        } else if (c < D2) {
+            val = v.dof_vel[f * v.num_dofs + dof_idx[c - D]];
+        } else if (c == D2) {
+            val = v.body_pos[(f * B + ref) * 3 + 2];
+        } else if (c < D2 + 5) {
+            val = v.body_rot[(f * B + ref) * 4 + (c - D2 - 1)];
+        } else if (c < D2 + 7) {
+            val = v.body_pos[(f * B + ref) * 3 + (c - D2 - 5)];
+        } else if (c < D2 + 10) {
+            val = v.body_lin[(f * B + ref) * 3 + (c - D2 - 7)];
+        } else if (c < D2 + 13) {
+            val = v.body_ang[(f * B + ref) * 3 + (c - D2 - 10)];
+        } else if (c < v.obs_width) {
+            const int j = (c - D2 - 13) / 3, a = (c - D2 - 13) % 3;
+            val = v.body_pos[(f * B + keys.k[j]) * 3 + a];
+        }
+        packed[e] = val;
+    }
+}
+
+// Looks up the trajectory of a sample and evaluates the float64 frame/blend math; clamps for memory safety and raises
+// the sticky flags where the reference would raise IndexError / propagate NaN.
+__device__ __forceinline__ FrameBlend lookup_frame(const LibView &v, double t, int64_t id) {
+    if (id < 0 || id >= v.num_traj) {
+        atomicOr(v.flags, 1u);
+        id = id < 0 ? 0 : v.num_traj - 1;
+    }
+    const int64_t start = v.starts[id], end = v.ends[id];
+    FrameBlend fb = frame_blend(t, v.durations[id], start, end, v.dt);
+    if (fb.i0 < start || fb.i0 > end) {  // only reachable with a NaN time (or a zero-length clip): rint(NaN) -> INT64_MIN
+        atomicOr(v.flags, 2u);
+        fb.i0 = fb.i0 < start ? start : end;
+        fb.i1 = fb.i0;
+    }
+    return fb;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// amp_frame_blend
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void frame_blend_kernel(LibView v, const double *__restrict__ times, const int64_t *__restrict__ ids,
+                                   int64_t S, int64_t *__restrict__ idx0, int64_t *__restrict__ idx1,
+                                   float *__restrict__ blend32, double *__restrict__ blend64) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < S; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t id = ids ? ids[i] : 0;
+        if (id < 0 || id >= v.num_traj) {
+            atomicOr(v.flags, 1u);
+            id = id < 0 ? 0 : v.num_traj - 1;
+        }
+        // the raw (unclamped) result is reported, exactly what the reference method returns
+        const FrameBlend fb = frame_blend(times[i], v.durations[id], v.starts[id], v.ends[id], v.dt);
+        idx0[i] = fb.i0;
+        idx1[i] = fb.i1;
+        if (blend32) blend32[i] = __double2float_rn(fb.blend);
+        if (blend64) blend64[i] = fb.blend;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// amp_sample_full: one warp per output frame; lanes stride the columns of each of the six tensors.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void lerp_row(const float *__restrict__ src, int64_t i0, int64_t i1, int width, float omb,
+                                         float b, float *__restrict__ dst, int lane) {
+    const float *a = src + i0 * width, *c = src + i1 * width;
+    for (int j = lane; j < width; j += 32) __stcs(dst + j, lerp_w(omb, b, __ldg(a + j), __ldg(c + j)));
+}
+
+__global__ void __launch_bounds__(256) sample_full_kernel(LibView v, const double *__restrict__ times,
+                                                           const int64_t *__restrict__ ids, int64_t S,
+                                                           float *__restrict__ dof_pos, float *__restrict__ dof_vel,
+                                                           float *__restrict__ body_pos, float *__restrict__ body_rot,
+                                                           float *__restrict__ body_lin, float *__restrict__ body_ang) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int D = v.num_dofs, B = v.num_bodies;
+    for (int64_t f = warp; f < S; f += nwarps) {
+        // every lane evaluates the same scalar index math (identical inputs -> identical result, no shuffle needed)
+        const FrameBlend fb = lookup_frame(v, times[f], ids ? ids[f] : 0);
+        const float b = __double2float_rn(fb.blend), omb = __fsub_rn(1.0f, b);
+        if (dof_pos) lerp_row(v.dof_pos, fb.i0, fb.i1, D, omb, b, dof_pos + f * D, lane);
+        if (dof_vel) lerp_row(v.dof_vel, fb.i0, fb.i1, D, omb, b, dof_vel + f * D, lane);
+        if (body_pos) lerp_row(v.body_pos, fb.i0, fb.i1, B * 3, omb, b, body_pos + f * B * 3, lane);
+        if (body_lin) lerp_row(v.body_lin, fb.i0, fb.i1, B * 3, omb, b, body_lin + f * B * 3, lane);
+        if (body_ang) lerp_row(v.body_ang, fb.i0, fb.i1, B * 3, omb, b, body_ang + f * B * 3, lane);
+        if (body_rot) {
+            const float4 *q0 = reinterpret_cast<const float4 *>(v.body_rot) + fb.i0 * B;
+            const float4 *q1 = reinterpret_cast<const float4 *>(v.body_rot) + fb.i1 * B;
+            float4 *o = reinterpret_cast<float4 *>(body_rot) + f * B;
+            for (int j = lane; j < B; j += 32) __stcs(o + j, slerp(__ldg(q0 + j), __ldg(q1 + j), b));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// amp_lerp / amp_slerp with explicit end points
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void lerp_kernel(const float *__restrict__ a, const float *__restrict__ b, const float *__restrict__ blend,
+                            int64_t total, int64_t inner, float *__restrict__ out) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
+        out[e] = lerp(blend[e / inner], a[e], b[e]);
+}
+
+__global__ void slerp_kernel(const float4 *__restrict__ q0, const float4 *__restrict__ q1,
+                             const float *__restrict__ blend, int64_t total, int64_t bodies, float4 *__restrict__ out) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
+        out[e] = slerp(q0[e], q1[e], blend[e / bodies]);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// amp_collect_reference: fused history times -> frame/blend -> gather + lerp -> root slerp -> compute_obs -> stacked row.
+//
+// A warp owns a tile of consecutive samples (tile_samples * K <= kFramesPerTile frames).
+//   phase 1  one lane per frame: float64 index math, root quaternion slerp, tangent/normal, root position, and the
+//            destination offset; staged as a 64-byte FrameMeta record in the warp's slice of shared memory;
+//   phase 2  the warp walks its frames; lane l produces columns l, l+32, l+64, ... so the two packed-row reads and the
+//            store are contiguous 128-byte runs.  Which lanes hold the tangent/normal and key-body columns does not
+//            depend on the frame, so that classification is hoisted out of the loop.
+// Only __syncwarp is needed: warps never share data.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kCollectWarps = 8;
+constexpr int kFramesPerTile = 64;
+
+struct __align__(16) FrameMeta {
+    int32_t off0, off1;  // float offsets of the two packed rows
+    float b, omb;        // blend, 1 - blend
+    float tn[6];         // tangent, normal of the slerped root rotation
+    float root[3];       // interpolated root position (x, y, z)
+    float _pad;
+    int64_t out;         // float offset of this frame's A columns in the destination
+};
+static_assert(sizeof(FrameMeta) == 64, "FrameMeta must stay one 64-byte record");
+
+template <int NSLOT>
+__global__ void __launch_bounds__(kCollectWarps * 32)
+collect_reference_kernel(LibView v, const double *__restrict__ cur_times, const int64_t *__restrict__ ids, int64_t n,
+                         int K, int tile_samples, float *__restrict__ out, int64_t row_stride, int64_t capacity,
+                         int64_t start_row, const int64_t *__restrict__ row_index, int64_t num_tiles) {
+    __shared__ FrameMeta meta_all[kCollectWarps][kFramesPerTile];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    FrameMeta *meta = meta_all[warp];
+    const int D2 = 2 * v.obs_dofs, A = v.obs_width, R = v.row_floats;
+    const float *__restrict__ packed = v.packed;
+
+    // frame-invariant classification of this lane's columns: -1 inactive, 0 plain lerp, 1 tangent/normal, 2 key body
+    int kind[NSLOT], aux[NSLOT];
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) {
+        const int c = lane + 32 * s;
+        kind[s] = 0;
+        aux[s] = 0;
+        if (c >= A) {
+            kind[s] = -1;
+        } else if (c > D2 && c < D2 + 7) {
+            kind[s] = 1;
+            aux[s] = c - (D2 + 1);
+        } else if (c >= D2 + 13) {
+            kind[s] = 2;
+            aux[s] = (c - (D2 + 13)) % 3;
+        }
+    }
+
+    for (int64_t tile = blockIdx.x * (int64_t)kCollectWarps + warp; tile < num_tiles;
+         tile += (int64_t)gridDim.x * kCollectWarps) {
+        const int64_t s0 = tile * tile_samples;
+        const int ns = (int)min((int64_t)tile_samples, n - s0);
+        const int nf = ns * K;
+
+        // ---- phase 1: per-frame scalars ------------------------------------------------------------------------
+        for (int fl = lane; fl < nf; fl += 32) {
+            const int si = fl / K, k = fl - si * K;
+            const int64_t sample = s0 + si;
+            // g1_amp_env.py:454-457  t - dt*k, float64, never clamped (negative -> extrapolation)
+            const double t = __dsub_rn(cur_times[sample], __dmul_rn(v.dt, (double)k));
+            const FrameBlend fb = lookup_frame(v, t, ids ? ids[sample] : 0);
+            const float b = __double2float_rn(fb.blend), omb = __fsub_rn(1.0f, b);
+            FrameMeta m;
+            m.off0 = (int32_t)(fb.i0 * R);
+            m.off1 = (int32_t)(fb.i1 * R);
+            m.b = b;
+            m.omb = omb;
+            const float *r0 = packed + m.off0, *r1 = packed + m.off1;
+            const float4 q0 = make_float4(__ldg(r0 + D2 + 1), __ldg(r0 + D2 + 2), __ldg(r0 + D2 + 3), __ldg(r0 + D2 + 4));
+            const float4 q1 = make_float4(__ldg(r1 + D2 + 1), __ldg(r1 + D2 + 2), __ldg(r1 + D2 + 3), __ldg(r1 + D2 + 4));
+            tangent_normal(slerp(q0, q1, b), m.tn);
+            m.root[0] = lerp_w(omb, b, __ldg(r0 + D2 + 5), __ldg(r1 + D2 + 5));
+            m.root[1] = lerp_w(omb, b, __ldg(r0 + D2 + 6), __ldg(r1 + D2 + 6));
+            m.root[2] = lerp_w(omb, b, __ldg(r0 + D2), __ldg(r1 + D2));
+            m._pad = 0.0f;
+            int64_t row;
+            if (row_index) {
+                row = row_index[sample];
+            } else {
+                row = start_row + sample;
+                if (capacity > 0) row %= capacity;
+            }
+            m.out = row * row_stride + (int64_t)k * A;
+            meta[fl] = m;
+        }
+        __syncwarp();
+
+        // ---- phase 2: stream the rows out ----------------------------------------------------------------------
+#pragma unroll 2
+        for (int f = 0; f < nf; ++f) {
+            const int4 head = *reinterpret_cast<const int4 *>(&meta[f]);  // off0, off1, b, omb in one broadcast read
+            const float b = __int_as_float(head.z), omb = __int_as_float(head.w);
+            const float *r0 = packed + head.x, *r1 = packed + head.y;
+            float *o = out + meta[f].out;
+#pragma unroll
+            for (int s = 0; s < NSLOT; ++s) {
+                if (kind[s] < 0) continue;
+                const int c = lane + 32 * s;
+                float val;
+                if (kind[s] == 1) {
+                    val = meta[f].tn[aux[s]];
+                } else {
+                    val = lerp_w(omb, b, __ldg(r0 + c), __ldg(r1 + c));
+                    // key body offset: (interpolated key position) - (interpolated root position), g1_amp_env.py:552
+                    if (kind[s] == 2) val = __fsub_rn(val, meta[f].root[aux[s]]);
+                }
+                __stcs(o + c, val);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// compute_obs on caller tensors (one warp per row) and the per-step env variant with in-place history shift.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float pick6(const float tn[6], int i) {
+    // register array indexed by a lane-dependent value: select chain instead of local memory
+    float r = tn[0];
+    r = i == 1 ? tn[1] : r;
+    r = i == 2 ? tn[2] : r;
+    r = i == 3 ? tn[3] : r;
+    r = i == 4 ? tn[4] : r;
+    r = i == 5 ? tn[5] : r;
+    return r;
+}
+
+__global__ void __launch_bounds__(256) compute_obs_kernel(const float *__restrict__ dof_pos,
+                                                           const float *__restrict__ dof_vel,
+                                                           const float *__restrict__ root_pos,
+                                                           const float *__restrict__ root_rot,
+                                                           const float *__restrict__ root_lin,
+                                                           const float *__restrict__ root_ang,
+                                                           const float *__restrict__ key_pos, int64_t n, int D, int Kb,
+                                                           float *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int D2 = 2 * D, A = D2 + 13 + 3 * Kb;
+    for (int64_t i = warp; i < n; i += nwarps) {
+        const float4 q = make_float4(root_rot[i * 4], root_rot[i * 4 + 1], root_rot[i * 4 + 2], root_rot[i * 4 + 3]);
+        float tn[6];
+        tangent_normal(q, tn);
+        for (int c = lane; c < A; c += 32) {
+            float val;
+            if (c < D) val = dof_pos[i * D + c];
+            else if (c < D2) val = dof_vel[i * D + c - D];
+            else if (c == D2) val = root_pos[i * 3 + 2];
+            else if (c < D2 + 7) val = pick6(tn, c - D2 - 1);
+            else if (c < D2 + 10) val = root_lin[i * 3 + c - D2 - 7];
+            else if (c < D2 + 13) val = root_ang[i * 3 + c - D2 - 10];
+            else {
+                const int e = c - D2 - 13;
+                val = __fsub_rn(key_pos[i * Kb * 3 + e], root_pos[i * 3 + e % 3]);
+            }
+            out[i * A + c] = val;
+        }
+    }
+}
+
+__global__ void tangent_normal_kernel(const float *__restrict__ q, int64_t n, float *__restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float tn[6];
+        tangent_normal(make_float4(q[i * 4], q[i * 4 + 1], q[i * 4 + 2], q[i * 4 + 3]), tn);
+#pragma unroll
+        for (int j = 0; j < 6; ++j) out[i * 6 + j] = tn[j];
+    }
+}
+
+// One warp per env.  Column c of env i: build the new observation value from simulator state, move history slot
+// s -> s+1 for s = K-2 .. 0 (oldest first, so nothing is overwritten before it is read; every lane touches only its
+// own column, so no cross-lane hazard), then write slot 0.  Reference g1_amp_env.py:176-193.
+__global__ void __launch_bounds__(256)
+obs_step_kernel(const float *__restrict__ joint_pos, const float *__restrict__ joint_vel,
+                const float *__restrict__ body_pos, const float *__restrict__ body_quat,
+                const float *__restrict__ body_lin, const float *__restrict__ body_ang, int64_t N, int D, int Bsim,
+                int ref, KeyList keys, int Kb, int K, float *__restrict__ amp_buf, float *__restrict__ policy_obs,
+                int64_t policy_stride) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int D2 = 2 * D, A = D2 + 13 + 3 * Kb, policy_width = A - 3 * Kb;
+    for (int64_t i = warp; i < N; i += nwarps) {
+        const int64_t rb = i * Bsim + ref;
+        const float4 q = __ldg(reinterpret_cast<const float4 *>(body_quat) + rb);
+        float tn[6];
+        tangent_normal(q, tn);
+        float *env = amp_buf + i * (int64_t)K * A;
+        for (int c = lane; c < A; c += 32) {
+            float val;
+            if (c < D) val = __ldg(joint_pos + i * D + c);
+            else if (c < D2) val = __ldg(joint_vel + i * D + c - D);
+            else if (c == D2) val = __ldg(body_pos + rb * 3 + 2);
+            else if (c < D2 + 7) val = pick6(tn, c - D2 - 1);
+            else if (c < D2 + 10) val = __ldg(body_lin + rb * 3 + c - D2 - 7);
+            else if (c < D2 + 13) val = __ldg(body_ang + rb * 3 + c - D2 - 10);
+            else {
+                const int e = c - D2 - 13, j = e / 3, a = e - 3 * j;
+                val = __fsub_rn(__ldg(body_pos + (i * Bsim + keys.k[j]) * 3 + a), __ldg(body_pos + rb * 3 + a));
+            }
+            float *col = env + c;
+            int s = K - 2;
+            for (; s >= 3; s -= 4) {  // four slots per trip: all loads issued before the stores
+                const float a0 = col[(int64_t)s * A], a1 = col[(int64_t)(s - 1) * A];
+                const float a2 = col[(int64_t)(s - 2) * A], a3 = col[(int64_t)(s - 3) * A];
+                col[(int64_t)(s + 1) * A] = a0;
+                col[(int64_t)s * A] = a1;
+                col[(int64_t)(s - 1) * A] = a2;
+                col[(int64_t)(s - 2) * A] = a3;
+            }
+            for (; s >= 0; --s) col[(int64_t)(s + 1) * A] = col[(int64_t)s * A];
+            col[0] = val;
+            if (policy_obs && c < policy_width) policy_obs[i * policy_stride + c] = val;
+        }
+    }
+}
+
+// ---- host helpers -------------------------------------------------------------------------------------------------
+static int grid_for(int64_t items, int per_block, int ctas_per_sm) {
+    const int64_t want = (items + per_block - 1) / per_block;
+    const int64_t cap = (int64_t)sm_count() * ctas_per_sm;
+    return (int)std::max<int64_t>(1, std::min(want, cap));
+}
+
+static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template <typename T>
+static int upload(amp_lib *lib, const T *host, size_t count, cudaStream_t st, T **dev) {
+    void *p = nullptr;
+    AMP_CUDA_TRY(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+    lib->owned[lib->n_owned++] = p;
+    if (count) AMP_CUDA_TRY(cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, st));
+    *dev = static_cast<T *>(p);
+    return AMP_OK;
+}
+
+}  // namespace amp
+
+using namespace amp;
+
+extern "C" {
+
+int amp_lib_create(const amp_lib_desc_t *d, void *stream, amp_lib_t **out) {
+    AMP_REQUIRE(d && out, "amp_lib_create: NULL argument");
+    *out = nullptr;
+    AMP_REQUIRE(d->num_frames > 0 && d->num_dofs > 0 && d->num_bodies > 0 && d->num_trajectories > 0,
+                "amp_lib_create: empty library (F=%lld D=%d B=%d T=%d)", (long long)d->num_frames, d->num_dofs,
+                d->num_bodies, d->num_trajectories);
+    AMP_REQUIRE(d->traj_starts && d->traj_ends && d->durations, "amp_lib_create: NULL trajectory tables");
+    AMP_REQUIRE(d->dof_positions && d->dof_velocities && d->body_positions && d->body_rotations &&
+                    d->body_linear_velocities && d->body_angular_velocities,
+                "amp_lib_create: NULL clip tensor");
+    AMP_REQUIRE(aligned16(d->body_rotations), "amp_lib_create: body_rotations must be 16-byte aligned");
+    AMP_REQUIRE(d->dt > 0.0, "amp_lib_create: dt must be positive");
+    for (int t = 0; t < d->num_trajectories; ++t)
+        AMP_REQUIRE(d->traj_starts[t] >= 0 && d->traj_ends[t] >= d->traj_starts[t] && d->traj_ends[t] < d->num_frames,
+                    "amp_lib_create: trajectory %d spans [%lld, %lld] outside [0, %lld)", t,
+                    (long long)d->traj_starts[t], (long long)d->traj_ends[t], (long long)d->num_frames);
+    const bool with_env = d->num_obs_dofs > 0;
+    if (with_env) {
+        AMP_REQUIRE(d->dof_indexes && d->num_key_bodies >= 0 && d->num_key_bodies <= kMaxKeyBodies &&
+                        (d->num_key_bodies == 0 || d->key_body_indexes),
+                    "amp_lib_create: bad env selection (Kb=%d, max %d)", d->num_key_bodies, kMaxKeyBodies);
+        AMP_REQUIRE(d->ref_body_index >= 0 && d->ref_body_index < d->num_bodies, "amp_lib_create: ref body %d out of range",
+                    d->ref_body_index);
+        for (int i = 0; i < d->num_obs_dofs; ++i)
+            AMP_REQUIRE(d->dof_indexes[i] >= 0 && d->dof_indexes[i] < d->num_dofs, "amp_lib_create: dof index %d out of range",
+                        d->dof_indexes[i]);
+        for (int i = 0; i < d->num_key_bodies; ++i)
+            AMP_REQUIRE(d->key_body_indexes[i] >= 0 && d->key_body_indexes[i] < d->num_bodies,
+                        "amp_lib_create: key body index %d out of range", d->key_body_indexes[i]);
+    }
+
+    amp_lib *lib = new (std::nothrow) amp_lib();
+    if (!lib) return fail(AMP_ENOMEM, "amp_lib_create: host allocation failed");
+    std::memset(lib, 0, sizeof(*lib));
+    cudaStream_t st = as_stream(stream);
+    int rc = AMP_OK;
+    auto bail = [&](int code) {
+        amp_lib_destroy(lib);
+        return code;
+    };
+    if (cudaGetDevice(&lib->device) != cudaSuccess) return bail(cuda_fail(cudaGetLastError(), "cudaGetDevice"));
+
+    LibView &v = lib->v;
+    v.num_frames = d->num_frames;
+    v.num_dofs = d->num_dofs;
+    v.num_bodies = d->num_bodies;
+    v.num_traj = d->num_trajectories;
+    v.dt = d->dt;
+    v.dof_pos = d->dof_positions;
+    v.dof_vel = d->dof_velocities;
+    v.body_pos = d->body_positions;
+    v.body_rot = d->body_rotations;
+    v.body_lin = d->body_linear_velocities;
+    v.body_ang = d->body_angular_velocities;
+
+    int64_t *starts = nullptr, *ends = nullptr;
+    double *durs = nullptr;
+    if ((rc = upload(lib, d->traj_starts, (size_t)d->num_trajectories, st, &starts))) return bail(rc);
+    if ((rc = upload(lib, d->traj_ends, (size_t)d->num_trajectories, st, &ends))) return bail(rc);
+    if ((rc = upload(lib, d->durations, (size_t)d->num_trajectories, st, &durs))) return bail(rc);
+    v.starts = starts;
+    v.ends = ends;
+    v.durations = durs;
+    uint32_t zero = 0, *flags = nullptr;
+    if ((rc = upload(lib, &zero, 1, st, &flags))) return bail(rc);
+    v.flags = flags;
+
+    if (with_env) {
+        v.obs_dofs = d->num_obs_dofs;
+        v.num_keys = d->num_key_bodies;
+        v.obs_width = 2 * v.obs_dofs + 13 + 3 * v.num_keys;
+        v.row_floats = (v.obs_width + 3) & ~3;
+        if (v.num_frames * (int64_t)v.row_floats >= (int64_t)1 << 31) {
+            set_error("amp_lib_create: packed table of %lld x %d floats exceeds 32-bit row offsets", (long long)v.num_frames,
+                      v.row_floats);
+            return bail(AMP_EINVAL);
+        }
+        int32_t *dof_idx = nullptr;
+        if ((rc = upload(lib, d->dof_indexes, (size_t)v.obs_dofs, st, &dof_idx))) return bail(rc);
+        void *packed = nullptr;
+        cudaError_t e = cudaMalloc(&packed, (size_t)v.num_frames * v.row_floats * sizeof(float));
+        if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc(packed rows)"));
+        lib->owned[lib->n_owned++] = packed;
+        v.packed = static_cast<float *>(packed);
+        KeyList keys{};
+        for (int i = 0; i < v.num_keys; ++i) keys.k[i] = d->key_body_indexes[i];
+        const int64_t total = v.num_frames * (int64_t)v.row_floats;
+        pack_rows_kernel<<<grid_for(total, 256, 8), 256, 0, st>>>(v, dof_idx, d->ref_body_index, keys,
+                                                                  static_cast<float *>(packed));
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return bail(cuda_fail(e, "pack_rows_kernel launch"));
+    }
+    // host arrays of the descriptor are read by the async copies above: finish them before returning
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return bail(cuda_fail(e, "cudaStreamSynchronize(amp_lib_create)"));
+    *out = lib;
+    return AMP_OK;
+}
+
+int amp_lib_destroy(amp_lib_t *lib) {
+    if (!lib) return AMP_OK;
+    for (int i = 0; i < lib->n_owned; ++i) cudaFree(lib->owned[i]);
+    delete lib;
+    return AMP_OK;
+}
+
+int amp_lib_obs_width(const amp_lib_t *lib) { return lib ? lib->v.obs_width : 0; }
+
+int amp_lib_poll_flags(amp_lib_t *lib, void *stream, uint32_t *flags) {
+    AMP_REQUIRE(lib && flags, "amp_lib_poll_flags: NULL argument");
+    cudaStream_t st = as_stream(stream);
+    AMP_CUDA_TRY(cudaMemcpyAsync(flags, lib->v.flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    AMP_CUDA_TRY(cudaMemsetAsync(lib->v.flags, 0, sizeof(uint32_t), st));
+    AMP_CUDA_TRY(cudaStreamSynchronize(st));
+    return AMP_OK;
+}
+
+int amp_frame_blend(amp_lib_t *lib, const double *times, const int64_t *ids, int64_t S, int64_t *idx0, int64_t *idx1,
+                    float *blend32, double *blend64, void *stream) {
+    AMP_REQUIRE(lib && S >= 0, "amp_frame_blend: bad handle or negative size");
+    if (S == 0) return AMP_OK;
+    AMP_REQUIRE(times && idx0 && idx1, "amp_frame_blend: NULL buffer");
+    frame_blend_kernel<<<grid_for(S, 256, 8), 256, 0, as_stream(stream)>>>(lib->v, times, ids, S, idx0, idx1, blend32,
+                                                                           blend64);
+    AMP_CUDA_TRY(cudaGetLastError());
+    return AMP_OK;
+}
+
+int amp_sample_full(amp_lib_t *lib, const double *times, const int64_t *ids, int64_t S, float *dof_pos, float *dof_vel,
+                    float *body_pos, float *body_rot, float *body_lin, float *body_ang, void *stream) {
+    AMP_REQUIRE(lib && S >= 0, "amp_sample_full: bad handle or negative size");
+    if (S == 0) return AMP_OK;
+    AMP_REQUIRE(times, "amp_sample_full: NULL times");
+    AMP_REQUIRE(!body_rot || aligned16(body_rot), "amp_sample_full: body_rot output must be 16-byte aligned");
+    sample_full_kernel<<<grid_for(S, 8, 8), 256, 0, as_stream(stream)>>>(lib->v, times, ids, S, dof_pos, dof_vel,
+                                                                         body_pos, body_rot, body_lin, body_ang);
+    AMP_CUDA_TRY(cudaGetLastError());
+    return AMP_OK;
+}
+
+int amp_lerp(const float *a, const float *b, const float *blend, int64_t n, int64_t inner, float *out, void *stream) {
+    AMP_REQUIRE(n >= 0 && inner >= 1, "amp_lerp: bad sizes");
+    if (n == 0) return AMP_OK;
+    AMP_REQUIRE(a && b && blend && out, "amp_lerp: NULL buffer");
+    lerp_kernel<<<grid_for(n * inner, 256, 8), 256, 0, as_stream(stream)>>>(a, b, blend, n * inner, inner, out);
+    AMP_CUDA_TRY(cudaGetLastError());
+    return AMP_OK;
+}
+
+int amp_slerp(const float *q0, const float *q1, const float *blend, int64_t n, int64_t bodies, float *out, void *stream) {
+    AMP_REQUIRE(n >= 0 && bodies >= 1, "amp_slerp: bad sizes");
+    if (n == 0) return AMP_OK;
+    AMP_REQUIRE(q0 && q1 && blend && out, "amp_slerp: NULL buffer");
+    AMP_REQUIRE(aligned16(q0) && aligned16(q1) && aligned16(out), "amp_slerp: quaternion buffers must be 16-byte aligned");
+    slerp_kernel<<<grid_for(n * bodies, 256, 8), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4 *>(q0), reinterpret_cast<const float4 *>(q1), blend, n * bodies, bodies,
+        reinterpret_cast<float4 *>(out));
+    AMP_CUDA_TRY(cudaGetLastError());
+    return AMP_OK;
+}
+
+int amp_collect_reference(amp_lib_t *lib, const double *cur_times, const int64_t *ids, int64_t n, int32_t K, float *out,
+                          int64_t row_stride, int64_t capacity_rows, int64_t start_row, const int64_t *row_index,
+                          void *stream) {
+    AMP_REQUIRE(lib && n >= 0, "amp_collect_reference: bad handle or negative size");
+    AMP_REQUIRE(lib->v.obs_width > 0, "amp_collect_reference: library was created without the env selection");
+    AMP_REQUIRE(K >= 1 && K <= kFramesPerTile, "amp_collect_reference: num_amp_observations %d outside [1, %d]", K,
+                kFramesPerTile);
+    if (n == 0) return AMP_OK;
+    const int A = lib->v.obs_width;
+    AMP_REQUIRE(cur_times && out, "amp_collect_reference: NULL buffer");
+    AMP_REQUIRE(row_stride >= (int64_t)K * A, "amp_collect_reference: row_stride %lld < K*A = %d", (long long)row_stride,
+                K * A);
+    AMP_REQUIRE(start_row >= 0, "amp_collect_reference: negative start_row");
+
+    // tile = consecutive samples of one warp; shrink it when the batch is small so the work still covers the chip
+    const int max_tile = std::max(1, kFramesPerTile / K);
+    const int64_t target_warps = (int64_t)sm_count() * kCollectWarps * 4;
+    const int tile_samples = (int)std::min<int64_t>(max_tile, std::max<int64_t>(1, (n + target_warps - 1) / target_warps));
+    const int64_t tiles = (n + tile_samples - 1) / tile_samples;
+    const int grid = grid_for(tiles, kCollectWarps, 4);
+    const int nslot = (A + 31) / 32;
+    cudaStream_t st = as_stream(stream);
+#define AMP_LAUNCH_COLLECT(NS)                                                                                        \
+    collect_reference_kernel<NS><<<grid, kCollectWarps * 32, 0, st>>>(lib->v, cur_times, ids, n, K, tile_samples, out, \
+                                                                      row_stride, capacity_rows, start_row, row_index,  \
+                                                                      tiles)
+    switch (nslot) {
+        case 1: AMP_LAUNCH_COLLECT(1); break;
+        case 2: AMP_LAUNCH_COLLECT(2); break;
+        case 3: AMP_LAUNCH_COLLECT(3); break;
+        case 4: AMP_LAUNCH_COLLECT(4); break;
+        case 5: AMP_LAUNCH_COLLECT(5); break;
+        case 6: AMP_LAUNCH_COLLECT(6); break;
+        case 7: AMP_LAUNCH_COLLECT(7); break;
+        case 8: AMP_LAUNCH_COLLECT(8); break;
+        default: return fail(AMP_EINVAL, "amp_collect_reference: observation width %d > 256 is not supported", A);
+    }
+#undef AMP_LAUNCH_COLLECT
+    AMP_CUDA_TRY(cudaGetLastError());
+    return AMP_OK;
+}
+
+int amp_compute_obs(const float *dof_pos, const float *dof_vel, const float *root_pos, const float *root_rot,
+                    const float *root_lin, const float *root_ang, const float *key_pos, int64_t n, int32_t D, int32_t Kb,
+                    float *out, void *stream) {
+    AMP_REQUIRE(n >= 0 && D >= 0 && Kb >= 0, "amp_compute_obs: bad sizes");
+    if (n == 0) return AMP_OK;
+    AMP_REQUIRE((D == 0 || (dof_pos && dof_vel)) && root_pos && root_rot && root_lin && root_ang && (Kb == 0 || key_pos) && out,
+                "amp_compute_obs: NULL buffer");
+    compute_obs_kernel<<<grid_for(n, 8, 8), 256, 0, as_stream(stream)>>>(dof_pos, dof_vel, root_pos, root_rot, root_lin,
+                                                                         root_ang, key_pos, n, D, Kb, out);
+    AMP_CUDA_TRY(cudaGetLastError());
+    return AMP_OK;
+}
+
+int amp_tangent_normal(const float *q, int64_t n, float *out, void *stream) {
+    AMP_REQUIRE(n >= 0, "amp_tangent_normal: negative size");
+    if (n == 0) return AMP_OK;
+    AMP_REQUIRE(q && out, "amp_tangent_normal: NULL buffer");
+    tangent_normal_kernel<<<grid_for(n, 256, 8), 256, 0, as_stream(stream)>>>(q, n, out);
+    AMP_CUDA_TRY(cudaGetLastError());
+    return AMP_OK;
+}
+
+int amp_obs_step(const float *joint_pos, const float *joint_vel, const float *body_pos_w, const float *body_quat_w,
+                 const float *body_lin_vel_w, const float *body_ang_vel_w, int64_t N, int32_t D, int32_t Bsim,
+                 int32_t ref_body, const int32_t *key_bodies, int32_t Kb, int32_t K, float *amp_buf, float *policy_obs,
+                 int64_t policy_stride, void *stream) {
+    AMP_REQUIRE(N >= 0 && D >= 1 && Bsim >= 1 && K >= 1, "amp_obs_step: bad sizes");
+    AMP_REQUIRE(Kb >= 0 && Kb <= kMaxKeyBodies && (Kb == 0 || key_bodies), "amp_obs_step: bad key body list");
+    AMP_REQUIRE(ref_body >= 0 && ref_body < Bsim, "amp_obs_step: ref body out of range");
+    if (N == 0) return AMP_OK;
+    AMP_REQUIRE(joint_pos && joint_vel && body_pos_w && body_quat_w && body_lin_vel_w && body_ang_vel_w && amp_buf,
+                "amp_obs_step: NULL buffer");
+    AMP_REQUIRE(aligned16(body_quat_w), "amp_obs_step: body_quat_w must be 16-byte aligned");
+    KeyList keys{};
+    for (int i = 0; i < Kb; ++i) {
+        AMP_REQUIRE(key_bodies[i] >= 0 && key_bodies[i] < Bsim, "amp_obs_step: key body %d out of range", key_bodies[i]);
+        keys.k[i] = key_bodies[i];
+    }
+    const int A = 2 * D + 13 + 3 * Kb;
+    AMP_REQUIRE(!policy_obs || policy_stride >= A - 3 * Kb, "amp_obs_step: policy_stride too small");
+    obs_step_kernel<<<grid_for(N, 8, 8), 256, 0, as_stream(stream)>>>(joint_pos, joint_vel, body_pos_w, body_quat_w,
+                                                                      body_lin_vel_w, body_ang_vel_w, N, D, Bsim, ref_body,
+                                                                      keys, Kb, K, amp_buf, policy_obs, policy_stride);
+    AMP_CUDA_TRY(cudaGetLastError());
+    return AMP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,169 @@
+/*
+ * amp_b200.h -- C ABI of the B200-native AMP hot path (libamp_b200.so, sm_100a).
+ *
+ * The reference (zhoushanghai/humanoid_amp) has no FFI for this path: its boundary is a Python call surface
+ * (SURVEY.md section 8b).  Every entry point below names the reference function it replaces (file:line into the
+ * reference tree).  The Python shims in humanoid_amp_b200/ keep the reference signatures and call these through ctypes.
+ *
+ * Conventions
+ *   - every pointer marked "device" is a caller-owned CUDA device pointer on the handle's device; "host" pointers are
+ *     read during the call only;
+ *   - every call enqueues on the passed cudaStream_t (void*; NULL = legacy default stream) and returns without
+ *     synchronising; no allocation happens after *_create;
+ *   - return value: 0 on success, a negative AMP_E* code otherwise; amp_last_error() gives a thread-local message;
+ *   - a handle belongs to one device; it is not safe for concurrent calls from several host threads, different
+ *     handles are independent;
+ *   - quaternions are wxyz, all float data is fp32, times are fp64, frame indices / motion ids are int64.
+ */
+#ifndef AMP_B200_H
+#define AMP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AMP_B200_ABI_VERSION 1
+
+/* The library is built with -fvisibility=hidden; only the entry points below are exported. */
+#if defined(__GNUC__)
+#define AMP_API __attribute__((visibility("default")))
+#else
+#define AMP_API
+#endif
+
+enum {
+    AMP_OK = 0,
+    AMP_EINVAL = -1,   /* bad argument (NULL pointer, negative size, misaligned buffer, ...) */
+    AMP_ECUDA = -2,    /* a CUDA runtime call or launch failed; amp_last_error() carries cudaGetErrorString */
+    AMP_ENODEV = -3,   /* no CUDA device / device is not sm_100 */
+    AMP_ERANGE = -4,   /* a motion id was outside [0, num_trajectories) or a time was NaN (see amp_lib_poll_flags) */
+    AMP_ENOMEM = -5
+};
+
+typedef struct amp_lib amp_lib_t;   /* a motion library staged on one device */
+typedef struct amp_disc amp_disc_t; /* discriminator weights staged for the tensor-core kernel */
+
+/* Description of a loaded motion library: what the reference MotionLoader.__init__ leaves behind
+ * (motions/motion_loader.py:98-164) plus the env's index lists (g1_amp_env.py:40-60). */
+typedef struct {
+    int64_t num_frames;        /* F, frames of all clips concatenated */
+    int32_t num_dofs;          /* D_clip, columns of dof_positions / dof_velocities */
+    int32_t num_bodies;        /* B, bodies per frame in the clip */
+    int32_t num_trajectories;  /* clips concatenated */
+    int32_t _pad0;
+    double dt;                 /* 1.0 / fps of the FIRST clip (motion_loader.py:122) */
+    const int64_t *traj_starts; /* host [num_trajectories] first global frame of each clip (:132) */
+    const int64_t *traj_ends;   /* host [num_trajectories] last global frame of each clip, inclusive (:134) */
+    const double *durations;    /* host [num_trajectories] dt * (frames - 1) (:135) */
+    /* the six fp32 tensors of the loader, device, C-contiguous (:141-158) */
+    const float *dof_positions;            /* (F, D_clip) */
+    const float *dof_velocities;           /* (F, D_clip) */
+    const float *body_positions;           /* (F, B, 3) */
+    const float *body_rotations;           /* (F, B, 4) wxyz */
+    const float *body_linear_velocities;   /* (F, B, 3) */
+    const float *body_angular_velocities;  /* (F, B, 3) */
+    /* env-side selection used by the fused AMP-observation path; all host arrays, may be NULL/0 when only
+     * amp_frame_blend / amp_sample_full are needed */
+    const int32_t *dof_indexes;  /* host [num_obs_dofs] clip column of each robot dof = motion_dof_indexes (g1_amp_env.py:52-54) */
+    int32_t num_obs_dofs;        /* D, robot dofs in the observation */
+    int32_t ref_body_index;      /* motion_ref_body_index (:55-57) */
+    const int32_t *key_body_indexes; /* host [num_key_bodies] motion_key_body_indexes (:58-60) */
+    int32_t num_key_bodies;      /* Kb */
+    int32_t _pad1;
+} amp_lib_desc_t;
+
+/* ---- library -------------------------------------------------------------------------------------------------- */
+AMP_API int amp_b200_abi_version(void);
+AMP_API const char *amp_last_error(void);
+/* Makes `device` current for the calling thread in the library's (statically linked) CUDA runtime.  The Python shims
+ * call it before every entry point so a process driving several GPUs always launches on the tensor's device. */
+AMP_API int amp_set_device(int device);
+/* SM count, major, minor of the current device (any pointer may be NULL). */
+AMP_API int amp_device_info(int *sm_count, int *cc_major, int *cc_minor);
+
+/* Stage a motion library: copies the trajectory tables and builds the packed AMP row table
+ * (one row per frame holding both interpolation end points of the columns compute_obs consumes).
+ * Replaces the device side of MotionLoader.__init__ (motion_loader.py:141-158) + the index gathers of
+ * collect_reference_motions (g1_amp_env.py:478-484) which are folded into the packing. */
+AMP_API int amp_lib_create(const amp_lib_desc_t *desc, void *stream, amp_lib_t **out);
+AMP_API int amp_lib_destroy(amp_lib_t *lib);
+/* AMP observation width A = 2*D + 13 + 3*Kb (0 if the library was created without the env selection). */
+AMP_API int amp_lib_obs_width(const amp_lib_t *lib);
+/* Reads and clears the device-side sticky flags (bit0: motion id out of range, bit1: NaN time). Synchronises the
+ * stream.  The kernels clamp such inputs for memory safety; the reference raises IndexError instead. */
+AMP_API int amp_lib_poll_flags(amp_lib_t *lib, void *stream, uint32_t *flags);
+
+/* MotionLoader._compute_frame_blend (motion_loader.py:281-307), float64 on device, bit-exact.
+ *   times  device f64[S]; motion_ids device i64[S] or NULL (= all zeros, the reference default at :366)
+ *   idx0, idx1 device i64[S] global frame indices; blend32 device f32[S] or NULL (the cast at :371);
+ *   blend64 device f64[S] or NULL (the value the reference method returns). */
+AMP_API int amp_frame_blend(amp_lib_t *lib, const double *times, const int64_t *motion_ids, int64_t S, int64_t *idx0,
+                    int64_t *idx1, float *blend32, double *blend64, void *stream);
+
+/* MotionLoader.sample with given times (motion_loader.py:368-390): frame/blend + 5 lerps + slerp over ALL bodies.
+ * Outputs device fp32, C-contiguous: dof_pos (S,D_clip) dof_vel (S,D_clip) body_pos (S,B,3) body_rot (S,B,4)
+ * body_lin_vel (S,B,3) body_ang_vel (S,B,3); any output pointer may be NULL to skip it. */
+AMP_API int amp_sample_full(amp_lib_t *lib, const double *times, const int64_t *motion_ids, int64_t S, float *dof_pos,
+                    float *dof_vel, float *body_pos, float *body_rot, float *body_lin_vel, float *body_ang_vel,
+                    void *stream);
+
+/* MotionLoader._interpolate / _slerp with explicit end points (motion_loader.py:211-215, :242-279).
+ *   a, b, out device f32[n * inner]; blend device f32[n] broadcast over inner.
+ *   q0, q1, out device f32[n * bodies * 4]; blend device f32[n] broadcast over bodies. */
+AMP_API int amp_lerp(const float *a, const float *b, const float *blend, int64_t n, int64_t inner, float *out, void *stream);
+AMP_API int amp_slerp(const float *q0, const float *q1, const float *blend, int64_t n, int64_t bodies, float *out,
+              void *stream);
+
+/* env.collect_reference_motions (g1_amp_env.py:445-486) fused end to end: history times t - dt*k (:454-457),
+ * frame/blend, gather+lerp of the consumed columns only, root slerp, compute_obs (:535-561), written as the
+ * history-stacked row (slot 0 = newest).
+ *   cur_times device f64[n]; motion_ids device i64[n] or NULL (= zeros, :462)
+ *   out device f32: row r of the destination starts at out + r*row_stride and receives K*A floats.
+ *   Destination row of sample i:  row_index ? row_index[i] : (start_row + i) % capacity_rows
+ *   (capacity_rows <= 0 means no wrap).  This is how the result lands directly in amp_observation_buffer[env_ids]
+ *   (:417-419) or in a skrl RandomMemory ring. */
+AMP_API int amp_collect_reference(amp_lib_t *lib, const double *cur_times, const int64_t *motion_ids, int64_t n, int32_t K,
+                          float *out, int64_t row_stride, int64_t capacity_rows, int64_t start_row,
+                          const int64_t *row_index, void *stream);
+
+/* Free function compute_obs (g1_amp_env.py:535-561) on contiguous inputs:
+ *   dof_pos, dof_vel (n,D); root_pos (n,3); root_rot (n,4); root_lin_vel, root_ang_vel (n,3); key_pos (n,Kb,3)
+ *   out (n, 2D+13+3Kb). */
+AMP_API int amp_compute_obs(const float *dof_pos, const float *dof_vel, const float *root_pos, const float *root_rot,
+                    const float *root_lin_vel, const float *root_ang_vel, const float *key_pos, int64_t n, int32_t D,
+                    int32_t Kb, float *out, void *stream);
+/* quaternion_to_tangent_and_normal (g1_amp_env.py:489-497): q (n,4) -> out (n,6). */
+AMP_API int amp_tangent_normal(const float *q, int64_t n, float *out, void *stream);
+
+/* Per-step env path, G1AmpEnv._get_observations AMP part (g1_amp_env.py:176-193): compute_obs from simulator state,
+ * shift the history (slot i -> i+1), write slot 0, all in place in amp_buf (N,K,A).
+ *   joint_pos, joint_vel (N,D); body_* (N,Bsim,3|4) as Isaac Lab's robot.data lays them out; ref_body and
+ *   key_bodies (host [Kb]) index Bsim.  policy_obs: optional (N, policy_width) output receiving obs[:, :A-3Kb]
+ *   (the "base actor obs" slice, :196) at row stride policy_stride; NULL to skip. */
+AMP_API int amp_obs_step(const float *joint_pos, const float *joint_vel, const float *body_pos_w, const float *body_quat_w,
+                 const float *body_lin_vel_w, const float *body_ang_vel_w, int64_t N, int32_t D, int32_t Bsim,
+                 int32_t ref_body, const int32_t *key_bodies, int32_t Kb, int32_t K, float *amp_buf, float *policy_obs,
+                 int64_t policy_stride, void *stream);
+
+/* ---- discriminator style reward (skrl AMP._update; cfg agents/skrl_g1_dance_amp_cfg.yaml:31-39, 80, 94-95) ------ */
+/* Network Linear(in,h1)-ReLU-Linear(h1,h2)-ReLU-Linear(h2,1) on RunningStandardScaler-normalised input.
+ * h1, h2 must be multiples of 128 (reference: 1024, 512); in_features any value >= 1 (padded to 64 internally). */
+AMP_API int amp_disc_create(int32_t in_features, int32_t h1, int32_t h2, int64_t max_rows, void *stream, amp_disc_t **out);
+AMP_API int amp_disc_destroy(amp_disc_t *d);
+/* Refresh the staged bf16 weights / fp32 biases / scaler statistics from the fp32 masters the trainer owns
+ * (device pointers; W row-major (out,in) as torch.nn.Linear stores them; mean/var are the scaler's float64 buffers). */
+AMP_API int amp_disc_load(amp_disc_t *d, const float *W1, const float *b1, const float *W2, const float *b2, const float *W3,
+                  const float *b3, const double *running_mean, const double *running_variance, void *stream);
+/* x device f32 (M, in_features) with row stride x_stride floats; reward device f32[M];
+ * logits device f32[M] or NULL.  reward = -log(max(1 - 1/(1+exp(-logit)), 1e-4)) * reward_scale. */
+AMP_API int amp_disc_style_reward(amp_disc_t *d, const float *x, int64_t x_stride, int64_t M, float reward_scale,
+                          float *reward, float *logits, void *stream);
+/* Standalone epilogue (logits -> reward) for callers that own the discriminator forward. */
+AMP_API int amp_style_reward_from_logits(const float *logits, int64_t M, float reward_scale, float *reward, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMP_B200_H */

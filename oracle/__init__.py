@@ -1,0 +1,40 @@
+"""CPU oracle for the AMP hot path -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+This package restates, in numpy + CPU torch (fp32, float64 host index math), the algorithm of the
+reference's per-step AMP path so the CUDA kernels in ``humanoid_amp_b200`` can be checked against it:
+
+* ``motion_oracle``  -- ``MotionLoader`` (reference ``motions/motion_loader.py:98-390``)
+* ``env_oracle``     -- ``compute_obs`` / ``quaternion_to_tangent_and_normal`` / ``collect_reference_motions`` /
+                        history shift / reset fill (reference ``g1_amp_env.py:175-193, 414-419, 445-497, 535-561``)
+* ``disc_oracle``    -- skrl ``RunningStandardScaler`` (eval) + MLP + AMP style reward (upstream skrl >= 1.4.3,
+                        ``agents/torch/amp/amp.py::_update``; configured by ``agents/skrl_g1_dance_amp_cfg.yaml:31-39, 80, 94-95``)
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import
+this package, and only as the checker or the timed CPU baseline.  The product package never imports it and has no CPU
+fallback: without the CUDA extension it raises.
+
+Parity pinning status
+---------------------
+* ``motion_oracle``: PINNED -- bit-identical to the live reference ``MotionLoader`` (imported by file path from
+  ``/root/reference``) on all 8 shipped clips; see ``tests/golden/make_golden.py`` and ``tests/test_oracle_pins.py``.
+  The committed fixtures under ``tests/golden/`` were produced by the live reference, not by this oracle.
+* ``env_oracle``: the reference env module imports ``isaaclab`` (absent) so it cannot be imported; the functions are
+  restated literally and pinned to the known answers recorded in SURVEY.md section 8c (obs row sums / slice for
+  G1_walk) which were produced with the live reference loader.  ``quat_apply`` is upstream Isaac Lab 2.2.0
+  (``isaaclab.utils.math.quat_apply``), not vendored: PARITY UNPINNED for that one function (closed-form rotation columns
+  agree to 1 ulp).
+* ``disc_oracle``: skrl is a third-party dependency that is neither vendored nor installed: PARITY UNPINNED; the oracle
+  is a literal restatement of the upstream expression.
+"""
+
+from .motion_oracle import OracleMotionLoader, frame_blend_f64, lerp_f32, slerp_f32  # noqa: F401
+from .env_oracle import (  # noqa: F401
+    quat_apply,
+    quaternion_to_tangent_and_normal,
+    compute_obs,
+    collect_reference_motions,
+    history_times,
+    shift_and_write_history,
+    reset_fill,
+)
+from .disc_oracle import OracleDiscriminator, running_standard_scaler_eval, style_reward_from_logits  # noqa: F401

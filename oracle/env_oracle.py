@@ -1,0 +1,107 @@
+"""Oracle restatement of the env-side AMP observation path (TEST INFRASTRUCTURE -- see ``oracle/__init__.py``).
+
+Follows ``/root/reference/g1_amp_env.py`` (the 28-DoF humanoid env ``humanoid_amp_env.py:219-286`` is the same math):
+
+* ``quaternion_to_tangent_and_normal`` ... ``:489-497``
+* ``compute_obs`` ........................ ``:535-561``
+* ``collect_reference_motions`` .......... ``:445-486``
+* history shift + slot-0 write ........... ``:187-193``
+* reset-time history fill ................ ``:414-419``
+
+``quat_apply`` is upstream ``isaaclab.utils.math.quat_apply`` (Isaac Lab 2.2.0, not vendored; call sites
+``g1_amp_env.py:16, 495-496``): restated from its published form, PARITY UNPINNED for that function alone.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+
+def quat_apply(quat: torch.Tensor, vec: torch.Tensor) -> torch.Tensor:
+    """Rotate ``vec`` by the wxyz quaternion ``quat``: ``v + w*t + xyz x t`` with ``t = 2 * (xyz x v)``."""
+    shape = vec.shape
+    quat = quat.reshape(-1, 4)
+    vec = vec.reshape(-1, 3)
+    xyz = quat[:, 1:]
+    t = xyz.cross(vec, dim=-1) * 2
+    return (vec + quat[:, 0:1] * t + xyz.cross(t, dim=-1)).view(shape)
+
+
+def quaternion_to_tangent_and_normal(q: torch.Tensor) -> torch.Tensor:
+    """Reference ``g1_amp_env.py:489-497``: rotate x-hat (tangent) and z-hat (normal) by ``q``, concatenate."""
+    x_hat = torch.zeros_like(q[..., :3])
+    z_hat = torch.zeros_like(q[..., :3])
+    x_hat[..., 0] = 1
+    z_hat[..., -1] = 1
+    return torch.cat([quat_apply(q, x_hat), quat_apply(q, z_hat)], dim=q.ndim - 1)
+
+
+def compute_obs(dof_pos, dof_vel, root_pos, root_rot, root_lin_vel, root_ang_vel, key_body_pos) -> torch.Tensor:
+    """Reference ``g1_amp_env.py:545-561``.
+
+    Row layout (A = 2D + 13 + 3*Kb):
+      [dof_pos D | dof_vel D | root_z 1 | tangent 3 | normal 3 | root_lin_vel 3 (world) | root_ang_vel 3 (world) |
+       (key_pos - root_pos) 3*Kb (world axes)]
+    """
+    rel = (key_body_pos - root_pos.unsqueeze(-2)).view(key_body_pos.shape[0], -1)
+    return torch.cat(
+        [dof_pos, dof_vel, root_pos[:, 2:3], quaternion_to_tangent_and_normal(root_rot), root_lin_vel, root_ang_vel, rel],
+        dim=-1,
+    )
+
+
+def history_times(current_times, dt, num_amp_observations):
+    """Reference ``g1_amp_env.py:454-457``: ``t - dt*k`` for k = 0..K-1, flattened sample-major (slot 0 = newest).
+
+    Times are NOT clamped: negative values extrapolate, values past the clip end hold the last frame.
+    """
+    return (np.expand_dims(current_times, axis=-1) - dt * np.arange(0, num_amp_observations)).flatten()
+
+
+def collect_reference_motions(
+    loader,
+    num_samples,
+    num_amp_observations,
+    dof_indexes,
+    ref_body_index,
+    key_body_indexes,
+    current_times=None,
+    motion_ids=None,
+):
+    """Reference ``g1_amp_env.py:445-486``.  ``loader`` is any object with the reference ``MotionLoader`` surface."""
+    if current_times is None:
+        motion_ids, current_times = loader.sample_times(num_samples)
+    times = history_times(current_times, loader.dt, num_amp_observations)
+    if motion_ids is not None:
+        ids = np.repeat(motion_ids, num_amp_observations)
+    else:
+        ids = np.zeros_like(times, dtype=np.int32)
+    dof_p, dof_v, body_p, body_r, body_lv, body_av = loader.sample(num_samples=num_samples, times=times, motion_ids=ids)
+    obs = compute_obs(
+        dof_p[:, dof_indexes],
+        dof_v[:, dof_indexes],
+        body_p[:, ref_body_index],
+        body_r[:, ref_body_index],
+        body_lv[:, ref_body_index],
+        body_av[:, ref_body_index],
+        body_p[:, key_body_indexes],
+    )
+    return obs.view(-1, num_amp_observations * obs.shape[-1])
+
+
+def shift_and_write_history(buffer: torch.Tensor, obs: torch.Tensor) -> torch.Tensor:
+    """Reference ``g1_amp_env.py:187-193``: slot i -> i+1 from the oldest down, then slot 0 = obs.  In place.
+
+    Returns the ``(N, K*A)`` view the reference exposes as ``extras["amp_obs"]``.
+    """
+    k = buffer.shape[1]
+    for i in reversed(range(k - 1)):
+        buffer[:, i + 1] = buffer[:, i]
+    buffer[:, 0] = obs.clone()
+    return buffer.view(-1, k * buffer.shape[2])
+
+
+def reset_fill(buffer: torch.Tensor, env_ids: torch.Tensor, amp_observations: torch.Tensor) -> None:
+    """Reference ``g1_amp_env.py:417-419``: reset envs receive the reference history rows.  In place."""
+    buffer[env_ids] = amp_observations.view(env_ids.shape[0], buffer.shape[1], -1)

@@ -1,0 +1,122 @@
+"""Pin the oracle: it must reproduce, BIT FOR BIT, what the live reference produced for the committed fixtures.
+
+The fixtures (``tests/golden``) were written by ``tests/golden/make_golden.py`` from the reference ``MotionLoader``
+imported by path.  When ``/root/reference`` is present (build container) the oracle is additionally compared with the
+live reference on the full shipped clips.
+"""
+
+from __future__ import annotations
+
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import CLIP_NAMES, REFERENCE_ROOT, clip_path, pooled_spec
+from oracle import OracleMotionLoader, env_oracle
+from humanoid_amp_b200.robots import G1, HUMANOID28, robot_for_clip
+
+OUT_NAMES = ("dof_pos", "dof_vel", "body_pos", "body_rot", "body_lin", "body_ang")
+
+
+def _same(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return a.shape == b.shape and np.array_equal(a, b, equal_nan=True)
+
+
+@pytest.mark.parametrize("name", CLIP_NAMES + ["pooled_humanoid"])
+def test_oracle_matches_reference_fixture_bitwise(golden, name):
+    files = pooled_spec().split(",") if name == "pooled_humanoid" else [clip_path(name)]
+    loader = OracleMotionLoader(files)
+    times, ids = golden[f"{name}/times"], golden[f"{name}/ids"]
+    i0, i1, blend = loader.compute_frame_blend(times, ids)
+    assert _same(i0, golden[f"{name}/idx0"]) and _same(i1, golden[f"{name}/idx1"])
+    assert _same(blend, golden[f"{name}/blend"])
+    outs = loader.sample(len(times), times=times, motion_ids=ids)
+    for key, t in zip(OUT_NAMES, outs):
+        assert _same(t.numpy(), golden[f"{name}/{key}"]), key
+
+    robot = robot_for_clip(loader.dof_names)
+    for k in (2, 10):
+        obs = env_oracle.collect_reference_motions(
+            loader, len(times), k,
+            loader.get_dof_index(robot.joint_names), loader.get_body_index([robot.reference_body])[0],
+            loader.get_body_index(robot.key_body_names), current_times=times, motion_ids=ids,
+        )  # fmt: skip
+        assert _same(obs.numpy(), golden[f"{name}/amp_obs_k{k}"])
+
+
+def test_pooled_sample_times_stream(golden):
+    loader = OracleMotionLoader(pooled_spec().split(","))
+    np.random.seed(123)
+    ids, times = loader.sample_times(16)
+    assert _same(ids, golden["pooled_humanoid/seed123_ids"])
+    assert _same(times, golden["pooled_humanoid/seed123_times"])
+    np.random.seed(5)
+    ids, times = loader.sample_times(7, start=True)
+    assert times.dtype == np.float64 and not times.any() and ids.shape == (7,)
+
+
+def test_survey_known_answers_index_math(kat):
+    """SURVEY.md 8c pins: frame indices / blends for G1_walk (F=399, 60 fps) need only the clip's frame count."""
+    from oracle import frame_blend_f64
+
+    g = kat["g1_walk"]
+    dt = 1.0 / np.int64(60)
+    assert float(dt).hex() == g["dt_hex"] == "0x1.1111111111111p-6"
+    durations = np.array([dt * (g["num_frames"] - 1)])
+    assert float(durations[0]).hex() == g["duration_hex"]
+    cur = np.array(g["current_times"])
+    t = env_oracle.history_times(cur, dt, 2)
+    i0, i1, b = frame_blend_f64(t, np.zeros(len(t), dtype=np.int32), durations, np.array([0]), np.array([g["num_frames"] - 1]), dt)
+    assert i0.tolist() == g["idx0"] == [0, 0, 0, 0, 1, 0, 60, 59, 200, 199, 398, 397, 398, 397, 398, 398]
+    assert i1.tolist() == g["idx1"] == [1, 1, 1, 1, 2, 1, 61, 60, 201, 200, 398, 398, 398, 398, 398, 398]
+    assert b.tolist() == g["blend"] == [0, -1, 0.24, -0.76, -0.25, -0.25, 0, 0, 0, 0, -0.2, -0.2, 0, 0, 22, 21]
+    assert g["dof_perm"] == [0, 6, 12, 1, 7, 13, 2, 8, 14, 3, 9, 15, 22, 4, 10, 16, 23, 5, 11, 17, 24, 18, 25, 19, 26, 20, 27, 21, 28]  # fmt: skip
+
+
+def test_env_oracle_known_answers_shapes():
+    q = torch.tensor([[1.0, 0, 0, 0], [0.70710678, 0, 0, 0.70710678]])
+    tn = env_oracle.quaternion_to_tangent_and_normal(q)
+    assert torch.allclose(tn[0], torch.tensor([1.0, 0, 0, 0, 0, 1]))
+    assert torch.allclose(tn[1], torch.tensor([0.0, 1, 0, 0, 0, 1]), atol=1e-6)  # yaw 90 deg: x-hat -> y-hat
+    buf = torch.zeros(3, 4, 5)
+    for step in range(1, 7):
+        view = env_oracle.shift_and_write_history(buf, torch.full((3, 5), float(step)))
+    assert view.shape == (3, 20) and buf[0, :, 0].tolist() == [6.0, 5.0, 4.0, 3.0]  # slot 0 = newest
+
+
+needs_reference = pytest.mark.skipif(
+    not os.path.exists(f"{REFERENCE_ROOT}/motions/motion_loader.py"), reason="live reference only exists in the build container"
+)
+
+
+@needs_reference
+@pytest.mark.parametrize("name", ["G1_walk", "G1_dance", "humanoid_walk", "G1_walk_lafan1"])
+def test_oracle_vs_live_reference_full_clip(name, kat):
+    spec = importlib.util.spec_from_file_location("ref_motion_loader", f"{REFERENCE_ROOT}/motions/motion_loader.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    path = f"{REFERENCE_ROOT}/motions/{name}.npz"
+    ref, ora = mod.MotionLoader(path, "cpu"), OracleMotionLoader([path])
+    rng = np.random.default_rng(7)
+    times = np.concatenate([rng.uniform(-0.2, ref.durations[0] + 0.2, 4000), (np.arange(300) + 0.5) * ref.dt])
+    ids = np.zeros(len(times), dtype=np.int64)
+    for a, b in zip(ref._compute_frame_blend(times, ids), ora.compute_frame_blend(times, ids)):
+        assert _same(a, b)
+    for a, b in zip(ref.sample(len(times), times=times, motion_ids=ids), ora.sample(len(times), times=times, motion_ids=ids)):
+        assert _same(a.numpy(), b.numpy())
+    if name == "G1_walk":
+        g = kat["g1_walk"]
+        obs = env_oracle.collect_reference_motions(
+            ora, 8, 2, ora.get_dof_index(G1.joint_names), ora.get_body_index(["pelvis"])[0],
+            ora.get_body_index(G1.key_body_names), current_times=np.array(g["current_times"]),
+            motion_ids=np.zeros(8, dtype=np.int64),
+        )  # fmt: skip
+        assert np.allclose(obs.double().sum(dim=1).numpy(), g["obs_row_sums"], rtol=0, atol=1e-9)
+        assert np.allclose(obs[3, 58:71].numpy(), g["obs3_58_71"], rtol=0, atol=0)
+        # values quoted (rounded) in SURVEY.md 8c
+        assert np.allclose(g["obs_row_sums"][:3], [2.52549723, 2.555956552, 2.592755598], atol=1e-8)
+        assert HUMANOID28.reference_body == "torso"
