@@ -38,13 +38,19 @@ constexpr int BM = 128;  // rows per tile = TMEM lanes
 constexpr int BN = 256;  // accumulator columns per tile = max UMMA N
 constexpr int BK = 64;   // bf16 per K-block = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
 constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KiB
 constexpr int NUM_THREADS = 192;
 constexpr int NUM_EPI_THREADS = 128;
 constexpr int TMEM_COLS = 512;
-constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 /*barriers*/ + 1024 /*alignment slack*/;
+// EPI_STORE keeps a bf16 staging area for TMA stores: per epilogue warp two 32-row x 64-column slabs (4 KiB each)
+constexpr int STORE_SLAB_BYTES = 32 * BK * 2;
+constexpr int STORE_STAGING_BYTES = 4 * 2 * STORE_SLAB_BYTES;  // 32 KiB
+__host__ __device__ constexpr int stages_for(int epi) { return epi == 0 ? 3 : 4; }
+__host__ __device__ constexpr int smem_bytes_for(int epi) {
+    return stages_for(epi) * (A_STAGE_BYTES + B_STAGE_BYTES) + (epi == 0 ? STORE_STAGING_BYTES : 0) + 256 /*barriers*/ +
+           1024 /*alignment slack*/;
+}
 
 // ---- PTX wrappers --------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -76,6 +82,21 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
         "l"(map), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0),
+                 "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -141,14 +162,16 @@ enum { EPI_STORE = 0, EPI_REWARD = 1 };
 
 template <int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-disc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M, int N,
-                 int num_k_blocks, EpilogueParams ep) {
+disc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ CUtensorMap tmap_out, int M, int N, int num_k_blocks, EpilogueParams ep) {
+    constexpr int STAGES = stages_for(EPI);
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B needs 1024-byte aligned stage buffers
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t smem_a = base;
     const uint32_t smem_b = base + STAGES * A_STAGE_BYTES;
-    const uint32_t bars = smem_b + STAGES * B_STAGE_BYTES;
+    const uint32_t staging = smem_b + STAGES * B_STAGE_BYTES;  // EPI_STORE only
+    const uint32_t bars = staging + (EPI == EPI_STORE ? STORE_STAGING_BYTES : 0);
     const uint32_t full_bar = bars;                    // STAGES x 8 B
     const uint32_t empty_bar = bars + 8 * STAGES;      // STAGES x 8 B
     const uint32_t tmem_full_bar = bars + 16 * STAGES; // 2 x 8 B
@@ -162,6 +185,7 @@ disc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+        if (EPI == EPI_STORE) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_out) : "memory");
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(full_bar + 8 * i, 1);
             mbar_init(empty_bar + 8 * i, 1);
@@ -233,39 +257,60 @@ disc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
         int acc = 0;
         uint32_t acc_phase = 0;
+        uint32_t store_it = 0;  // EPI_STORE: running count of TMA stores issued by this warp (selects the slab)
         for (int mt = blockIdx.x; mt < num_m_tiles; mt += gridDim.x) {
             const int row = mt * BM + quarter * 32 + lane;
             float dot = 0.0f;
             for (int nt = 0; nt < num_n_tiles; ++nt) {
                 mbar_wait(tmem_full_bar + 8 * acc, acc_phase);
                 tcgen05_fence_after();
+                if constexpr (EPI == EPI_STORE) {
+                    // bias + ReLU -> bf16, staged per warp as a [32 rows x 64 cols] slab in the 128B-swizzled layout and
+                    // written with one TMA store per slab (full 128-byte lines; rows past M are clipped by the tensor map)
 #pragma unroll 1
-                for (int chunk = 0; chunk < BN / 32; ++chunk) {
-                    uint32_t v[32];
-                    tmem_ld_32x32(tmem_base + lane_base + (uint32_t)(acc * BN + chunk * 32), v);
-                    tmem_ld_wait();
-                    const int col0 = nt * BN + chunk * 32;
-                    const float4 *bias4 = reinterpret_cast<const float4 *>(ep.bias + col0);
-                    if constexpr (EPI == EPI_STORE) {
-                        uint32_t packed[16];
+                    for (int cb = 0; cb < BN / BK; ++cb) {
+                        const uint32_t slab = staging + (uint32_t)((quarter * 2 + (store_it & 1)) * STORE_SLAB_BYTES);
+                        if (lane == 0) bulk_wait_read<1>();  // the store that last read this slab has drained it
+                        __syncwarp();
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 bb = __ldg(bias4 + j);
-                            const float h0 = fmaxf(__uint_as_float(v[4 * j + 0]) + bb.x, 0.0f);
-                            const float h1 = fmaxf(__uint_as_float(v[4 * j + 1]) + bb.y, 0.0f);
-                            const float h2 = fmaxf(__uint_as_float(v[4 * j + 2]) + bb.z, 0.0f);
-                            const float h3 = fmaxf(__uint_as_float(v[4 * j + 3]) + bb.w, 0.0f);
-                            __nv_bfloat162 p0 = __floats2bfloat162_rn(h0, h1), p1 = __floats2bfloat162_rn(h2, h3);
-                            packed[2 * j] = *reinterpret_cast<uint32_t *>(&p0);
-                            packed[2 * j + 1] = *reinterpret_cast<uint32_t *>(&p1);
-                        }
-                        if (row < M) {
-                            uint4 *dst = reinterpret_cast<uint4 *>(ep.out + (size_t)row * N + col0);
+                        for (int half = 0; half < 2; ++half) {
+                            uint32_t v[32];
+                            tmem_ld_32x32(tmem_base + lane_base + (uint32_t)(acc * BN + cb * BK + half * 32), v);
+                            tmem_ld_wait();
+                            const float4 *bias4 = reinterpret_cast<const float4 *>(ep.bias + nt * BN + cb * BK + half * 32);
 #pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                            for (int j = 0; j < 4; ++j) {  // 16-byte chunk (half*4 + j) of this thread's 128-byte row
+                                const float4 b0 = __ldg(bias4 + 2 * j), b1 = __ldg(bias4 + 2 * j + 1);
+                                const __nv_bfloat162 p0 = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[8 * j + 0]) + b0.x, 0.0f),
+                                                                                fmaxf(__uint_as_float(v[8 * j + 1]) + b0.y, 0.0f));
+                                const __nv_bfloat162 p1 = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[8 * j + 2]) + b0.z, 0.0f),
+                                                                                fmaxf(__uint_as_float(v[8 * j + 3]) + b0.w, 0.0f));
+                                const __nv_bfloat162 p2 = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[8 * j + 4]) + b1.x, 0.0f),
+                                                                                fmaxf(__uint_as_float(v[8 * j + 5]) + b1.y, 0.0f));
+                                const __nv_bfloat162 p3 = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[8 * j + 6]) + b1.z, 0.0f),
+                                                                                fmaxf(__uint_as_float(v[8 * j + 7]) + b1.w, 0.0f));
+                                const int chunk = (half * 4 + j) ^ (lane & 7);  // SWIZZLE_128B: chunk index XOR (row % 8)
+                                st_shared_v4(slab + (uint32_t)(lane * 128 + chunk * 16), *reinterpret_cast<const uint32_t *>(&p0),
+                                             *reinterpret_cast<const uint32_t *>(&p1), *reinterpret_cast<const uint32_t *>(&p2),
+                                             *reinterpret_cast<const uint32_t *>(&p3));
+                            }
                         }
-                    } else {
+                        fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA (async proxy)
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&tmap_out, slab, nt * BN + cb * BK, mt * BM + quarter * 32);
+                            bulk_commit();
+                        }
+                        ++store_it;
+                    }
+                } else {
+#pragma unroll 1
+                    for (int chunk = 0; chunk < BN / 32; ++chunk) {
+                        uint32_t v[32];
+                        tmem_ld_32x32(tmem_base + lane_base + (uint32_t)(acc * BN + chunk * 32), v);
+                        tmem_ld_wait();
+                        const int col0 = nt * BN + chunk * 32;
+                        const float4 *bias4 = reinterpret_cast<const float4 *>(ep.bias + col0);
                         const float4 *w4 = reinterpret_cast<const float4 *>(ep.w3 + col0);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
@@ -290,6 +335,9 @@ disc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 }
             }
         }
+        if constexpr (EPI == EPI_STORE) {
+            if (lane == 0) bulk_wait_all();  // all TMA stores of this warp have completed before the CTA exits
+        }
     }
 
     tcgen05_fence_before();
@@ -301,31 +349,68 @@ disc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 }
 
 // ---- RunningStandardScaler (eval) + bf16 cast: x (M, in) fp32 -> x_hat (M, Kp) bf16, zero padded -----------------------
-// One warp per row, lane l handles column pairs l, l+32, ...: 8-byte loads and 4-byte stores, fully coalesced.
+// One warp per row; lane l owns the column pairs (2(l + 32 j), +1), j < NB = Kp / 64, of EVERY row it visits, so the
+// scaler statistics of its columns live in registers and a row costs NB 8-byte loads and NB 4-byte stores per lane, all
+// fully coalesced.  VEC = rows are 8-byte aligned (even stride), else scalar loads.
+template <int NB, bool VEC>
 __global__ void __launch_bounds__(256) normalise_cast_kernel(const float *__restrict__ x, int64_t x_stride, int64_t M,
-                                                              int in_features, int Kp, const float *__restrict__ mean,
+                                                              int in_features, const float *__restrict__ mean,
                                                               const float *__restrict__ denom,
                                                               __nv_bfloat16 *__restrict__ out) {
+    constexpr int Kp = NB * 64;
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    float2 mu[NB], dn[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+        const int c = 2 * (lane + 32 * j);
+        mu[j] = make_float2(c < in_features ? mean[c] : 0.0f, c + 1 < in_features ? mean[c + 1] : 0.0f);
+        dn[j] = make_float2(c < in_features ? denom[c] : 1.0f, c + 1 < in_features ? denom[c + 1] : 1.0f);
+    }
     for (int64_t r = warp; r < M; r += nwarps) {
         const float *xr = x + r * x_stride;
         __nv_bfloat162 *orow = reinterpret_cast<__nv_bfloat162 *>(out + r * Kp);
-        for (int p = lane; p < Kp / 2; p += 32) {
-            const int c = 2 * p;
-            float a = 0.0f, b = 0.0f;
-            if (c < in_features) {
-                a = __fdiv_rn(__fsub_rn(__ldg(xr + c), __ldg(mean + c)), __ldg(denom + c));
-                a = fminf(fmaxf(a, -5.0f), 5.0f);
+        float2 v[NB];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+            const int c = 2 * (lane + 32 * j);
+            v[j] = make_float2(0.0f, 0.0f);
+            if (VEC && c + 1 < in_features) {
+                v[j] = __ldcs(reinterpret_cast<const float2 *>(xr + c));
+            } else {
+                if (c < in_features) v[j].x = __ldcs(xr + c);
+                if (c + 1 < in_features) v[j].y = __ldcs(xr + c + 1);
             }
-            if (c + 1 < in_features) {
-                b = __fdiv_rn(__fsub_rn(__ldg(xr + c + 1), __ldg(mean + c + 1)), __ldg(denom + c + 1));
-                b = fminf(fmaxf(b, -5.0f), 5.0f);
-            }
-            orow[p] = __floats2bfloat162_rn(a, b);
+        }
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+            const int c = 2 * (lane + 32 * j);
+            // clamp((x - mean) / (sqrt(var) + 1e-8), -5, 5); padding columns stay exactly 0
+            float a = fminf(fmaxf(__fdiv_rn(__fsub_rn(v[j].x, mu[j].x), dn[j].x), -5.0f), 5.0f);
+            float b = fminf(fmaxf(__fdiv_rn(__fsub_rn(v[j].y, mu[j].y), dn[j].y), -5.0f), 5.0f);
+            if (c >= in_features) a = 0.0f;
+            if (c + 1 >= in_features) b = 0.0f;
+            orow[lane + 32 * j] = __floats2bfloat162_rn(a, b);
         }
     }
+}
+
+template <bool VEC>
+static int launch_normalise_cast(int nb, int grid, cudaStream_t st, const float *x, int64_t x_stride, int64_t rows, int in_features,
+                                 const float *mean, const float *denom, __nv_bfloat16 *out) {
+#define AMP_CAST_CASE(NBV)                                                                                            \
+    case NBV:                                                                                                         \
+        normalise_cast_kernel<NBV, VEC><<<grid, 256, 0, st>>>(x, x_stride, rows, in_features, mean, denom, out);      \
+        break
+    switch (nb) {
+        AMP_CAST_CASE(1); AMP_CAST_CASE(2); AMP_CAST_CASE(3); AMP_CAST_CASE(4); AMP_CAST_CASE(5); AMP_CAST_CASE(6);
+        AMP_CAST_CASE(7); AMP_CAST_CASE(8); AMP_CAST_CASE(9); AMP_CAST_CASE(10); AMP_CAST_CASE(11); AMP_CAST_CASE(12);
+        AMP_CAST_CASE(13); AMP_CAST_CASE(14); AMP_CAST_CASE(15); AMP_CAST_CASE(16);
+        default: return fail(AMP_EINVAL, "discriminator input wider than 1024 columns is not supported (got %d K-blocks)", nb);
+    }
+#undef AMP_CAST_CASE
+    return AMP_OK;
 }
 
 // fp32 master (rows, cols) -> bf16 (rows, cols_padded), zero padded
@@ -450,9 +535,10 @@ int amp_disc_create(int32_t in_features, int32_t h1, int32_t h2, int64_t max_row
     int rc = make_tmap(&d->tmap_w1, d->W1, h1, d->Kp, d->Kp, BN);
     if (rc == AMP_OK) rc = make_tmap(&d->tmap_w2, d->W2, h2, h1, h1, BN);
     if (rc == AMP_OK) {
-        e = cudaFuncSetAttribute(disc_gemm_kernel<EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        e = cudaFuncSetAttribute(disc_gemm_kernel<EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(EPI_STORE));
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(disc_gemm_kernel<EPI_REWARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+            e = cudaFuncSetAttribute(disc_gemm_kernel<EPI_REWARD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     smem_bytes_for(EPI_REWARD));
         if (e != cudaSuccess) rc = cuda_fail(e, "cudaFuncSetAttribute(disc_gemm_kernel)");
     }
     if (rc != AMP_OK) {
@@ -471,6 +557,8 @@ int amp_disc_destroy(amp_disc_t *d) {
     delete d;
     return AMP_OK;
 }
+
+int64_t amp_disc_chunk_rows(const amp_disc_t *d) { return d ? d->chunk_rows : 0; }
 
 int amp_disc_load(amp_disc_t *d, const float *W1, const float *b1, const float *W2, const float *b2, const float *W3,
                   const float *b3, const double *running_mean, const double *running_variance, void *stream) {
@@ -505,20 +593,27 @@ int amp_disc_style_reward(amp_disc_t *d, const float *x, int64_t x_stride, int64
         const int64_t rows = std::min<int64_t>(d->chunk_rows, M - r0);
         const int m_tiles = (int)((rows + BM - 1) / BM);
         const int grid = std::min(m_tiles, sms);
-        normalise_cast_kernel<<<(int)std::min<int64_t>((rows + 7) / 8, (int64_t)sms * 8), 256, 0, st>>>(
-            x + r0 * x_stride, x_stride, rows, d->in_features, d->Kp, d->mean, d->denom, d->xhat);
+        const float *xc = x + r0 * x_stride;
+        const bool vec = (x_stride % 2 == 0) && ((reinterpret_cast<uintptr_t>(xc) & 7u) == 0);
+        const int cast_grid = (int)std::min<int64_t>((rows + 7) / 8, (int64_t)sms * 8);
+        int rc = vec ? launch_normalise_cast<true>(d->Kp / BK, cast_grid, st, xc, x_stride, rows, d->in_features, d->mean, d->denom, d->xhat)
+                     : launch_normalise_cast<false>(d->Kp / BK, cast_grid, st, xc, x_stride, rows, d->in_features, d->mean, d->denom, d->xhat);
+        if (rc != AMP_OK) return rc;
         AMP_CUDA_TRY(cudaGetLastError());
 
-        CUtensorMap tm_x, tm_h;
-        int rc = make_tmap(&tm_x, d->xhat, rows, d->Kp, d->Kp, BM);
+        CUtensorMap tm_x, tm_h, tm_h_store;
+        rc = make_tmap(&tm_x, d->xhat, rows, d->Kp, d->Kp, BM);
         if (rc != AMP_OK) return rc;
         rc = make_tmap(&tm_h, d->hid, rows, d->h1, d->h1, BM);
+        if (rc != AMP_OK) return rc;
+        rc = make_tmap(&tm_h_store, d->hid, rows, d->h1, d->h1, 32);  // epilogue slabs: 32 rows x 64 columns
         if (rc != AMP_OK) return rc;
 
         EpilogueParams e1{};
         e1.bias = d->b1;
         e1.out = d->hid;
-        disc_gemm_kernel<EPI_STORE><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tm_x, d->tmap_w1, (int)rows, d->h1, d->Kp / BK, e1);
+        disc_gemm_kernel<EPI_STORE><<<grid, NUM_THREADS, smem_bytes_for(EPI_STORE), st>>>(tm_x, d->tmap_w1, tm_h_store, (int)rows,
+                                                                                          d->h1, d->Kp / BK, e1);
         AMP_CUDA_TRY(cudaGetLastError());
 
         EpilogueParams e2{};
@@ -528,7 +623,8 @@ int amp_disc_style_reward(amp_disc_t *d, const float *x, int64_t x_stride, int64
         e2.scale = reward_scale;
         e2.reward = reward + r0;
         e2.logits = logits ? logits + r0 : nullptr;
-        disc_gemm_kernel<EPI_REWARD><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tm_h, d->tmap_w2, (int)rows, d->h2, d->h1 / BK, e2);
+        disc_gemm_kernel<EPI_REWARD><<<grid, NUM_THREADS, smem_bytes_for(EPI_REWARD), st>>>(tm_h, d->tmap_w2, tm_h, (int)rows, d->h2,
+                                                                                            d->h1 / BK, e2);
         AMP_CUDA_TRY(cudaGetLastError());
     }
     return AMP_OK;

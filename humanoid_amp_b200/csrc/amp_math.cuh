@@ -56,10 +56,13 @@ __device__ __forceinline__ float4 slerp(float4 q0, float4 q1, float blend) {
         q1.x = -q1.x; q1.y = -q1.y; q1.z = -q1.z; q1.w = -q1.w;
     }
     c = fabsf(c);
-    const float half = acosf(c);                                      // NaN for c > 1, masked below
+    // acos / sin are evaluated in float64 and rounded once to fp32: that is the correctly rounded value of each fp32 op,
+    // which torch's SLEEF kernels match in all but their <= 1 ulp cases.  libdevice acosf/sinf (up to 2 ulp off) would add
+    // a second, independent error that extrapolation (|blend| up to K-1) amplifies past the 1e-6 absolute bar.
+    const float half = __double2float_rn(acos((double)c));            // NaN for c > 1, masked below
     const float s = __fsqrt_rn(__fsub_rn(1.0f, __fmul_rn(c, c)));     // sqrt(1.0 - c*c), unfused (:262)
-    const float ra = __fdiv_rn(sinf(__fmul_rn(__fsub_rn(1.0f, blend), half)), s);
-    const float rb = __fdiv_rn(sinf(__fmul_rn(blend, half)), s);
+    const float ra = __fdiv_rn(__double2float_rn(sin((double)__fmul_rn(__fsub_rn(1.0f, blend), half))), s);
+    const float rb = __fdiv_rn(__double2float_rn(sin((double)__fmul_rn(blend, half))), s);
     float4 o;
     o.x = __fadd_rn(__fmul_rn(ra, q0.x), __fmul_rn(rb, q1.x));
     o.y = __fadd_rn(__fmul_rn(ra, q0.y), __fmul_rn(rb, q1.y));

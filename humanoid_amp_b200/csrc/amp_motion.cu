@@ -170,45 +170,47 @@ __global__ void slerp_kernel(const float4 *__restrict__ q0, const float4 *__rest
 // Only __syncwarp is needed: warps never share data.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kCollectWarps = 8;
-constexpr int kFramesPerTile = 64;
+constexpr int kMaxHistory = 64;      // largest num_amp_observations the fused kernel accepts
+constexpr int kTileFrames = 32;      // frames per warp tile (one phase-1 pass) when K <= 32
 
+// 16 floats per frame; indices into the record viewed as float[16]
 struct __align__(16) FrameMeta {
-    int32_t off0, off1;  // float offsets of the two packed rows
-    float b, omb;        // blend, 1 - blend
-    float tn[6];         // tangent, normal of the slerped root rotation
-    float root[3];       // interpolated root position (x, y, z)
-    float _pad;
-    int64_t out;         // float offset of this frame's A columns in the destination
+    int32_t off0, off1;  // [0] [1]   float offsets of the two packed rows
+    float b, omb;        // [2] [3]   blend, 1 - blend
+    float tn[6];         // [4..9]    tangent, normal of the slerped root rotation
+    float root[3];       // [10..12]  interpolated root position (x, y, z)
+    float zero;          // [13]      0.0f: the "nothing to subtract" slot of the branch-free column fix-up
+    int64_t out;         // [14] [15] float offset of this frame's A columns in the destination
 };
 static_assert(sizeof(FrameMeta) == 64, "FrameMeta must stay one 64-byte record");
 
 template <int NSLOT>
-__global__ void __launch_bounds__(kCollectWarps * 32)
+__global__ void __launch_bounds__(kCollectWarps * 32, 4)
 collect_reference_kernel(LibView v, const double *__restrict__ cur_times, const int64_t *__restrict__ ids, int64_t n,
-                         int K, int tile_samples, float *__restrict__ out, int64_t row_stride, int64_t capacity,
-                         int64_t start_row, const int64_t *__restrict__ row_index, int64_t num_tiles) {
-    __shared__ FrameMeta meta_all[kCollectWarps][kFramesPerTile];
+                         int K, int tile_samples, int tile_cap, float *__restrict__ out, int64_t row_stride,
+                         int64_t capacity, int64_t start_row, const int64_t *__restrict__ row_index, int64_t num_tiles) {
+    extern __shared__ __align__(16) unsigned char collect_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    FrameMeta *meta = meta_all[warp];
+    FrameMeta *meta = reinterpret_cast<FrameMeta *>(collect_smem) + warp * tile_cap;
     const int D2 = 2 * v.obs_dofs, A = v.obs_width, R = v.row_floats;
     const float *__restrict__ packed = v.packed;
 
-    // frame-invariant classification of this lane's columns: -1 inactive, 0 plain lerp, 1 tangent/normal, 2 key body
-    int kind[NSLOT], aux[NSLOT];
+    // Frame-invariant classification of this lane's columns (column c = lane + 32*s):
+    //   plain columns         value = lerp
+    //   key-body columns      value = lerp - root[axis]          -> sub_idx points at root[axis], else at the zero slot
+    //   tangent/normal        value = tn[i]                      -> take_tn selects meta[tn_idx] instead
+    // so the per-frame loop is branch-free: lerp, one subtraction of a shared-memory operand, one select.
+    int sub_idx[NSLOT], tn_idx[NSLOT];
+    bool take_tn[NSLOT], active[NSLOT], special[NSLOT];
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) {
         const int c = lane + 32 * s;
-        kind[s] = 0;
-        aux[s] = 0;
-        if (c >= A) {
-            kind[s] = -1;
-        } else if (c > D2 && c < D2 + 7) {
-            kind[s] = 1;
-            aux[s] = c - (D2 + 1);
-        } else if (c >= D2 + 13) {
-            kind[s] = 2;
-            aux[s] = (c - (D2 + 13)) % 3;
-        }
+        active[s] = c < A;
+        take_tn[s] = c > D2 && c < D2 + 7;
+        tn_idx[s] = take_tn[s] ? 4 + c - (D2 + 1) : 13;
+        sub_idx[s] = (c >= D2 + 13 && c < A) ? 10 + (c - (D2 + 13)) % 3 : 13;
+        // warp-uniform: does any lane of this slot need the fix-up at all?
+        special[s] = __any_sync(0xffffffffu, take_tn[s] || sub_idx[s] != 13);
     }
 
     for (int64_t tile = blockIdx.x * (int64_t)kCollectWarps + warp; tile < num_tiles;
@@ -237,7 +239,7 @@ collect_reference_kernel(LibView v, const double *__restrict__ cur_times, const 
             m.root[0] = lerp_w(omb, b, __ldg(r0 + D2 + 5), __ldg(r1 + D2 + 5));
             m.root[1] = lerp_w(omb, b, __ldg(r0 + D2 + 6), __ldg(r1 + D2 + 6));
             m.root[2] = lerp_w(omb, b, __ldg(r0 + D2), __ldg(r1 + D2));
-            m._pad = 0.0f;
+            m.zero = 0.0f;
             int64_t row;
             if (row_index) {
                 row = row_index[sample];
@@ -251,25 +253,32 @@ collect_reference_kernel(LibView v, const double *__restrict__ cur_times, const 
         __syncwarp();
 
         // ---- phase 2: stream the rows out ----------------------------------------------------------------------
+        // Lane l reads packed[off + l + 32 s] unconditionally (the table is padded so the last row may be over-read) and
+        // only the store is predicated.
 #pragma unroll 2
         for (int f = 0; f < nf; ++f) {
-            const int4 head = *reinterpret_cast<const int4 *>(&meta[f]);  // off0, off1, b, omb in one broadcast read
+            const float *mf = reinterpret_cast<const float *>(&meta[f]);
+            const int4 head = *reinterpret_cast<const int4 *>(mf);  // off0, off1, b, omb in one broadcast read
             const float b = __int_as_float(head.z), omb = __int_as_float(head.w);
-            const float *r0 = packed + head.x, *r1 = packed + head.y;
-            float *o = out + meta[f].out;
+            const float *p0 = packed + head.x + lane, *p1 = packed + head.y + lane;
+            float *o = out + meta[f].out + lane;
+            float a0[NSLOT], a1[NSLOT];
 #pragma unroll
             for (int s = 0; s < NSLOT; ++s) {
-                if (kind[s] < 0) continue;
-                const int c = lane + 32 * s;
-                float val;
-                if (kind[s] == 1) {
-                    val = meta[f].tn[aux[s]];
-                } else {
-                    val = lerp_w(omb, b, __ldg(r0 + c), __ldg(r1 + c));
-                    // key body offset: (interpolated key position) - (interpolated root position), g1_amp_env.py:552
-                    if (kind[s] == 2) val = __fsub_rn(val, meta[f].root[aux[s]]);
+                a0[s] = __ldg(p0 + 32 * s);
+                a1[s] = __ldg(p1 + 32 * s);
+            }
+#pragma unroll
+            for (int s = 0; s < NSLOT; ++s) {
+                float val = lerp_w(omb, b, a0[s], a1[s]);
+                if (special[s]) {  // warp-uniform
+                    // key body offset: (interpolated key position) - (interpolated root position), g1_amp_env.py:552;
+                    // x - 0.0f == x bit for bit for every other column
+                    val = __fsub_rn(val, mf[sub_idx[s]]);
+                    const float tnv = mf[tn_idx[s]];
+                    val = take_tn[s] ? tnv : val;
                 }
-                __stcs(o + c, val);
+                if (active[s]) __stcs(o + 32 * s, val);
             }
         }
         __syncwarp();
@@ -485,7 +494,8 @@ int amp_lib_create(const amp_lib_desc_t *d, void *stream, amp_lib_t **out) {
         int32_t *dof_idx = nullptr;
         if ((rc = upload(lib, d->dof_indexes, (size_t)v.obs_dofs, st, &dof_idx))) return bail(rc);
         void *packed = nullptr;
-        cudaError_t e = cudaMalloc(&packed, (size_t)v.num_frames * v.row_floats * sizeof(float));
+        // + 1 KiB: the fused kernel reads up to 32*NSLOT floats from a row start without a bounds check
+        cudaError_t e = cudaMalloc(&packed, (size_t)v.num_frames * v.row_floats * sizeof(float) + 1024);
         if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc(packed rows)"));
         lib->owned[lib->n_owned++] = packed;
         v.packed = static_cast<float *>(packed);
@@ -571,8 +581,8 @@ int amp_collect_reference(amp_lib_t *lib, const double *cur_times, const int64_t
                           void *stream) {
     AMP_REQUIRE(lib && n >= 0, "amp_collect_reference: bad handle or negative size");
     AMP_REQUIRE(lib->v.obs_width > 0, "amp_collect_reference: library was created without the env selection");
-    AMP_REQUIRE(K >= 1 && K <= kFramesPerTile, "amp_collect_reference: num_amp_observations %d outside [1, %d]", K,
-                kFramesPerTile);
+    AMP_REQUIRE(K >= 1 && K <= kMaxHistory, "amp_collect_reference: num_amp_observations %d outside [1, %d]", K,
+                kMaxHistory);
     if (n == 0) return AMP_OK;
     const int A = lib->v.obs_width;
     AMP_REQUIRE(cur_times && out, "amp_collect_reference: NULL buffer");
@@ -580,18 +590,21 @@ int amp_collect_reference(amp_lib_t *lib, const double *cur_times, const int64_t
                 K * A);
     AMP_REQUIRE(start_row >= 0, "amp_collect_reference: negative start_row");
 
-    // tile = consecutive samples of one warp; shrink it when the batch is small so the work still covers the chip
-    const int max_tile = std::max(1, kFramesPerTile / K);
+    // tile = consecutive samples of one warp (one phase-1 pass of 32 frames; a whole sample when K > 32); shrink it when
+    // the batch is small so the work still covers the chip
+    const int tile_cap = K <= kTileFrames ? kTileFrames : kMaxHistory;
+    const int max_tile = std::max(1, tile_cap / K);
     const int64_t target_warps = (int64_t)sm_count() * kCollectWarps * 4;
     const int tile_samples = (int)std::min<int64_t>(max_tile, std::max<int64_t>(1, (n + target_warps - 1) / target_warps));
     const int64_t tiles = (n + tile_samples - 1) / tile_samples;
     const int grid = grid_for(tiles, kCollectWarps, 4);
     const int nslot = (A + 31) / 32;
+    const size_t smem = (size_t)kCollectWarps * tile_cap * sizeof(FrameMeta);
     cudaStream_t st = as_stream(stream);
 #define AMP_LAUNCH_COLLECT(NS)                                                                                        \
-    collect_reference_kernel<NS><<<grid, kCollectWarps * 32, 0, st>>>(lib->v, cur_times, ids, n, K, tile_samples, out, \
-                                                                      row_stride, capacity_rows, start_row, row_index,  \
-                                                                      tiles)
+    collect_reference_kernel<NS><<<grid, kCollectWarps * 32, smem, st>>>(lib->v, cur_times, ids, n, K, tile_samples,  \
+                                                                         tile_cap, out, row_stride, capacity_rows,     \
+                                                                         start_row, row_index, tiles)
     switch (nslot) {
         case 1: AMP_LAUNCH_COLLECT(1); break;
         case 2: AMP_LAUNCH_COLLECT(2); break;

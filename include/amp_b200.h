@@ -152,6 +152,8 @@ AMP_API int amp_obs_step(const float *joint_pos, const float *joint_vel, const f
  * h1, h2 must be multiples of 128 (reference: 1024, 512); in_features any value >= 1 (padded to 64 internally). */
 AMP_API int amp_disc_create(int32_t in_features, int32_t h1, int32_t h2, int64_t max_rows, void *stream, amp_disc_t **out);
 AMP_API int amp_disc_destroy(amp_disc_t *d);
+/* Rows processed per internal chunk (three kernel launches per chunk); 0 for a NULL handle. */
+AMP_API int64_t amp_disc_chunk_rows(const amp_disc_t *d);
 /* Refresh the staged bf16 weights / fp32 biases / scaler statistics from the fp32 masters the trainer owns
  * (device pointers; W row-major (out,in) as torch.nn.Linear stores them; mean/var are the scaler's float64 buffers). */
 AMP_API int amp_disc_load(amp_disc_t *d, const float *W1, const float *b1, const float *W2, const float *b2, const float *W3,

@@ -1,0 +1,120 @@
+"""Discriminator forward + style reward on tcgen05 (``-m gpu``) against the fp32 oracle.
+
+Stated bf16 tolerance (SURVEY.md sections 7.2 / 8a row 14; layers 1-2 use bf16 operands with fp32 accumulation, the
+last layer and the reward are fp32):
+
+    |logit - logit_fp32|   <= 1e-2 * max(1, max|logit|)
+    |reward - reward_fp32| <= 2e-2 * max(1, max|logit|)       (reward_scale = 2)
+
+Against the oracle run with the SAME bf16 rounding of the operands the kernel must agree much more tightly (only the
+fp32 accumulation order differs): |dlogit| <= 2e-3 * max(1, max|logit|).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def build(in_features, gain, seed=42, max_rows=65536):
+    import humanoid_amp_b200 as amp
+    from humanoid_amp_b200.synthetic import skrl_style_discriminator_params
+    from oracle import OracleDiscriminator
+
+    W, b = skrl_style_discriminator_params(in_features, seed=seed, logit_gain=gain)
+    ora = OracleDiscriminator(in_features, weights=W, biases=b)
+    g = torch.Generator().manual_seed(seed + 1)
+    # realistic statistics: a few batches of "observations" with per-column scale / offset
+    scale = torch.rand(in_features, generator=g) * 3 + 0.05
+    shift = torch.randn(in_features, generator=g)
+    for _ in range(3):
+        ora.update_statistics(torch.randn(512, in_features, generator=g) * scale + shift)
+    disc = amp.AmpDiscriminator(in_features, device="cuda:0", max_rows=max_rows)
+    disc.load(W, b, ora.running_mean, ora.running_variance)
+
+    def inputs(M, s):
+        gg = torch.Generator().manual_seed(s)
+        x = torch.randn(M, in_features, generator=gg) * scale + shift
+        x[::13] *= 4.0  # some rows hit the +-5 clamp of the scaler
+        return x
+
+    return disc, ora, inputs
+
+
+@pytest.mark.parametrize("in_features", [166, 830, 162])
+@pytest.mark.parametrize("gain", [1.0, 30.0])
+def test_style_reward_vs_oracle(in_features, gain):
+    disc, ora, inputs = build(in_features, gain)
+    for M in (1, 127, 128, 129, 4096):
+        x = inputs(M, M)
+        reward, logits = disc.style_reward(x.cuda(), return_logits=True)
+        assert reward.shape == (M, 1) and logits.shape == (M, 1)
+        want_logits = ora.logits(x)
+        want_reward = ora.style_reward(x)
+        span = max(1.0, float(want_logits.abs().max()))
+        dl = (logits.cpu() - want_logits).abs().max().item()
+        dr = (reward.cpu() - want_reward).abs().max().item()
+        assert dl <= 1e-2 * span, f"M={M}: |dlogit| {dl:.3e} > {1e-2 * span:.3e}"
+        assert dr <= 2e-2 * span, f"M={M}: |dreward| {dr:.3e}"
+        emu = ora.logits(x, emulate_bf16=True)
+        de = (logits.cpu() - emu).abs().max().item()
+        assert de <= 2e-3 * span, f"M={M}: vs bf16-emulated oracle {de:.3e}"
+        # the reward is exactly the reward expression applied to the kernel's own logits
+        from humanoid_amp_b200 import style_reward_from_logits
+
+        assert torch.equal(style_reward_from_logits(logits, 2.0), reward)
+
+
+def test_reward_expression_and_clamp():
+    from humanoid_amp_b200 import style_reward_from_logits
+    from oracle import style_reward_from_logits as ref
+
+    d = torch.cat([torch.linspace(-30, 30, 4001), torch.tensor([9.2102, 9.2104, 50.0, -50.0, 0.0])])
+    got = style_reward_from_logits(d.cuda(), 2.0).cpu()
+    want = ref(d, 2.0)
+    # away from the clamp the two fp32 evaluations agree closely; inside 6 < d < 9.21 the reference's own
+    # 1 - 1/(1+exp(-d)) cancels, so a 1-ulp difference in exp shows up as ~1e-3 relative in p
+    far = d < 6
+    assert torch.allclose(got[far], want[far], rtol=1e-5, atol=1e-6)
+    assert (got - want).abs().max() <= 5e-3
+    assert got[d > 9.3].eq(got[d > 9.3][0]).all() and abs(got[-3].item() - 2 * np.log(1e4)) < 1e-4  # clamp at 1e-4
+    assert abs(got[-1].item() - 2 * np.log(2.0)) < 1e-6
+
+
+def test_multi_chunk_rows_and_row_independence():
+    """More rows than one L2-resident chunk (2 x 148 x 128 = 37888), with a strided input view (a memory slice)."""
+    disc, ora, inputs = build(166, 5.0, max_rows=100_000)
+    M = 37888 + 128 + 5
+    x = inputs(M, 3).cuda()
+    wide = torch.zeros(M, 200, device="cuda")
+    wide[:, :166] = x
+    r_all, l_all = disc.style_reward(x, return_logits=True)
+    r_view = disc.style_reward(wide[:, :166])  # row stride 200
+    assert torch.equal(r_all, r_view)
+    # rows are independent: any sub-batch gives the same bits
+    part = disc.style_reward(x[1000:1300])
+    assert torch.equal(part, r_all[1000:1300])
+    idx = torch.arange(0, M, 97)
+    want = ora.logits(x[idx].cpu())
+    span = max(1.0, float(want.abs().max()))
+    assert (l_all[idx].cpu() - want).abs().max() <= 1e-2 * span
+    # leading dims are preserved: memory["amp_states"] is (rollouts, envs, K*A)
+    r3 = disc.style_reward(x[: 16 * 64].view(16, 64, 166))
+    assert r3.shape == (16, 64, 1) and torch.equal(r3.view(-1, 1), r_all[: 16 * 64])
+    assert disc.style_reward(x[:0]).shape == (0, 1)
+
+
+def test_weight_refresh_changes_result():
+    disc, ora, inputs = build(162, 1.0)
+    x = inputs(256, 1).cuda()
+    before = disc.style_reward(x)
+    W = [w * 1.5 for w in ora.weights]
+    disc.load(W, ora.biases, ora.running_mean, ora.running_variance)
+    after = disc.style_reward(x)
+    assert not torch.equal(before, after)
+    ora.weights = W
+    want = ora.style_reward(x.cpu())
+    assert (after.cpu() - want).abs().max() <= 2e-2 * max(1.0, float(ora.logits(x.cpu()).abs().max()))
