@@ -161,17 +161,26 @@ __global__ void slerp_kernel(const float4 *__restrict__ q0, const float4 *__rest
 // ------------------------------------------------------------------------------------------------------------------
 // amp_collect_reference: fused history times -> frame/blend -> gather + lerp -> root slerp -> compute_obs -> stacked row.
 //
-// A warp owns a tile of consecutive samples (tile_samples * K <= kFramesPerTile frames).
+// A warp owns a tile of consecutive samples (tile_samples * K <= tile_cap frames).
 //   phase 1  one lane per frame: float64 index math, root quaternion slerp, tangent/normal, root position, and the
 //            destination offset; staged as a 64-byte FrameMeta record in the warp's slice of shared memory;
 //   phase 2  the warp walks its frames; lane l produces columns l, l+32, l+64, ... so the two packed-row reads and the
 //            store are contiguous 128-byte runs.  Which lanes hold the tangent/normal and key-body columns does not
-//            depend on the frame, so that classification is hoisted out of the loop.
-// Only __syncwarp is needed: warps never share data.
+//            depend on the frame, so that classification is hoisted out of the loop and the loop body is branch-free.
+// Only __syncwarp is needed inside the loop: warps never share data.
+//
+// Two variants (template SMEM_TABLE):
+//   true   the whole packed table (G1_walk 134 KB, G1_dance 202 KB) is copied once per CTA into shared memory and one
+//          persistent CTA per SM (up to 32 warps) streams rows out of it: the gathers become conflict-free LDS with
+//          32-bit addresses and L1/L2 only carry the output stream.  ncu on the global-table version showed the L1 data
+//          pipe at 84 % (two tag wavefronts per misaligned 128-byte row read) -- that is the limiter this removes.
+//   false  table stays in global memory (L1/L2 resident): for pooled libraries that do not fit in 227 KB and for
+//          small batches where copying the table per CTA would cost more than the gathers.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kCollectWarps = 8;
+constexpr int kCollectWarps = 8;     // warps per CTA of the global-table variant
 constexpr int kMaxHistory = 64;      // largest num_amp_observations the fused kernel accepts
 constexpr int kTileFrames = 32;      // frames per warp tile (one phase-1 pass) when K <= 32
+constexpr int kMaxSmemOptin = 232448;  // 227 KiB per CTA on sm_100
 
 // 16 floats per frame; indices into the record viewed as float[16]
 struct __align__(16) FrameMeta {
@@ -179,42 +188,60 @@ struct __align__(16) FrameMeta {
     float b, omb;        // [2] [3]   blend, 1 - blend
     float tn[6];         // [4..9]    tangent, normal of the slerped root rotation
     float root[3];       // [10..12]  interpolated root position (x, y, z)
-    float zero;          // [13]      0.0f: the "nothing to subtract" slot of the branch-free column fix-up
+    float zero;          // [13]      0.0f: the "nothing to subtract" operand of the branch-free column fix-up
     int64_t out;         // [14] [15] float offset of this frame's A columns in the destination
 };
 static_assert(sizeof(FrameMeta) == 64, "FrameMeta must stay one 64-byte record");
 
-template <int NSLOT>
-__global__ void __launch_bounds__(kCollectWarps * 32, 4)
+template <bool SMEM_TABLE>
+__device__ __forceinline__ float table_ld(const float *p) {
+    if constexpr (SMEM_TABLE) return *p;  // generic load from a shared-memory address: LDS
+    else return __ldg(p);
+}
+
+template <int NSLOT, bool SMEM_TABLE>
+__global__ void __launch_bounds__(SMEM_TABLE ? 1024 : kCollectWarps * 32, SMEM_TABLE ? 1 : 4)
 collect_reference_kernel(LibView v, const double *__restrict__ cur_times, const int64_t *__restrict__ ids, int64_t n,
                          int K, int tile_samples, int tile_cap, float *__restrict__ out, int64_t row_stride,
                          int64_t capacity, int64_t start_row, const int64_t *__restrict__ row_index, int64_t num_tiles) {
     extern __shared__ __align__(16) unsigned char collect_smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    FrameMeta *meta = reinterpret_cast<FrameMeta *>(collect_smem) + warp * tile_cap;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
     const int D2 = 2 * v.obs_dofs, A = v.obs_width, R = v.row_floats;
-    const float *__restrict__ packed = v.packed;
+
+    const float *tab = v.packed;
+    unsigned char *meta_base = collect_smem;
+    if constexpr (SMEM_TABLE) {
+        const int quads = (int)(v.num_frames * R / 4);
+        float4 *dst = reinterpret_cast<float4 *>(collect_smem);
+        const float4 *src = reinterpret_cast<const float4 *>(v.packed);
+        for (int i = threadIdx.x; i < quads; i += blockDim.x) dst[i] = __ldg(src + i);
+        tab = reinterpret_cast<const float *>(collect_smem);
+        // the last row may be over-read by 32*NSLOT - R floats (values discarded): keep that slack inside the allocation
+        meta_base = collect_smem + (size_t)quads * 16 + 512;
+        __syncthreads();
+    }
+    FrameMeta *meta = reinterpret_cast<FrameMeta *>(meta_base) + warp * tile_cap;
 
     // Frame-invariant classification of this lane's columns (column c = lane + 32*s):
-    //   plain columns         value = lerp
-    //   key-body columns      value = lerp - root[axis]          -> sub_idx points at root[axis], else at the zero slot
-    //   tangent/normal        value = tn[i]                      -> take_tn selects meta[tn_idx] instead
-    // so the per-frame loop is branch-free: lerp, one subtraction of a shared-memory operand, one select.
-    int sub_idx[NSLOT], tn_idx[NSLOT];
-    bool take_tn[NSLOT], active[NSLOT], special[NSLOT];
+    //   plain columns      value = lerp - 0.0f                 (x - 0.0f == x bit for bit)
+    //   key-body columns   value = lerp - root[axis]           (g1_amp_env.py:552, interpolated key minus interpolated root)
+    //   tangent/normal     value = tn[i]
+    // One shared-memory operand w = meta[fix_idx] per special slot serves all three; tn_mask selects w itself.
+    int fix_idx[NSLOT];
+    uint32_t tn_mask[NSLOT];
+    bool special[NSLOT];
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) {
         const int c = lane + 32 * s;
-        active[s] = c < A;
-        take_tn[s] = c > D2 && c < D2 + 7;
-        tn_idx[s] = take_tn[s] ? 4 + c - (D2 + 1) : 13;
-        sub_idx[s] = (c >= D2 + 13 && c < A) ? 10 + (c - (D2 + 13)) % 3 : 13;
-        // warp-uniform: does any lane of this slot need the fix-up at all?
-        special[s] = __any_sync(0xffffffffu, take_tn[s] || sub_idx[s] != 13);
+        const bool is_tn = c > D2 && c < D2 + 7;
+        const bool is_key = c >= D2 + 13 && c < A;
+        fix_idx[s] = is_tn ? 4 + c - (D2 + 1) : (is_key ? 10 + (c - (D2 + 13)) % 3 : 13);
+        tn_mask[s] = is_tn ? 0xffffffffu : 0u;
+        special[s] = __any_sync(0xffffffffu, is_tn || is_key);  // warp-uniform: does this slot need the fix-up at all?
     }
+    const bool last_active = lane + 32 * (NSLOT - 1) < A;  // only the last slot can have lanes past the row end
 
-    for (int64_t tile = blockIdx.x * (int64_t)kCollectWarps + warp; tile < num_tiles;
-         tile += (int64_t)gridDim.x * kCollectWarps) {
+    for (int64_t tile = blockIdx.x * (int64_t)warps + warp; tile < num_tiles; tile += (int64_t)gridDim.x * warps) {
         const int64_t s0 = tile * tile_samples;
         const int ns = (int)min((int64_t)tile_samples, n - s0);
         const int nf = ns * K;
@@ -232,13 +259,15 @@ collect_reference_kernel(LibView v, const double *__restrict__ cur_times, const 
             m.off1 = (int32_t)(fb.i1 * R);
             m.b = b;
             m.omb = omb;
-            const float *r0 = packed + m.off0, *r1 = packed + m.off1;
-            const float4 q0 = make_float4(__ldg(r0 + D2 + 1), __ldg(r0 + D2 + 2), __ldg(r0 + D2 + 3), __ldg(r0 + D2 + 4));
-            const float4 q1 = make_float4(__ldg(r1 + D2 + 1), __ldg(r1 + D2 + 2), __ldg(r1 + D2 + 3), __ldg(r1 + D2 + 4));
+            const float *r0 = tab + m.off0, *r1 = tab + m.off1;
+            const float4 q0 = make_float4(table_ld<SMEM_TABLE>(r0 + D2 + 1), table_ld<SMEM_TABLE>(r0 + D2 + 2),
+                                          table_ld<SMEM_TABLE>(r0 + D2 + 3), table_ld<SMEM_TABLE>(r0 + D2 + 4));
+            const float4 q1 = make_float4(table_ld<SMEM_TABLE>(r1 + D2 + 1), table_ld<SMEM_TABLE>(r1 + D2 + 2),
+                                          table_ld<SMEM_TABLE>(r1 + D2 + 3), table_ld<SMEM_TABLE>(r1 + D2 + 4));
             tangent_normal(slerp(q0, q1, b), m.tn);
-            m.root[0] = lerp_w(omb, b, __ldg(r0 + D2 + 5), __ldg(r1 + D2 + 5));
-            m.root[1] = lerp_w(omb, b, __ldg(r0 + D2 + 6), __ldg(r1 + D2 + 6));
-            m.root[2] = lerp_w(omb, b, __ldg(r0 + D2), __ldg(r1 + D2));
+            m.root[0] = lerp_w(omb, b, table_ld<SMEM_TABLE>(r0 + D2 + 5), table_ld<SMEM_TABLE>(r1 + D2 + 5));
+            m.root[1] = lerp_w(omb, b, table_ld<SMEM_TABLE>(r0 + D2 + 6), table_ld<SMEM_TABLE>(r1 + D2 + 6));
+            m.root[2] = lerp_w(omb, b, table_ld<SMEM_TABLE>(r0 + D2), table_ld<SMEM_TABLE>(r1 + D2));
             m.zero = 0.0f;
             int64_t row;
             if (row_index) {
@@ -253,32 +282,30 @@ collect_reference_kernel(LibView v, const double *__restrict__ cur_times, const 
         __syncwarp();
 
         // ---- phase 2: stream the rows out ----------------------------------------------------------------------
-        // Lane l reads packed[off + l + 32 s] unconditionally (the table is padded so the last row may be over-read) and
-        // only the store is predicated.
+        // Lane l reads table[off + l + 32 s] unconditionally (the allocation is padded so the last row may be
+        // over-read) and only the store of the last slot is predicated.
 #pragma unroll 2
         for (int f = 0; f < nf; ++f) {
             const float *mf = reinterpret_cast<const float *>(&meta[f]);
             const int4 head = *reinterpret_cast<const int4 *>(mf);  // off0, off1, b, omb in one broadcast read
             const float b = __int_as_float(head.z), omb = __int_as_float(head.w);
-            const float *p0 = packed + head.x + lane, *p1 = packed + head.y + lane;
-            float *o = out + meta[f].out + lane;
+            const float *p0 = tab + head.x + lane, *p1 = tab + head.y + lane;
+            float *o = out + *reinterpret_cast<const int64_t *>(mf + 14) + lane;
             float a0[NSLOT], a1[NSLOT];
 #pragma unroll
             for (int s = 0; s < NSLOT; ++s) {
-                a0[s] = __ldg(p0 + 32 * s);
-                a1[s] = __ldg(p1 + 32 * s);
+                a0[s] = table_ld<SMEM_TABLE>(p0 + 32 * s);
+                a1[s] = table_ld<SMEM_TABLE>(p1 + 32 * s);
             }
 #pragma unroll
             for (int s = 0; s < NSLOT; ++s) {
                 float val = lerp_w(omb, b, a0[s], a1[s]);
-                if (special[s]) {  // warp-uniform
-                    // key body offset: (interpolated key position) - (interpolated root position), g1_amp_env.py:552;
-                    // x - 0.0f == x bit for bit for every other column
-                    val = __fsub_rn(val, mf[sub_idx[s]]);
-                    const float tnv = mf[tn_idx[s]];
-                    val = take_tn[s] ? tnv : val;
+                if (special[s]) {  // warp-uniform branch
+                    const float w = mf[fix_idx[s]];
+                    const float d = __fsub_rn(val, w);
+                    val = __uint_as_float((__float_as_uint(w) & tn_mask[s]) | (__float_as_uint(d) & ~tn_mask[s]));
                 }
-                if (active[s]) __stcs(o + 32 * s, val);
+                if (s < NSLOT - 1 || last_active) __stcs(o + 32 * s, val);
             }
         }
         __syncwarp();
@@ -590,21 +617,58 @@ int amp_collect_reference(amp_lib_t *lib, const double *cur_times, const int64_t
                 K * A);
     AMP_REQUIRE(start_row >= 0, "amp_collect_reference: negative start_row");
 
-    // tile = consecutive samples of one warp (one phase-1 pass of 32 frames; a whole sample when K > 32); shrink it when
-    // the batch is small so the work still covers the chip
+    // tile = consecutive samples of one warp (one phase-1 pass of 32 frames; a whole sample when K > 32)
     const int tile_cap = K <= kTileFrames ? kTileFrames : kMaxHistory;
     const int max_tile = std::max(1, tile_cap / K);
-    const int64_t target_warps = (int64_t)sm_count() * kCollectWarps * 4;
-    const int tile_samples = (int)std::min<int64_t>(max_tile, std::max<int64_t>(1, (n + target_warps - 1) / target_warps));
-    const int64_t tiles = (n + tile_samples - 1) / tile_samples;
-    const int grid = grid_for(tiles, kCollectWarps, 4);
     const int nslot = (A + 31) / 32;
-    const size_t smem = (size_t)kCollectWarps * tile_cap * sizeof(FrameMeta);
+    const int sms = sm_count();
     cudaStream_t st = as_stream(stream);
-#define AMP_LAUNCH_COLLECT(NS)                                                                                        \
-    collect_reference_kernel<NS><<<grid, kCollectWarps * 32, smem, st>>>(lib->v, cur_times, ids, n, K, tile_samples,  \
-                                                                         tile_cap, out, row_stride, capacity_rows,     \
-                                                                         start_row, row_index, tiles)
+
+    // shared-memory-table variant: table + >= 8 warps of frame records must fit in 227 KiB, and every warp of the
+    // persistent grid should get at least two full tiles (otherwise copying the table per CTA is not worth it)
+    const size_t table_bytes = (size_t)lib->v.num_frames * lib->v.row_floats * sizeof(float) + 512;
+    const size_t per_warp = (size_t)tile_cap * sizeof(FrameMeta);
+    int smem_warps = table_bytes + 8 * per_warp <= (size_t)kMaxSmemOptin ? (int)std::min<size_t>(32, (kMaxSmemOptin - table_bytes) / per_warp) : 0;
+    const int64_t full_tiles = (n + max_tile - 1) / max_tile;
+    const bool use_smem = smem_warps >= 8 && full_tiles >= (int64_t)2 * sms * smem_warps;
+
+    int tile_samples, grid, threads;
+    int64_t tiles;
+    size_t smem;
+    if (use_smem) {
+        tile_samples = max_tile;
+        tiles = full_tiles;
+        threads = smem_warps * 32;
+        grid = (int)std::min<int64_t>(sms, (tiles + smem_warps - 1) / smem_warps);
+        smem = table_bytes + (size_t)smem_warps * per_warp;
+    } else {
+        // shrink the tile when the batch is small so the work still covers the chip
+        const int64_t target_warps = (int64_t)sms * kCollectWarps * 4;
+        tile_samples = (int)std::min<int64_t>(max_tile, std::max<int64_t>(1, (n + target_warps - 1) / target_warps));
+        tiles = (n + tile_samples - 1) / tile_samples;
+        threads = kCollectWarps * 32;
+        grid = grid_for(tiles, kCollectWarps, 4);
+        smem = (size_t)kCollectWarps * per_warp;
+    }
+#define AMP_LAUNCH_COLLECT(NS)                                                                                          \
+    do {                                                                                                                \
+        if (use_smem) {                                                                                                 \
+            static bool attr_set[64] = {false};                                                                         \
+            if (!attr_set[lib->device & 63]) {                                                                          \
+                AMP_CUDA_TRY(cudaFuncSetAttribute(collect_reference_kernel<NS, true>,                                   \
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));         \
+                attr_set[lib->device & 63] = true;                                                                      \
+            }                                                                                                           \
+            collect_reference_kernel<NS, true><<<grid, threads, smem, st>>>(lib->v, cur_times, ids, n, K, tile_samples, \
+                                                                            tile_cap, out, row_stride, capacity_rows,   \
+                                                                            start_row, row_index, tiles);               \
+        } else {                                                                                                        \
+            collect_reference_kernel<NS, false><<<grid, threads, smem, st>>>(lib->v, cur_times, ids, n, K,              \
+                                                                             tile_samples, tile_cap, out, row_stride,   \
+                                                                             capacity_rows, start_row, row_index,       \
+                                                                             tiles);                                    \
+        }                                                                                                               \
+    } while (0)
     switch (nslot) {
         case 1: AMP_LAUNCH_COLLECT(1); break;
         case 2: AMP_LAUNCH_COLLECT(2); break;
