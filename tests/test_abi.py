@@ -62,7 +62,7 @@ def test_binary_carries_sm100a_tensor_core_and_tma_code():
         pytest.skip("cuobjdump not available")
     sass = subprocess.run([exe, "-sass", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
     assert "sm_100a" in sass
-    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG", "UTCBAR"):
+    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG", "UTMASTG", "UTCBAR"):
         assert mnemonic in sass, f"{mnemonic} not found in SASS"
 
 
