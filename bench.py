@@ -260,7 +260,7 @@ def run_ours(args, spec, rank, world, local_rank):
             dist.all_reduce(grads)
             grads.div_(world)
 
-    launches_per_step = 1 + (1 if state is not None else 0) + 3 * ((reward_rows + disc.chunk_rows - 1) // disc.chunk_rows)
+    launches_per_step = 1 + (1 if state is not None else 0) + 2 * ((reward_rows + disc.chunk_rows - 1) // disc.chunk_rows)
 
     def sync_all():
         if distributed:

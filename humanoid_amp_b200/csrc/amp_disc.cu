@@ -10,17 +10,10 @@
 //   logit  = h2 . w3 + b3                 fp32, folded into the TMEM read-out of layer 2 (one thread owns one row)
 //   reward = -log(max(1 - 1/(1+exp(-logit)), 1e-4)) * scale
 //
-// Structure (one persistent CTA per SM, 192 threads, warp-specialised):
-//   warp 0      TMA producer: cp.async.bulk.tensor 2D loads of the A (activations) and B (weights) K-blocks into a
-//               4-stage 128B-swizzled shared-memory ring, completion on mbarriers
-//   warp 1      TMEM allocator + MMA issuer: one elected lane issues tcgen05.mma (M=128, N=256, K=16) and commits to the
-//               ring's "empty" barriers and to the accumulator "full" barrier
-//   warps 2..5  epilogue: tcgen05.ld of the fp32 accumulator (each warp owns its 32-lane TMEM quarter, each thread one
-//               output row), bias + ReLU, then either bf16 store of h1 or the running dot product with w3
-//   Two 256-column accumulator stages (all 512 TMEM columns) let the epilogue of tile i overlap the MMAs of tile i+1.
-//
-// Rows are processed in chunks sized so that the bf16 activations of a chunk (x_hat and h1) stay resident in the
-// 126 MB L2 between the three launches of a chunk; HBM sees x once and the rewards once.
+// Structure: see disc_fused_kernel below (one persistent CTA per SM, 320 threads, warp-specialised: TMA producer, single
+// thread tcgen05.mma issuer, two sets of four epilogue warps).  Rows are processed in chunks whose bf16 x_hat stays
+// L2-resident between the scaler/cast kernel and the fused kernel; the cast of chunk c+1 runs on a side stream under the
+// fused kernel of chunk c.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -40,17 +33,11 @@ constexpr int BK = 64;   // bf16 per K-block = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
 constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KiB
-constexpr int NUM_THREADS = 192;
 constexpr int NUM_EPI_THREADS = 128;
 constexpr int TMEM_COLS = 512;
-// EPI_STORE keeps a bf16 staging area for TMA stores: per epilogue warp two 32-row x 64-column slabs (4 KiB each)
+// bf16 staging area for the h1 TMA stores: per E1 warp two 32-row x 64-column slabs (4 KiB each)
 constexpr int STORE_SLAB_BYTES = 32 * BK * 2;
 constexpr int STORE_STAGING_BYTES = 4 * 2 * STORE_SLAB_BYTES;  // 32 KiB
-__host__ __device__ constexpr int stages_for(int epi) { return epi == 0 ? 3 : 4; }
-__host__ __device__ constexpr int smem_bytes_for(int epi) {
-    return stages_for(epi) * (A_STAGE_BYTES + B_STAGE_BYTES) + (epi == 0 ? STORE_STAGING_BYTES : 0) + 256 /*barriers*/ +
-           1024 /*alignment slack*/;
-}
 
 // ---- PTX wrappers --------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -148,55 +135,99 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
 // (bits 15, 16 = 0), N >> 3 @ bits [17,23), M >> 4 @ bits [24,29).
 constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
-struct EpilogueParams {
-    const float *bias;      // [N]
-    __nv_bfloat16 *out;     // EPI_STORE: (M, N) row-major bf16
-    const float *w3;        // EPI_REWARD: [N]
-    const float *b3;        // EPI_REWARD: device scalar
-    float scale;            // EPI_REWARD
-    float *reward;          // EPI_REWARD: [M]
-    float *logits;          // EPI_REWARD: [M] or NULL
+// =====================================================================================================================
+// Fused two-layer kernel: layer 1 and layer 2 share ONE persistent launch and keep the tensor pipe busy.
+//
+// Why not keep h1 on chip: one 128-row tile needs h1 = 128 x 1024 bf16 = 256 KB (> 227 KB smem) for the K loop of layer 2,
+// and its accumulator D2 = 128 x 512 fp32 already fills all 512 TMEM columns.  So the accumulators are halved
+// (D1 = columns [0,256), D2 = [256,512)) and h1 makes a round trip through a per-CTA, double-buffered workspace that
+// never leaves the L2 (148 CTAs x 2 slots x 256 KB = 77.6 MB), written with TMA stores and read back with TMA loads.
+//
+// The single MMA-issuing thread interleaves the two GEMMs in a static software pipeline over the CTA's row tiles:
+//     prologue   G1(t0, nt = 0..3)
+//     iteration i, group g = 0..3:   G1(t[i+1], nt = g)  then  G2(t[i]) units [8g, 8g+8)        (unit = one 64-wide K block
+//                                                                                                of one 256-column N tile)
+// so while the epilogue warps E1 drain D1 (bias + ReLU + bf16 + swizzled st.shared + TMA store; ~3k cycles, the slow part of
+// the split version) the tensor pipe runs 8 units = 4096 cycles of layer-2 MMAs, and while E2 drains D2 it runs a layer-1
+// tile.  Per row tile the pipe is busy 4*1536 + 32*512 = 22528 cycles, the MMA-bound floor of the two layers together.
+//
+// Warp roles (320 threads): 0 TMA producer, 1 TMEM alloc + MMA issuer, 2..5 E1 (D1 -> h1), 6..9 E2 (D2 -> logit, reward).
+// Producer and issuer walk the same schedule (walk_schedule); E1/E2 just follow their accumulator barriers.
+// =====================================================================================================================
+constexpr int FUSED_STAGES = 4;
+constexpr int FUSED_THREADS = 320;
+constexpr int FUSED_SMEM_BYTES = FUSED_STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + STORE_STAGING_BYTES + 256 + 1024;
+constexpr uint32_t D1_COL = 0, D2_COL = 256;
+
+template <class G1, class G2>
+__device__ __forceinline__ void walk_schedule(int T, int n1_tiles, int units, G1 &&g1, G2 &&g2) {
+    if (T <= 0) return;
+    for (int nt = 0; nt < n1_tiles; ++nt) g1(0, nt);
+    const int per_group = (units + n1_tiles - 1) / n1_tiles;
+    for (int i = 0; i < T; ++i) {
+        int u = 0;
+        for (int g = 0; g < n1_tiles; ++g) {
+            if (i + 1 < T) g1(i + 1, g);
+            const int end = min(units, u + per_group);
+            for (; u < end; ++u) g2(i, u);
+        }
+    }
+}
+
+struct FusedParams {
+    int M;          // rows of this launch (x_hat rows)
+    int kb1;        // K blocks of layer 1 (Kp / 64)
+    int n1_tiles;   // h1 / 256
+    int n2_tiles;   // h2 / 256
+    const float *b1, *b2, *w3, *b3;
+    float scale;
+    float *reward;  // [M]
+    float *logits;  // [M] or NULL
 };
 
-enum { EPI_STORE = 0, EPI_REWARD = 1 };
-
-template <int EPI>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-disc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const __grid_constant__ CUtensorMap tmap_out, int M, int N, int num_k_blocks, EpilogueParams ep) {
-    constexpr int STAGES = stages_for(EPI);
+__global__ void __launch_bounds__(FUSED_THREADS, 1)
+disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w1,
+                  const __grid_constant__ CUtensorMap tmap_h_load, const __grid_constant__ CUtensorMap tmap_h_store,
+                  const __grid_constant__ CUtensorMap tmap_w2, FusedParams p) {
+    constexpr int STAGES = FUSED_STAGES;
     extern __shared__ uint8_t smem_raw[];
-    // SWIZZLE_128B needs 1024-byte aligned stage buffers
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t smem_a = base;
     const uint32_t smem_b = base + STAGES * A_STAGE_BYTES;
-    const uint32_t staging = smem_b + STAGES * B_STAGE_BYTES;  // EPI_STORE only
-    const uint32_t bars = staging + (EPI == EPI_STORE ? STORE_STAGING_BYTES : 0);
-    const uint32_t full_bar = bars;                    // STAGES x 8 B
-    const uint32_t empty_bar = bars + 8 * STAGES;      // STAGES x 8 B
-    const uint32_t tmem_full_bar = bars + 16 * STAGES; // 2 x 8 B
-    const uint32_t tmem_empty_bar = tmem_full_bar + 16;// 2 x 8 B
-    const uint32_t tmem_slot = tmem_empty_bar + 16;    // 4 B
+    const uint32_t staging = smem_b + STAGES * B_STAGE_BYTES;
+    const uint32_t bars = staging + STORE_STAGING_BYTES;
+    const uint32_t full_bar = bars, empty_bar = bars + 8 * STAGES;
+    const uint32_t d1_full = bars + 16 * STAGES, d1_empty = d1_full + 8, d2_full = d1_full + 16, d2_empty = d1_full + 24;
+    const uint32_t h1_ready = d1_full + 32;  // 2 x 8 B
+    const uint32_t tmem_slot = h1_ready + 16;
     uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_m_tiles = (M + BM - 1) / BM, num_n_tiles = N / BN;
+    const int num_m_tiles = (p.M + BM - 1) / BM;
+    const int T = ((int)blockIdx.x < num_m_tiles) ? (num_m_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int kb2 = 4 * p.n1_tiles;            // K blocks of layer 2 = h1 / 64
+    const int units = p.n2_tiles * kb2;        // layer-2 units per row tile
+    const int slot_row0 = (int)blockIdx.x * 2 * BM;  // first row of this CTA's two h1 slots in the workspace
 
     if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
-        if (EPI == EPI_STORE) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_out) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w1) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_h_load) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_h_store) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w2) : "memory");
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(full_bar + 8 * i, 1);
             mbar_init(empty_bar + 8 * i, 1);
         }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(tmem_full_bar + 8 * i, 1);
-            mbar_init(tmem_empty_bar + 8 * i, NUM_EPI_THREADS);
-        }
+        mbar_init(d1_full, 1);
+        mbar_init(d1_empty, NUM_EPI_THREADS);
+        mbar_init(d2_full, 1);
+        mbar_init(d2_empty, NUM_EPI_THREADS);
+        mbar_init(h1_ready, 4);
+        mbar_init(h1_ready + 8, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {  // whole warp: allocate all 512 TMEM columns, publish the base address through shared memory
+    if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -210,133 +241,160 @@ disc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int mt = blockIdx.x; mt < num_m_tiles; mt += gridDim.x) {
-                for (int nt = 0; nt < num_n_tiles; ++nt) {
-                    for (int kb = 0; kb < num_k_blocks; ++kb) {
-                        mbar_wait(empty_bar + 8 * stage, phase ^ 1);
-                        mbar_arrive_expect_tx(full_bar + 8 * stage, A_STAGE_BYTES + B_STAGE_BYTES);
-                        tma_load_2d(smem_a + stage * A_STAGE_BYTES, &tmap_a, kb * BK, mt * BM, full_bar + 8 * stage);
-                        tma_load_2d(smem_b + stage * B_STAGE_BYTES, &tmap_b, kb * BK, nt * BN, full_bar + 8 * stage);
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            auto load_pair = [&](const CUtensorMap *ma, int a_col, int a_row, const CUtensorMap *mb, int b_col, int b_row) {
+                mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+                mbar_arrive_expect_tx(full_bar + 8 * stage, A_STAGE_BYTES + B_STAGE_BYTES);
+                tma_load_2d(smem_a + stage * A_STAGE_BYTES, ma, a_col, a_row, full_bar + 8 * stage);
+                tma_load_2d(smem_b + stage * B_STAGE_BYTES, mb, b_col, b_row, full_bar + 8 * stage);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            };
+            walk_schedule(
+                T, p.n1_tiles, units,
+                [&](int ti, int nt) {
+                    const int m = (int)blockIdx.x + ti * (int)gridDim.x;
+                    for (int kb = 0; kb < p.kb1; ++kb) load_pair(&tmap_x, kb * BK, m * BM, &tmap_w1, kb * BK, nt * BN);
+                },
+                [&](int ti, int u) {
+                    const int n2 = u / kb2, kb = u - n2 * kb2;
+                    if (u == 0) {  // h1 of this row tile has been written (all four E1 warps' TMA stores completed)
+                        mbar_wait(h1_ready + 8 * (ti & 1), (uint32_t)((ti >> 1) & 1));
+                        asm volatile("fence.proxy.async.global;" ::: "memory");
                     }
-                }
-            }
+                    load_pair(&tmap_h_load, kb * BK, slot_row0 + (ti & 1) * BM, &tmap_w2, kb * BK, n2 * BN);
+                });
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            int stage = 0, acc = 0;
-            uint32_t phase = 0, acc_phase = 0;
-            for (int mt = blockIdx.x; mt < num_m_tiles; mt += gridDim.x) {
-                for (int nt = 0; nt < num_n_tiles; ++nt) {
-                    mbar_wait(tmem_empty_bar + 8 * acc, acc_phase ^ 1);  // epilogue drained this accumulator
-                    tcgen05_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-                    for (int kb = 0; kb < num_k_blocks; ++kb) {
-                        mbar_wait(full_bar + 8 * stage, phase);          // TMA bytes landed
-                        tcgen05_fence_after();
-                        const uint64_t a0 = make_kmajor_sw128_desc(smem_a + stage * A_STAGE_BYTES);
-                        const uint64_t b0 = make_kmajor_sw128_desc(smem_b + stage * B_STAGE_BYTES);
+            int stage = 0;
+            uint32_t phase = 0, c1 = 0, c2 = 0;
+            auto mma_block = [&](uint32_t d_tmem, bool first) {
+                mbar_wait(full_bar + 8 * stage, phase);
+                tcgen05_fence_after();
+                const uint64_t a0 = make_kmajor_sw128_desc(smem_a + stage * A_STAGE_BYTES);
+                const uint64_t b0 = make_kmajor_sw128_desc(smem_b + stage * B_STAGE_BYTES);
 #pragma unroll
-                        for (int k = 0; k < BK / UMMA_K; ++k) {
-                            // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
-                            umma_bf16(d_tmem, a0 + 2 * k, b0 + 2 * k, kInstrDesc, (uint32_t)((kb | k) != 0));
-                        }
-                        umma_commit(empty_bar + 8 * stage);              // frees the smem slot once these MMAs retire
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16(d_tmem, a0 + 2 * k, b0 + 2 * k, kInstrDesc, (uint32_t)(!first || k != 0));
+                umma_commit(empty_bar + 8 * stage);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            };
+            walk_schedule(
+                T, p.n1_tiles, units,
+                [&](int, int) {
+                    mbar_wait(d1_empty, (c1 & 1) ^ 1);  // E1 has drained D1
+                    tcgen05_fence_after();
+                    for (int kb = 0; kb < p.kb1; ++kb) mma_block(tmem_base + D1_COL, kb == 0);
+                    umma_commit(d1_full);
+                    ++c1;
+                },
+                [&](int, int u) {
+                    const int kb = u % kb2;
+                    if (kb == 0) {
+                        mbar_wait(d2_empty, (c2 & 1) ^ 1);  // E2 has drained D2
+                        tcgen05_fence_after();
                     }
-                    umma_commit(tmem_full_bar + 8 * acc);                // accumulator complete -> epilogue
-                    acc ^= 1;
-                    if (acc == 0) acc_phase ^= 1;
+                    mma_block(tmem_base + D2_COL, kb == 0);
+                    if (kb == kb2 - 1) {
+                        umma_commit(d2_full);
+                        ++c2;
+                    }
+                });
+        }
+    } else if (warp < 6) {
+        // ================= E1: D1 -> bias + ReLU -> bf16 h1 slabs -> TMA store into the CTA's L2-resident slot =================
+        const int quarter = warp & 3;
+        const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+        uint32_t c1 = 0, store_it = 0;
+        for (int ti = 0; ti < T; ++ti) {
+            const int row0 = slot_row0 + (ti & 1) * BM + quarter * 32;
+            for (int nt = 0; nt < p.n1_tiles; ++nt) {
+                mbar_wait(d1_full, c1 & 1);
+                tcgen05_fence_after();
+#pragma unroll 1
+                for (int cb = 0; cb < BN / BK; ++cb) {
+                    const uint32_t slab = staging + (uint32_t)((quarter * 2 + (store_it & 1)) * STORE_SLAB_BYTES);
+                    if (lane == 0) bulk_wait_read<1>();
+                    __syncwarp();
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        uint32_t v[32];
+                        tmem_ld_32x32(tmem_base + lane_base + D1_COL + (uint32_t)(cb * BK + half * 32), v);
+                        tmem_ld_wait();
+                        const float4 *bias4 = reinterpret_cast<const float4 *>(p.b1 + nt * BN + cb * BK + half * 32);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 b0 = __ldg(bias4 + 2 * j), b1v = __ldg(bias4 + 2 * j + 1);
+                            const __nv_bfloat162 p0 = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[8 * j + 0]) + b0.x, 0.0f),
+                                                                            fmaxf(__uint_as_float(v[8 * j + 1]) + b0.y, 0.0f));
+                            const __nv_bfloat162 p1 = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[8 * j + 2]) + b0.z, 0.0f),
+                                                                            fmaxf(__uint_as_float(v[8 * j + 3]) + b0.w, 0.0f));
+                            const __nv_bfloat162 p2 = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[8 * j + 4]) + b1v.x, 0.0f),
+                                                                            fmaxf(__uint_as_float(v[8 * j + 5]) + b1v.y, 0.0f));
+                            const __nv_bfloat162 p3 = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[8 * j + 6]) + b1v.z, 0.0f),
+                                                                            fmaxf(__uint_as_float(v[8 * j + 7]) + b1v.w, 0.0f));
+                            const int chunk = (half * 4 + j) ^ (lane & 7);
+                            st_shared_v4(slab + (uint32_t)(lane * 128 + chunk * 16), *reinterpret_cast<const uint32_t *>(&p0),
+                                         *reinterpret_cast<const uint32_t *>(&p1), *reinterpret_cast<const uint32_t *>(&p2),
+                                         *reinterpret_cast<const uint32_t *>(&p3));
+                        }
+                    }
+                    if (cb == BN / BK - 1) {  // last TMEM read of this accumulator: release D1 to the issuer early
+                        tcgen05_fence_before();
+                        mbar_arrive(d1_empty);
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmap_h_store, slab, nt * BN + cb * BK, row0);
+                        bulk_commit();
+                    }
+                    ++store_it;
                 }
+                ++c1;
+            }
+            if (lane == 0) {  // this warp's 32 rows of h1 are complete in the workspace
+                bulk_wait_all();
+                mbar_arrive(h1_ready + 8 * (ti & 1));
             }
         }
     } else {
-        // ================= epilogue warps 2..5 =================
-        const int quarter = warp & 3;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
+        // ================= E2: D2 -> bias + ReLU -> running dot with w3 -> logit -> reward =================
+        const int quarter = warp & 3;
         const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        uint32_t store_it = 0;  // EPI_STORE: running count of TMA stores issued by this warp (selects the slab)
-        for (int mt = blockIdx.x; mt < num_m_tiles; mt += gridDim.x) {
-            const int row = mt * BM + quarter * 32 + lane;
+        uint32_t c2 = 0;
+        for (int ti = 0; ti < T; ++ti) {
+            const int m = (int)blockIdx.x + ti * (int)gridDim.x;
+            const int row = m * BM + quarter * 32 + lane;
             float dot = 0.0f;
-            for (int nt = 0; nt < num_n_tiles; ++nt) {
-                mbar_wait(tmem_full_bar + 8 * acc, acc_phase);
+            for (int n2 = 0; n2 < p.n2_tiles; ++n2) {
+                mbar_wait(d2_full, c2 & 1);
                 tcgen05_fence_after();
-                if constexpr (EPI == EPI_STORE) {
-                    // bias + ReLU -> bf16, staged per warp as a [32 rows x 64 cols] slab in the 128B-swizzled layout and
-                    // written with one TMA store per slab (full 128-byte lines; rows past M are clipped by the tensor map)
 #pragma unroll 1
-                    for (int cb = 0; cb < BN / BK; ++cb) {
-                        const uint32_t slab = staging + (uint32_t)((quarter * 2 + (store_it & 1)) * STORE_SLAB_BYTES);
-                        if (lane == 0) bulk_wait_read<1>();  // the store that last read this slab has drained it
-                        __syncwarp();
+                for (int chunk = 0; chunk < BN / 32; ++chunk) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_base + lane_base + D2_COL + (uint32_t)(chunk * 32), v);
+                    tmem_ld_wait();
+                    const int col0 = n2 * BN + chunk * 32;
+                    const float4 *bias4 = reinterpret_cast<const float4 *>(p.b2 + col0);
+                    const float4 *w4 = reinterpret_cast<const float4 *>(p.w3 + col0);
 #pragma unroll
-                        for (int half = 0; half < 2; ++half) {
-                            uint32_t v[32];
-                            tmem_ld_32x32(tmem_base + lane_base + (uint32_t)(acc * BN + cb * BK + half * 32), v);
-                            tmem_ld_wait();
-                            const float4 *bias4 = reinterpret_cast<const float4 *>(ep.bias + nt * BN + cb * BK + half * 32);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {  // 16-byte chunk (half*4 + j) of this thread's 128-byte row
-                                const float4 b0 = __ldg(bias4 + 2 * j), b1 = __ldg(bias4 + 2 * j + 1);
-                                const __nv_bfloat162 p0 = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[8 * j + 0]) + b0.x, 0.0f),
-                                                                                fmaxf(__uint_as_float(v[8 * j + 1]) + b0.y, 0.0f));
-                                const __nv_bfloat162 p1 = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[8 * j + 2]) + b0.z, 0.0f),
-                                                                                fmaxf(__uint_as_float(v[8 * j + 3]) + b0.w, 0.0f));
-                                const __nv_bfloat162 p2 = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[8 * j + 4]) + b1.x, 0.0f),
-                                                                                fmaxf(__uint_as_float(v[8 * j + 5]) + b1.y, 0.0f));
-                                const __nv_bfloat162 p3 = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[8 * j + 6]) + b1.z, 0.0f),
-                                                                                fmaxf(__uint_as_float(v[8 * j + 7]) + b1.w, 0.0f));
-                                const int chunk = (half * 4 + j) ^ (lane & 7);  // SWIZZLE_128B: chunk index XOR (row % 8)
-                                st_shared_v4(slab + (uint32_t)(lane * 128 + chunk * 16), *reinterpret_cast<const uint32_t *>(&p0),
-                                             *reinterpret_cast<const uint32_t *>(&p1), *reinterpret_cast<const uint32_t *>(&p2),
-                                             *reinterpret_cast<const uint32_t *>(&p3));
-                            }
-                        }
-                        fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA (async proxy)
-                        __syncwarp();
-                        if (lane == 0) {
-                            tma_store_2d(&tmap_out, slab, nt * BN + cb * BK, mt * BM + quarter * 32);
-                            bulk_commit();
-                        }
-                        ++store_it;
-                    }
-                } else {
-#pragma unroll 1
-                    for (int chunk = 0; chunk < BN / 32; ++chunk) {
-                        uint32_t v[32];
-                        tmem_ld_32x32(tmem_base + lane_base + (uint32_t)(acc * BN + chunk * 32), v);
-                        tmem_ld_wait();
-                        const int col0 = nt * BN + chunk * 32;
-                        const float4 *bias4 = reinterpret_cast<const float4 *>(ep.bias + col0);
-                        const float4 *w4 = reinterpret_cast<const float4 *>(ep.w3 + col0);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 bb = __ldg(bias4 + j), ww = __ldg(w4 + j);
-                            dot = fmaf(fmaxf(__uint_as_float(v[4 * j + 0]) + bb.x, 0.0f), ww.x, dot);
-                            dot = fmaf(fmaxf(__uint_as_float(v[4 * j + 1]) + bb.y, 0.0f), ww.y, dot);
-                            dot = fmaf(fmaxf(__uint_as_float(v[4 * j + 2]) + bb.z, 0.0f), ww.z, dot);
-                            dot = fmaf(fmaxf(__uint_as_float(v[4 * j + 3]) + bb.w, 0.0f), ww.w, dot);
-                        }
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 bb = __ldg(bias4 + j), ww = __ldg(w4 + j);
+                        dot = fmaf(fmaxf(__uint_as_float(v[4 * j + 0]) + bb.x, 0.0f), ww.x, dot);
+                        dot = fmaf(fmaxf(__uint_as_float(v[4 * j + 1]) + bb.y, 0.0f), ww.y, dot);
+                        dot = fmaf(fmaxf(__uint_as_float(v[4 * j + 2]) + bb.z, 0.0f), ww.z, dot);
+                        dot = fmaf(fmaxf(__uint_as_float(v[4 * j + 3]) + bb.w, 0.0f), ww.w, dot);
                     }
                 }
                 tcgen05_fence_before();
-                mbar_arrive(tmem_empty_bar + 8 * acc);  // this thread is done reading the accumulator stage
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1;
+                mbar_arrive(d2_empty);
+                ++c2;
             }
-            if constexpr (EPI == EPI_REWARD) {
-                if (row < M) {
-                    const float logit = dot + __ldg(ep.b3);
-                    if (ep.logits) ep.logits[row] = logit;
-                    ep.reward[row] = style_reward(logit, ep.scale);
-                }
+            if (row < p.M) {
+                const float logit = dot + __ldg(p.b3);
+                if (p.logits) p.logits[row] = logit;
+                p.reward[row] = style_reward(logit, p.scale);
             }
-        }
-        if constexpr (EPI == EPI_STORE) {
-            if (lane == 0) bulk_wait_all();  // all TMA stores of this warp have completed before the CTA exits
         }
     }
 
@@ -361,17 +419,18 @@ __global__ void __launch_bounds__(256) normalise_cast_kernel(const float *__rest
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    float2 mu[NB], dn[NB];
+    // (x - mean) / denom is evaluated as (x - mean) * (1 / denom) with an IEEE reciprocal held in registers: at most 1 ulp
+    // (fp32) from the division, and the result is rounded to bf16 (8-bit mantissa) right after, so the two agree except
+    // when the quotient sits within 2^-16 relative of a bf16 rounding boundary.  Padding columns get rcp = 0 -> exactly 0.
+    float2 mu[NB], rc[NB];
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
         const int c = 2 * (lane + 32 * j);
         mu[j] = make_float2(c < in_features ? mean[c] : 0.0f, c + 1 < in_features ? mean[c + 1] : 0.0f);
-        dn[j] = make_float2(c < in_features ? denom[c] : 1.0f, c + 1 < in_features ? denom[c + 1] : 1.0f);
+        rc[j] = make_float2(c < in_features ? __frcp_rn(denom[c]) : 0.0f, c + 1 < in_features ? __frcp_rn(denom[c + 1]) : 0.0f);
     }
-    for (int64_t r = warp; r < M; r += nwarps) {
+    auto load_row = [&](int64_t r, float2(&v)[NB]) {
         const float *xr = x + r * x_stride;
-        __nv_bfloat162 *orow = reinterpret_cast<__nv_bfloat162 *>(out + r * Kp);
-        float2 v[NB];
 #pragma unroll
         for (int j = 0; j < NB; ++j) {
             const int c = 2 * (lane + 32 * j);
@@ -383,16 +442,30 @@ __global__ void __launch_bounds__(256) normalise_cast_kernel(const float *__rest
                 if (c + 1 < in_features) v[j].y = __ldcs(xr + c + 1);
             }
         }
+    };
+    auto store_row = [&](int64_t r, const float2(&v)[NB]) {
+        __nv_bfloat162 *orow = reinterpret_cast<__nv_bfloat162 *>(out + r * Kp);
 #pragma unroll
         for (int j = 0; j < NB; ++j) {
-            const int c = 2 * (lane + 32 * j);
-            // clamp((x - mean) / (sqrt(var) + 1e-8), -5, 5); padding columns stay exactly 0
-            float a = fminf(fmaxf(__fdiv_rn(__fsub_rn(v[j].x, mu[j].x), dn[j].x), -5.0f), 5.0f);
-            float b = fminf(fmaxf(__fdiv_rn(__fsub_rn(v[j].y, mu[j].y), dn[j].y), -5.0f), 5.0f);
-            if (c >= in_features) a = 0.0f;
-            if (c + 1 >= in_features) b = 0.0f;
+            const float a = fminf(fmaxf(__fmul_rn(__fsub_rn(v[j].x, mu[j].x), rc[j].x), -5.0f), 5.0f);
+            const float b = fminf(fmaxf(__fmul_rn(__fsub_rn(v[j].y, mu[j].y), rc[j].y), -5.0f), 5.0f);
             orow[lane + 32 * j] = __floats2bfloat162_rn(a, b);
         }
+    };
+    int64_t r = warp;
+    if constexpr (NB <= 4) {  // two rows in flight per warp while the register budget allows it
+        for (; r + nwarps < M; r += 2 * nwarps) {
+            float2 v0[NB], v1[NB];
+            load_row(r, v0);
+            load_row(r + nwarps, v1);
+            store_row(r, v0);
+            store_row(r + nwarps, v1);
+        }
+    }
+    for (; r < M; r += nwarps) {
+        float2 v0[NB];
+        load_row(r, v0);
+        store_row(r, v0);
     }
 }
 
@@ -477,12 +550,16 @@ static int make_tmap(CUtensorMap *map, const void *ptr, int64_t rows, int64_t co
 struct amp_disc {
     int in_features, Kp, h1, h2;
     int64_t chunk_rows;
+    int ws_ctas;  // persistent CTAs the h1 workspace was sized for
     int device;
     __nv_bfloat16 *W1, *W2;       // (h1, Kp), (h2, h1) bf16
     float *b1, *b2, *w3, *b3;     // fp32
     float *mean, *denom;          // fp32 [in_features]
-    __nv_bfloat16 *xhat, *hid;    // workspaces (chunk_rows, Kp), (chunk_rows, h1)
+    __nv_bfloat16 *xhat[2], *hid; // workspaces 2 x (chunk_rows, Kp) (double buffer) and (ws_ctas * 2 * 128, h1)
+    cudaStream_t side;            // the scaler/cast of chunk i+1 runs here, under the fused kernel of chunk i
+    cudaEvent_t ev_start, ev_ready[2], ev_free[2];
     CUtensorMap tmap_w1, tmap_w2; // weights never move: encoded once
+    CUtensorMap tmap_h_load, tmap_h_store;  // h1 workspace: 128-row loads, 32-row epilogue slab stores
     bool loaded;
 };
 
@@ -512,10 +589,12 @@ int amp_disc_create(int32_t in_features, int32_t h1, int32_t h2, int64_t max_row
     d->Kp = (in_features + BK - 1) / BK * BK;
     d->h1 = h1;
     d->h2 = h2;
-    // two 128-row tiles per SM per chunk: full waves, and x_hat + h1 of a chunk (~80 MB at h1 = 1024) stay in L2
-    const int64_t wave_rows = (int64_t)sm_count() * BM * 2;
-    d->chunk_rows = std::min<int64_t>((max_rows + BM - 1) / BM * BM, wave_rows);
-
+    // Rows per launch ("chunk"): the bf16 x_hat of a chunk should stay L2-resident between the cast kernel that writes it
+    // and the fused kernel that reads it (<= ~64 MB), in whole waves of 128-row tiles: 8 tiles per SM at K*A = 166.
+    const int64_t per_wave_bytes = (int64_t)sm_count() * BM * d->Kp * 2;
+    const int64_t tiles_per_cta = std::max<int64_t>(1, std::min<int64_t>(8, ((int64_t)64 << 20) / per_wave_bytes));
+    d->chunk_rows = std::min<int64_t>((max_rows + BM - 1) / BM * BM, (int64_t)sm_count() * BM * tiles_per_cta);
+    d->ws_ctas = sm_count();  // h1 workspace: two 128-row slots per persistent CTA, L2-resident
     auto alloc = [&](void **p, size_t bytes) { return cudaMalloc(p, bytes); };
     cudaError_t e = cudaSuccess;
     if (e == cudaSuccess) e = alloc((void **)&d->W1, (size_t)h1 * d->Kp * 2);
@@ -526,20 +605,26 @@ int amp_disc_create(int32_t in_features, int32_t h1, int32_t h2, int64_t max_row
     if (e == cudaSuccess) e = alloc((void **)&d->b3, 4);
     if (e == cudaSuccess) e = alloc((void **)&d->mean, (size_t)in_features * 4);
     if (e == cudaSuccess) e = alloc((void **)&d->denom, (size_t)in_features * 4);
-    if (e == cudaSuccess) e = alloc((void **)&d->xhat, (size_t)d->chunk_rows * d->Kp * 2);
-    if (e == cudaSuccess) e = alloc((void **)&d->hid, (size_t)d->chunk_rows * h1 * 2);
+    if (e == cudaSuccess) e = alloc((void **)&d->xhat[0], (size_t)d->chunk_rows * d->Kp * 2);
+    if (e == cudaSuccess && max_rows > d->chunk_rows) e = alloc((void **)&d->xhat[1], (size_t)d->chunk_rows * d->Kp * 2);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->side, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_start, cudaEventDisableTiming);
+    for (int i = 0; i < 2; ++i) {
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_ready[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_free[i], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = alloc((void **)&d->hid, (size_t)d->ws_ctas * 2 * BM * h1 * 2);
     if (e != cudaSuccess) {
         amp_disc_destroy(d);
         return cuda_fail(e, "cudaMalloc(amp_disc_create)");
     }
     int rc = make_tmap(&d->tmap_w1, d->W1, h1, d->Kp, d->Kp, BN);
     if (rc == AMP_OK) rc = make_tmap(&d->tmap_w2, d->W2, h2, h1, h1, BN);
+    if (rc == AMP_OK) rc = make_tmap(&d->tmap_h_load, d->hid, (int64_t)d->ws_ctas * 2 * BM, h1, h1, BM);
+    if (rc == AMP_OK) rc = make_tmap(&d->tmap_h_store, d->hid, (int64_t)d->ws_ctas * 2 * BM, h1, h1, 32);
     if (rc == AMP_OK) {
-        e = cudaFuncSetAttribute(disc_gemm_kernel<EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(EPI_STORE));
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(disc_gemm_kernel<EPI_REWARD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     smem_bytes_for(EPI_REWARD));
-        if (e != cudaSuccess) rc = cuda_fail(e, "cudaFuncSetAttribute(disc_gemm_kernel)");
+        e = cudaFuncSetAttribute(disc_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM_BYTES);
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaFuncSetAttribute(disc_fused_kernel)");
     }
     if (rc != AMP_OK) {
         amp_disc_destroy(d);
@@ -551,9 +636,15 @@ int amp_disc_create(int32_t in_features, int32_t h1, int32_t h2, int64_t max_row
 
 int amp_disc_destroy(amp_disc_t *d) {
     if (!d) return AMP_OK;
-    void *ptrs[] = {d->W1, d->W2, d->b1, d->b2, d->w3, d->b3, d->mean, d->denom, d->xhat, d->hid};
+    void *ptrs[] = {d->W1, d->W2, d->b1, d->b2, d->w3, d->b3, d->mean, d->denom, d->xhat[0], d->xhat[1], d->hid};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    if (d->side) cudaStreamDestroy(d->side);
+    if (d->ev_start) cudaEventDestroy(d->ev_start);
+    for (int i = 0; i < 2; ++i) {
+        if (d->ev_ready[i]) cudaEventDestroy(d->ev_ready[i]);
+        if (d->ev_free[i]) cudaEventDestroy(d->ev_free[i]);
+    }
     delete d;
     return AMP_OK;
 }
@@ -589,43 +680,59 @@ int amp_disc_style_reward(amp_disc_t *d, const float *x, int64_t x_stride, int64
                 d->in_features);
     cudaStream_t st = as_stream(stream);
     const int sms = sm_count();
-    for (int64_t r0 = 0; r0 < M; r0 += d->chunk_rows) {
-        const int64_t rows = std::min<int64_t>(d->chunk_rows, M - r0);
-        const int m_tiles = (int)((rows + BM - 1) / BM);
-        const int grid = std::min(m_tiles, sms);
+    const int64_t n_chunks = (M + d->chunk_rows - 1) / d->chunk_rows;
+    AMP_REQUIRE(n_chunks == 1 || d->xhat[1], "amp_disc_style_reward: %lld rows exceed the max_rows given to amp_disc_create",
+                (long long)M);
+    // With several chunks the scaler/cast of chunk c+1 runs on the handle's side stream underneath the fused kernel of
+    // chunk c (the fused kernel is operand-delivery bound and leaves HBM and most issue slots idle; the cast kernel uses no
+    // shared memory, so its CTAs co-reside with the persistent fused CTAs).  A single chunk stays on the caller's stream.
+    const bool overlap = n_chunks > 1;
+    auto issue_cast = [&](int64_t c) -> int {
+        const int b = (int)(c & 1);
+        const int64_t r0 = c * d->chunk_rows, rows = std::min<int64_t>(d->chunk_rows, M - r0);
+        cudaStream_t cs = overlap ? d->side : st;
+        if (overlap && c >= 2) AMP_CUDA_TRY(cudaStreamWaitEvent(cs, d->ev_free[b], 0));  // fused(c-2) is done with xhat[b]
         const float *xc = x + r0 * x_stride;
         const bool vec = (x_stride % 2 == 0) && ((reinterpret_cast<uintptr_t>(xc) & 7u) == 0);
         const int cast_grid = (int)std::min<int64_t>((rows + 7) / 8, (int64_t)sms * 8);
-        int rc = vec ? launch_normalise_cast<true>(d->Kp / BK, cast_grid, st, xc, x_stride, rows, d->in_features, d->mean, d->denom, d->xhat)
-                     : launch_normalise_cast<false>(d->Kp / BK, cast_grid, st, xc, x_stride, rows, d->in_features, d->mean, d->denom, d->xhat);
+        int rc = vec ? launch_normalise_cast<true>(d->Kp / BK, cast_grid, cs, xc, x_stride, rows, d->in_features, d->mean, d->denom, d->xhat[b])
+                     : launch_normalise_cast<false>(d->Kp / BK, cast_grid, cs, xc, x_stride, rows, d->in_features, d->mean, d->denom, d->xhat[b]);
         if (rc != AMP_OK) return rc;
         AMP_CUDA_TRY(cudaGetLastError());
-
-        CUtensorMap tm_x, tm_h, tm_h_store;
-        rc = make_tmap(&tm_x, d->xhat, rows, d->Kp, d->Kp, BM);
+        if (overlap) AMP_CUDA_TRY(cudaEventRecord(d->ev_ready[b], cs));
+        return AMP_OK;
+    };
+    if (overlap) {  // the side stream starts after everything already queued on the caller's stream (x may still be in flight)
+        AMP_CUDA_TRY(cudaEventRecord(d->ev_start, st));
+        AMP_CUDA_TRY(cudaStreamWaitEvent(d->side, d->ev_start, 0));
+    }
+    int rc = issue_cast(0);
+    if (rc != AMP_OK) return rc;
+    for (int64_t c = 0; c < n_chunks; ++c) {
+        const int b = (int)(c & 1);
+        const int64_t r0 = c * d->chunk_rows, rows = std::min<int64_t>(d->chunk_rows, M - r0);
+        if (c + 1 < n_chunks && (rc = issue_cast(c + 1)) != AMP_OK) return rc;
+        if (overlap) AMP_CUDA_TRY(cudaStreamWaitEvent(st, d->ev_ready[b], 0));
+        const int m_tiles = (int)((rows + BM - 1) / BM);
+        const int grid = std::min(m_tiles, std::min(sms, d->ws_ctas));
+        CUtensorMap tm_x;
+        rc = make_tmap(&tm_x, d->xhat[b], rows, d->Kp, d->Kp, BM);
         if (rc != AMP_OK) return rc;
-        rc = make_tmap(&tm_h, d->hid, rows, d->h1, d->h1, BM);
-        if (rc != AMP_OK) return rc;
-        rc = make_tmap(&tm_h_store, d->hid, rows, d->h1, d->h1, 32);  // epilogue slabs: 32 rows x 64 columns
-        if (rc != AMP_OK) return rc;
-
-        EpilogueParams e1{};
-        e1.bias = d->b1;
-        e1.out = d->hid;
-        disc_gemm_kernel<EPI_STORE><<<grid, NUM_THREADS, smem_bytes_for(EPI_STORE), st>>>(tm_x, d->tmap_w1, tm_h_store, (int)rows,
-                                                                                          d->h1, d->Kp / BK, e1);
+        FusedParams fp{};
+        fp.M = (int)rows;
+        fp.kb1 = d->Kp / BK;
+        fp.n1_tiles = d->h1 / BN;
+        fp.n2_tiles = d->h2 / BN;
+        fp.b1 = d->b1;
+        fp.b2 = d->b2;
+        fp.w3 = d->w3;
+        fp.b3 = d->b3;
+        fp.scale = reward_scale;
+        fp.reward = reward + r0;
+        fp.logits = logits ? logits + r0 : nullptr;
+        disc_fused_kernel<<<grid, FUSED_THREADS, FUSED_SMEM_BYTES, st>>>(tm_x, d->tmap_w1, d->tmap_h_load, d->tmap_h_store, d->tmap_w2, fp);
         AMP_CUDA_TRY(cudaGetLastError());
-
-        EpilogueParams e2{};
-        e2.bias = d->b2;
-        e2.w3 = d->w3;
-        e2.b3 = d->b3;
-        e2.scale = reward_scale;
-        e2.reward = reward + r0;
-        e2.logits = logits ? logits + r0 : nullptr;
-        disc_gemm_kernel<EPI_REWARD><<<grid, NUM_THREADS, smem_bytes_for(EPI_REWARD), st>>>(tm_h, d->tmap_w2, tm_h, (int)rows, d->h2,
-                                                                                            d->h1 / BK, e2);
-        AMP_CUDA_TRY(cudaGetLastError());
+        if (overlap) AMP_CUDA_TRY(cudaEventRecord(d->ev_free[b], st));
     }
     return AMP_OK;
 }

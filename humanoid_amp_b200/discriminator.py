@@ -31,7 +31,7 @@ class AmpDiscriminator:
         _lib.check(lib.amp_disc_create(self.in_features, self.hidden[0], self.hidden[1], int(max_rows), stream, C.byref(h)))
         self._h = h
         self._masters = None
-        self.chunk_rows = int(lib.amp_disc_chunk_rows(h))  # rows per internal chunk: 3 kernel launches each
+        self.chunk_rows = int(lib.amp_disc_chunk_rows(h))  # rows per internal chunk: 2 kernel launches each (cast + fused two-layer kernel)
 
     def load(self, weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor], running_mean: torch.Tensor, running_variance: torch.Tensor) -> None:
         """Refresh the staged copies from ``[W1 (h1,in), W2 (h2,h1), W3 (1,h2)]``, ``[b1, b2, b3]`` (torch.nn.Linear layout)
