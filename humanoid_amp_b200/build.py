@@ -29,7 +29,8 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hi
 SOURCES = {
     "amp_core.cu": [],
     "amp_motion.cu": ["-fmad=false"],
-    "amp_disc.cu": [],
+    # AMP_DISC_PROFILE=1 (developer builds only) adds in-kernel cycle counters to the fused discriminator kernel
+    "amp_disc.cu": ["-DAMP_DISC_PROFILE"] if os.environ.get("AMP_DISC_PROFILE") == "1" else [],
 }
 HEADERS = ["amp_internal.h", "amp_math.cuh", os.path.join(ROOT, "include", "amp_b200.h")]
 

@@ -18,6 +18,8 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -33,11 +35,11 @@ constexpr int BK = 64;   // bf16 per K-block = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
 constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KiB
-constexpr int NUM_EPI_THREADS = 128;
+constexpr int NUM_EPI_THREADS = 256;  // eight epilogue warps
 constexpr int TMEM_COLS = 512;
 // bf16 staging area for the h1 TMA stores: per E1 warp two 32-row x 64-column slabs (4 KiB each)
 constexpr int STORE_SLAB_BYTES = 32 * BK * 2;
-constexpr int STORE_STAGING_BYTES = 4 * 2 * STORE_SLAB_BYTES;  // 32 KiB
+constexpr int STORE_STAGING_BYTES = 8 * 2 * STORE_SLAB_BYTES;  // 64 KiB: eight epilogue warps, two slabs each
 
 // ---- PTX wrappers --------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -84,6 +86,50 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// ---- cluster / CTA-pair (cta_group::2) forms ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+}
+// TMA load issued by either CTA of a pair: data lands in the executing CTA's smem, the transaction bytes are credited to
+// the mbarrier at `bar_cluster_addr` (the leader CTA's barrier)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar_cluster_addr) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+// arrive on the barrier at the same offset in every CTA of `mask` once all MMAs issued so far by this thread have retired
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(mask)
+                 : "memory");
+}
+// M = 256 across the CTA pair: each CTA supplies its own 128 rows of A and its own half (128 rows) of the N = 256 B tile
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -134,6 +180,8 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
 // Instruction descriptor for kind::f16: D = fp32 (c_format 1 @ bit 4), A = B = bf16 (format 1 @ bits 7, 10), both K-major
 // (bits 15, 16 = 0), N >> 3 @ bits [17,23), M >> 4 @ bits [24,29).
 constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// same for cta_group::2: M = 256 (128 rows per CTA of the pair)
+constexpr uint32_t kInstrDescPair = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
 
 // =====================================================================================================================
 // Fused two-layer kernel: layer 1 and layer 2 share ONE persistent launch and keep the tensor pipe busy.
@@ -151,13 +199,24 @@ constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)
 // the split version) the tensor pipe runs 8 units = 4096 cycles of layer-2 MMAs, and while E2 drains D2 it runs a layer-1
 // tile.  Per row tile the pipe is busy 4*1536 + 32*512 = 22528 cycles, the MMA-bound floor of the two layers together.
 //
-// Warp roles (320 threads): 0 TMA producer, 1 TMEM alloc + MMA issuer, 2..5 E1 (D1 -> h1), 6..9 E2 (D2 -> logit, reward).
-// Producer and issuer walk the same schedule (walk_schedule); E1/E2 just follow their accumulator barriers.
+// Warp roles (320 threads): 0 TMA producer, 1 TMEM alloc + MMA issuer, 2..9 epilogue (warps w and w+4 share a TMEM lane
+// quarter and split the accumulator columns).  Producer, issuer and epilogue warps all walk the same static schedule
+// (walk_schedule).
 // =====================================================================================================================
-constexpr int FUSED_STAGES = 4;
+// =====================================================================================================================
+// PAIR = true runs the same pipeline on a CTA pair (cluster of 2, tcgen05 cta_group::2): one MMA covers 256 rows (128 per
+// CTA) and each CTA stages only ITS half of the 256-row weight block, so the operand bytes delivered per SM per MMA drop
+// from 48 KB to 32 KB per K block.  ncu on the single-CTA version showed TMA loads pinned at 40 % of the xbar->L1 peak on
+// every SM (2.57 GB per 151 552 rows, ~51 B/cycle/SM) with the tensor pipe 55 % active: operand delivery, not math, is
+// the limiter, and a CTA pair is the only way to shrink it without more TMEM.
 constexpr int FUSED_THREADS = 320;
-constexpr int FUSED_SMEM_BYTES = FUSED_STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + STORE_STAGING_BYTES + 256 + 1024;
 constexpr uint32_t D1_COL = 0, D2_COL = 256;
+__host__ __device__ constexpr int fused_stages(bool pair) { return pair ? 5 : 3; }
+__host__ __device__ constexpr int fused_b_bytes(bool pair) { return pair ? B_STAGE_BYTES / 2 : B_STAGE_BYTES; }
+__host__ __device__ constexpr int fused_smem_bytes(bool pair) {
+    return fused_stages(pair) * (A_STAGE_BYTES + fused_b_bytes(pair)) + STORE_STAGING_BYTES + 256 /*barriers*/ +
+           1024 /*partial dots*/ + 1024 /*alignment slack*/;
+}
 
 template <class G1, class G2>
 __device__ __forceinline__ void walk_schedule(int T, int n1_tiles, int units, G1 &&g1, G2 &&g2) {
@@ -183,28 +242,53 @@ struct FusedParams {
     float scale;
     float *reward;  // [M]
     float *logits;  // [M] or NULL
+    long long *prof;  // AMP_DISC_PROFILE builds only: per-CTA cycle counters of the producer / issuer waits, else NULL
 };
 
+#ifdef AMP_DISC_PROFILE
+#define AMP_PROF_T0 const long long _t0 = clock64()
+#define AMP_PROF_ADD(var) var += clock64() - _t0
+#else
+#define AMP_PROF_T0
+#define AMP_PROF_ADD(var)
+#endif
+
+template <bool PAIR>
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
 disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w1,
                   const __grid_constant__ CUtensorMap tmap_h_load, const __grid_constant__ CUtensorMap tmap_h_store,
                   const __grid_constant__ CUtensorMap tmap_w2, FusedParams p) {
-    constexpr int STAGES = FUSED_STAGES;
+    constexpr int STAGES = fused_stages(PAIR);
+    constexpr int B_BYTES = fused_b_bytes(PAIR);
+    constexpr int B_ROWS = PAIR ? BN / 2 : BN;  // weight rows staged by this CTA per K block
+    constexpr uint32_t STAGE_TX = PAIR ? 2u * (A_STAGE_BYTES + B_BYTES) : (uint32_t)(A_STAGE_BYTES + B_BYTES);
+    // one arrival per epilogue warp (lane 0, after the warp's TMEM reads are fenced and the warp has synchronised): with a
+    // CTA pair the peer's arrivals are remote mbarrier operations, and 256 of them per drain serialised for thousands of cycles
+    constexpr uint32_t EPI_ARRIVALS = (PAIR ? 2 : 1) * (NUM_EPI_THREADS / 32);
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t smem_a = base;
     const uint32_t smem_b = base + STAGES * A_STAGE_BYTES;
-    const uint32_t staging = smem_b + STAGES * B_STAGE_BYTES;
+    const uint32_t staging = smem_b + STAGES * B_BYTES;
     const uint32_t bars = staging + STORE_STAGING_BYTES;
     const uint32_t full_bar = bars, empty_bar = bars + 8 * STAGES;
     const uint32_t d1_full = bars + 16 * STAGES, d1_empty = d1_full + 8, d2_full = d1_full + 16, d2_empty = d1_full + 24;
     const uint32_t h1_ready = d1_full + 32;  // 2 x 8 B
     const uint32_t tmem_slot = h1_ready + 16;
+    const uint32_t part_smem = bars + 256;  // 2 x 4 x 32 floats
     uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
     const int num_m_tiles = (p.M + BM - 1) / BM;
-    const int T = ((int)blockIdx.x < num_m_tiles) ? (num_m_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    // work unit = one 128-row tile per CTA; a pair takes two consecutive tiles (a 256-row block) so both CTAs always walk
+    // the same schedule (the second tile of the last block may lie entirely past M: TMA zero-fills, stores are clipped)
+    const int group = PAIR ? (int)blockIdx.x / 2 : (int)blockIdx.x;
+    const int num_groups = PAIR ? (int)gridDim.x / 2 : (int)gridDim.x;
+    const int num_blocks = PAIR ? (num_m_tiles + 1) / 2 : num_m_tiles;
+    const int T = group < num_blocks ? (num_blocks - 1 - group) / num_groups + 1 : 0;
+    auto tile_of = [&](int ti) { return PAIR ? 2 * (group + ti * num_groups) + (int)rank : group + ti * num_groups; };
     const int kb2 = 4 * p.n1_tiles;            // K blocks of layer 2 = h1 / 64
     const int units = p.n2_tiles * kb2;        // layer-2 units per row tile
     const int slot_row0 = (int)blockIdx.x * 2 * BM;  // first row of this CTA's two h1 slots in the workspace
@@ -220,189 +304,295 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             mbar_init(empty_bar + 8 * i, 1);
         }
         mbar_init(d1_full, 1);
-        mbar_init(d1_empty, NUM_EPI_THREADS);
+        mbar_init(d1_empty, EPI_ARRIVALS);
         mbar_init(d2_full, 1);
-        mbar_init(d2_empty, NUM_EPI_THREADS);
-        mbar_init(h1_ready, 4);
-        mbar_init(h1_ready + 8, 4);
+        mbar_init(d2_empty, EPI_ARRIVALS);
+        mbar_init(h1_ready, 8);  // one arrival per epilogue warp
+        mbar_init(h1_ready + 8, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (warp == 1) {  // the same warp of both CTAs of a pair allocates (all 512 columns) and later frees
+        if constexpr (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tcgen05_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    // accumulator-drained barriers live in the leader CTA; the epilogue threads of both CTAs arrive there
+    const uint32_t d1_empty_at_leader = PAIR ? mapa_rank(d1_empty, 0) : d1_empty;
+    const uint32_t d2_empty_at_leader = PAIR ? mapa_rank(d2_empty, 0) : d2_empty;
+    auto arrive_drained = [&](uint32_t addr) {
+        if constexpr (PAIR) mbar_arrive_cluster(addr); else mbar_arrive(addr);
+    };
 
     if (warp == 0) {
-        // ================= TMA producer =================
+        // ================= TMA producer (every CTA loads its own rows of A and its own part of the weight block) =========
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            long long w_empty = 0, w_h1 = 0;
             auto load_pair = [&](const CUtensorMap *ma, int a_col, int a_row, const CUtensorMap *mb, int b_col, int b_row) {
-                mbar_wait(empty_bar + 8 * stage, phase ^ 1);
-                mbar_arrive_expect_tx(full_bar + 8 * stage, A_STAGE_BYTES + B_STAGE_BYTES);
-                tma_load_2d(smem_a + stage * A_STAGE_BYTES, ma, a_col, a_row, full_bar + 8 * stage);
-                tma_load_2d(smem_b + stage * B_STAGE_BYTES, mb, b_col, b_row, full_bar + 8 * stage);
+                {
+                    AMP_PROF_T0;
+                    mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+                    AMP_PROF_ADD(w_empty);
+                }
+                const uint32_t fb = full_bar + 8 * stage;
+                if constexpr (PAIR) {
+                    if (leader) mbar_arrive_expect_tx(fb, STAGE_TX);  // bytes of both CTAs are credited to the leader's barrier
+                    const uint32_t fb_leader = mapa_rank(fb, 0);
+                    tma_load_2d_pair(smem_a + stage * A_STAGE_BYTES, ma, a_col, a_row, fb_leader);
+                    tma_load_2d_pair(smem_b + stage * B_BYTES, mb, b_col, b_row + (int)rank * B_ROWS, fb_leader);
+                } else {
+                    mbar_arrive_expect_tx(fb, STAGE_TX);
+                    tma_load_2d(smem_a + stage * A_STAGE_BYTES, ma, a_col, a_row, fb);
+                    tma_load_2d(smem_b + stage * B_BYTES, mb, b_col, b_row, fb);
+                }
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             };
             walk_schedule(
                 T, p.n1_tiles, units,
                 [&](int ti, int nt) {
-                    const int m = (int)blockIdx.x + ti * (int)gridDim.x;
+                    const int m = tile_of(ti);
                     for (int kb = 0; kb < p.kb1; ++kb) load_pair(&tmap_x, kb * BK, m * BM, &tmap_w1, kb * BK, nt * BN);
                 },
                 [&](int ti, int u) {
                     const int n2 = u / kb2, kb = u - n2 * kb2;
                     if (u == 0) {  // h1 of this row tile has been written (all four E1 warps' TMA stores completed)
+                        AMP_PROF_T0;
                         mbar_wait(h1_ready + 8 * (ti & 1), (uint32_t)((ti >> 1) & 1));
+                        AMP_PROF_ADD(w_h1);
                         asm volatile("fence.proxy.async.global;" ::: "memory");
                     }
                     load_pair(&tmap_h_load, kb * BK, slot_row0 + (ti & 1) * BM, &tmap_w2, kb * BK, n2 * BN);
                 });
+#ifdef AMP_DISC_PROFILE
+            if (p.prof) {
+                p.prof[blockIdx.x * 8 + 4] = w_empty;
+                p.prof[blockIdx.x * 8 + 5] = w_h1;
+            }
+#endif
         }
+        __syncwarp();
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
+        // ================= MMA issuer (one thread; for a pair, one thread of the leader CTA drives both SMs) =============
+        if (lane == 0 && leader) {
             int stage = 0;
             uint32_t phase = 0, c1 = 0, c2 = 0;
+            long long w_full = 0, w_d1 = 0, w_d2 = 0;
+#ifdef AMP_DISC_PROFILE
+            const long long t_begin = clock64();
+#endif
+            auto commit = [&](uint32_t bar) {
+                if constexpr (PAIR) umma_commit_pair(bar, (uint16_t)0x3); else umma_commit(bar);
+            };
             auto mma_block = [&](uint32_t d_tmem, bool first) {
-                mbar_wait(full_bar + 8 * stage, phase);
+                {
+                    AMP_PROF_T0;
+                    mbar_wait(full_bar + 8 * stage, phase);
+                    AMP_PROF_ADD(w_full);
+                }
                 tcgen05_fence_after();
                 const uint64_t a0 = make_kmajor_sw128_desc(smem_a + stage * A_STAGE_BYTES);
-                const uint64_t b0 = make_kmajor_sw128_desc(smem_b + stage * B_STAGE_BYTES);
+                const uint64_t b0 = make_kmajor_sw128_desc(smem_b + stage * B_BYTES);
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16(d_tmem, a0 + 2 * k, b0 + 2 * k, kInstrDesc, (uint32_t)(!first || k != 0));
-                umma_commit(empty_bar + 8 * stage);
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    if constexpr (PAIR) umma_bf16_pair(d_tmem, a0 + 2 * k, b0 + 2 * k, kInstrDescPair, (uint32_t)(!first || k != 0));
+                    else umma_bf16(d_tmem, a0 + 2 * k, b0 + 2 * k, kInstrDesc, (uint32_t)(!first || k != 0));
+                }
+                commit(empty_bar + 8 * stage);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             };
             walk_schedule(
                 T, p.n1_tiles, units,
                 [&](int, int) {
-                    mbar_wait(d1_empty, (c1 & 1) ^ 1);  // E1 has drained D1
+                    {
+                        AMP_PROF_T0;
+                        mbar_wait(d1_empty, (c1 & 1) ^ 1);  // E1 (of both CTAs) has drained D1
+                        AMP_PROF_ADD(w_d1);
+                    }
                     tcgen05_fence_after();
                     for (int kb = 0; kb < p.kb1; ++kb) mma_block(tmem_base + D1_COL, kb == 0);
-                    umma_commit(d1_full);
+                    commit(d1_full);
                     ++c1;
                 },
                 [&](int, int u) {
                     const int kb = u % kb2;
                     if (kb == 0) {
-                        mbar_wait(d2_empty, (c2 & 1) ^ 1);  // E2 has drained D2
+                        {
+                            AMP_PROF_T0;
+                            mbar_wait(d2_empty, (c2 & 1) ^ 1);  // E2 (of both CTAs) has drained D2
+                            AMP_PROF_ADD(w_d2);
+                        }
                         tcgen05_fence_after();
                     }
                     mma_block(tmem_base + D2_COL, kb == 0);
                     if (kb == kb2 - 1) {
-                        umma_commit(d2_full);
+                        commit(d2_full);
                         ++c2;
                     }
                 });
+#ifdef AMP_DISC_PROFILE
+            if (p.prof) {
+                p.prof[blockIdx.x * 8 + 0] = clock64() - t_begin;
+                p.prof[blockIdx.x * 8 + 1] = w_full;
+                p.prof[blockIdx.x * 8 + 2] = w_d1;
+                p.prof[blockIdx.x * 8 + 3] = w_d2;
+            }
+#endif
         }
-    } else if (warp < 6) {
-        // ================= E1: D1 -> bias + ReLU -> bf16 h1 slabs -> TMA store into the CTA's L2-resident slot =================
+        __syncwarp();
+    } else {
+        // ================= epilogue warps 2..9: both accumulators, columns split between the two warps of a TMEM quarter ======
+        // Warp w and warp w+4 own the same 32 TMEM lanes (rows); w takes columns [0,128) of every 256-column accumulator and
+        // w+4 takes [128,256), so each drain is half as long as with one warp per quarter -- the issuer's in-kernel cycle
+        // counters showed it waiting ~20 % of the time for D2 and ~12 % for D1 to be drained.  The warps follow the issuer's
+        // schedule: D1 tiles (bias + ReLU -> bf16 -> swizzled slab -> TMA store of h1) and, after the last K block of each
+        // layer-2 N tile, D2 (bias + ReLU -> dot with w3).  tcgen05.ld of the next 32 columns is in flight while the current
+        // 32 are processed.
+        const int ew = warp - 2;
         const int quarter = warp & 3;
+        const int colhalf = ew >> 2;
         const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-        uint32_t c1 = 0, store_it = 0;
-        for (int ti = 0; ti < T; ++ti) {
-            const int row0 = slot_row0 + (ti & 1) * BM + quarter * 32;
-            for (int nt = 0; nt < p.n1_tiles; ++nt) {
+        const uint32_t col_base = (uint32_t)(colhalf * (BN / 2));
+        float *part = reinterpret_cast<float *>(smem_raw + (part_smem - smem_u32(smem_raw)));  // [2][4][32] partial dots
+        uint32_t c1 = 0, c2 = 0, store_it = 0;
+        float dot[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        walk_schedule(
+            T, p.n1_tiles, units,
+            [&](int ti, int nt) {
+                // ---- D1 (ti, nt): this warp's 128 columns = two 64-column slabs ----
+                const int row0 = slot_row0 + (ti & 1) * BM + quarter * 32;
                 mbar_wait(d1_full, c1 & 1);
                 tcgen05_fence_after();
-#pragma unroll 1
-                for (int cb = 0; cb < BN / BK; ++cb) {
-                    const uint32_t slab = staging + (uint32_t)((quarter * 2 + (store_it & 1)) * STORE_SLAB_BYTES);
-                    if (lane == 0) bulk_wait_read<1>();
-                    __syncwarp();
+                uint32_t v[2][32];
+                tmem_ld_32x32(tmem_base + lane_base + D1_COL + col_base, v[0]);
+                uint32_t slab = 0;
 #pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        uint32_t v[32];
-                        tmem_ld_32x32(tmem_base + lane_base + D1_COL + (uint32_t)(cb * BK + half * 32), v);
-                        tmem_ld_wait();
-                        const float4 *bias4 = reinterpret_cast<const float4 *>(p.b1 + nt * BN + cb * BK + half * 32);
+                for (int h = 0; h < 4; ++h) {
+                    const int half = h & 1;
+                    const int col = nt * BN + (int)col_base + h * 32;  // h1 column of this step
+                    const float4 *bias4 = reinterpret_cast<const float4 *>(p.b1 + col);
+                    float4 bb[8];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float4 b0 = __ldg(bias4 + 2 * j), b1v = __ldg(bias4 + 2 * j + 1);
-                            const __nv_bfloat162 p0 = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[8 * j + 0]) + b0.x, 0.0f),
-                                                                            fmaxf(__uint_as_float(v[8 * j + 1]) + b0.y, 0.0f));
-                            const __nv_bfloat162 p1 = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[8 * j + 2]) + b0.z, 0.0f),
-                                                                            fmaxf(__uint_as_float(v[8 * j + 3]) + b0.w, 0.0f));
-                            const __nv_bfloat162 p2 = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[8 * j + 4]) + b1v.x, 0.0f),
-                                                                            fmaxf(__uint_as_float(v[8 * j + 5]) + b1v.y, 0.0f));
-                            const __nv_bfloat162 p3 = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[8 * j + 6]) + b1v.z, 0.0f),
-                                                                            fmaxf(__uint_as_float(v[8 * j + 7]) + b1v.w, 0.0f));
-                            const int chunk = (half * 4 + j) ^ (lane & 7);
-                            st_shared_v4(slab + (uint32_t)(lane * 128 + chunk * 16), *reinterpret_cast<const uint32_t *>(&p0),
-                                         *reinterpret_cast<const uint32_t *>(&p1), *reinterpret_cast<const uint32_t *>(&p2),
-                                         *reinterpret_cast<const uint32_t *>(&p3));
-                        }
+                    for (int j = 0; j < 8; ++j) bb[j] = __ldg(bias4 + j);
+                    if (half == 0) {
+                        slab = staging + (uint32_t)((ew * 2 + (store_it & 1)) * STORE_SLAB_BYTES);
+                        if (lane == 0) bulk_wait_read<1>();  // the store that last read this slab has drained it
+                        __syncwarp();
                     }
-                    if (cb == BN / BK - 1) {  // last TMEM read of this accumulator: release D1 to the issuer early
+                    tmem_ld_wait();  // v[h & 1] has landed
+                    if (h + 1 < 4) {
+                        tmem_ld_32x32(tmem_base + lane_base + D1_COL + col_base + (uint32_t)((h + 1) * 32), v[(h + 1) & 1]);
+                    } else {  // last TMEM read of this accumulator by this warp: release D1 to the issuer now
                         tcgen05_fence_before();
-                        mbar_arrive(d1_empty);
+                        __syncwarp();
+                        if (lane == 0) arrive_drained(d1_empty_at_leader);
                     }
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) {
-                        tma_store_2d(&tmap_h_store, slab, nt * BN + cb * BK, row0);
-                        bulk_commit();
+                    const uint32_t(&cur)[32] = v[h & 1];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {  // 16-byte chunk (half*4 + j) of this thread's 128-byte slab row
+                        const float4 b0 = bb[2 * j], b1v = bb[2 * j + 1];
+                        const __nv_bfloat162 p0 = __floats2bfloat162_rn(fmaxf(__uint_as_float(cur[8 * j + 0]) + b0.x, 0.0f),
+                                                                        fmaxf(__uint_as_float(cur[8 * j + 1]) + b0.y, 0.0f));
+                        const __nv_bfloat162 p1 = __floats2bfloat162_rn(fmaxf(__uint_as_float(cur[8 * j + 2]) + b0.z, 0.0f),
+                                                                        fmaxf(__uint_as_float(cur[8 * j + 3]) + b0.w, 0.0f));
+                        const __nv_bfloat162 p2 = __floats2bfloat162_rn(fmaxf(__uint_as_float(cur[8 * j + 4]) + b1v.x, 0.0f),
+                                                                        fmaxf(__uint_as_float(cur[8 * j + 5]) + b1v.y, 0.0f));
+                        const __nv_bfloat162 p3 = __floats2bfloat162_rn(fmaxf(__uint_as_float(cur[8 * j + 6]) + b1v.z, 0.0f),
+                                                                        fmaxf(__uint_as_float(cur[8 * j + 7]) + b1v.w, 0.0f));
+                        const int chunk = (half * 4 + j) ^ (lane & 7);  // SWIZZLE_128B: chunk index XOR (row % 8)
+                        st_shared_v4(slab + (uint32_t)(lane * 128 + chunk * 16), *reinterpret_cast<const uint32_t *>(&p0),
+                                     *reinterpret_cast<const uint32_t *>(&p1), *reinterpret_cast<const uint32_t *>(&p2),
+                                     *reinterpret_cast<const uint32_t *>(&p3));
                     }
-                    ++store_it;
+                    if (half == 1) {
+                        fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA (async proxy)
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&tmap_h_store, slab, col - 32, row0);
+                            bulk_commit();
+                        }
+                        ++store_it;
+                    }
                 }
                 ++c1;
-            }
-            if (lane == 0) {  // this warp's 32 rows of h1 are complete in the workspace
-                bulk_wait_all();
-                mbar_arrive(h1_ready + 8 * (ti & 1));
-            }
-        }
-    } else {
-        // ================= E2: D2 -> bias + ReLU -> running dot with w3 -> logit -> reward =================
-        const int quarter = warp & 3;
-        const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-        uint32_t c2 = 0;
-        for (int ti = 0; ti < T; ++ti) {
-            const int m = (int)blockIdx.x + ti * (int)gridDim.x;
-            const int row = m * BM + quarter * 32 + lane;
-            float dot = 0.0f;
-            for (int n2 = 0; n2 < p.n2_tiles; ++n2) {
+                if (nt == p.n1_tiles - 1 && lane == 0) {  // this warp's part of h1(ti) is complete in the workspace
+                    bulk_wait_all();
+                    mbar_arrive(h1_ready + 8 * (ti & 1));
+                }
+            },
+            [&](int ti, int u) {
+                const int n2 = u / kb2;
+                if (u - n2 * kb2 != kb2 - 1) return;  // D2 (ti, n2) is complete after the last K block of the N tile
+                // ---- D2 (ti, n2): this warp's 128 columns ----
                 mbar_wait(d2_full, c2 & 1);
                 tcgen05_fence_after();
-#pragma unroll 1
-                for (int chunk = 0; chunk < BN / 32; ++chunk) {
-                    uint32_t v[32];
-                    tmem_ld_32x32(tmem_base + lane_base + D2_COL + (uint32_t)(chunk * 32), v);
-                    tmem_ld_wait();
-                    const int col0 = n2 * BN + chunk * 32;
+                uint32_t v[2][32];
+                tmem_ld_32x32(tmem_base + lane_base + D2_COL + col_base, v[0]);
+#pragma unroll
+                for (int chunk = 0; chunk < 4; ++chunk) {
+                    const int col0 = n2 * BN + (int)col_base + chunk * 32;
                     const float4 *bias4 = reinterpret_cast<const float4 *>(p.b2 + col0);
                     const float4 *w4 = reinterpret_cast<const float4 *>(p.w3 + col0);
+                    float4 bb[8], ww[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const float4 bb = __ldg(bias4 + j), ww = __ldg(w4 + j);
-                        dot = fmaf(fmaxf(__uint_as_float(v[4 * j + 0]) + bb.x, 0.0f), ww.x, dot);
-                        dot = fmaf(fmaxf(__uint_as_float(v[4 * j + 1]) + bb.y, 0.0f), ww.y, dot);
-                        dot = fmaf(fmaxf(__uint_as_float(v[4 * j + 2]) + bb.z, 0.0f), ww.z, dot);
-                        dot = fmaf(fmaxf(__uint_as_float(v[4 * j + 3]) + bb.w, 0.0f), ww.w, dot);
+                        bb[j] = __ldg(bias4 + j);
+                        ww[j] = __ldg(w4 + j);
+                    }
+                    tmem_ld_wait();  // v[chunk & 1] has landed
+                    if (chunk + 1 < 4) {
+                        tmem_ld_32x32(tmem_base + lane_base + D2_COL + col_base + (uint32_t)((chunk + 1) * 32), v[(chunk + 1) & 1]);
+                    } else {  // last TMEM read: hand D2 back before finishing the arithmetic
+                        tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) arrive_drained(d2_empty_at_leader);
+                    }
+                    const uint32_t(&cur)[32] = v[chunk & 1];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        dot[0] = fmaf(fmaxf(__uint_as_float(cur[4 * j + 0]) + bb[j].x, 0.0f), ww[j].x, dot[0]);
+                        dot[1] = fmaf(fmaxf(__uint_as_float(cur[4 * j + 1]) + bb[j].y, 0.0f), ww[j].y, dot[1]);
+                        dot[2] = fmaf(fmaxf(__uint_as_float(cur[4 * j + 2]) + bb[j].z, 0.0f), ww[j].z, dot[2]);
+                        dot[3] = fmaf(fmaxf(__uint_as_float(cur[4 * j + 3]) + bb[j].w, 0.0f), ww[j].w, dot[3]);
                     }
                 }
-                tcgen05_fence_before();
-                mbar_arrive(d2_empty);
                 ++c2;
-            }
-            if (row < p.M) {
-                const float logit = dot + __ldg(p.b3);
-                if (p.logits) p.logits[row] = logit;
-                p.reward[row] = style_reward(logit, p.scale);
-            }
-        }
+                if (n2 == p.n2_tiles - 1) {
+                    // combine the two column halves of this row: the upper-half warp hands its partial sum over through
+                    // shared memory (double-buffered by tile parity), a 64-thread named barrier orders the exchange
+                    const float mine = (dot[0] + dot[1]) + (dot[2] + dot[3]);
+                    float *slot = part + ((ti & 1) * 4 + quarter) * 32 + lane;
+                    if (colhalf == 1) *slot = mine;
+                    asm volatile("bar.sync %0, 64;" ::"r"(8 + quarter) : "memory");
+                    if (colhalf == 0) {
+                        const int row = tile_of(ti) * BM + quarter * 32 + lane;
+                        if (row < p.M) {
+                            const float logit = (mine + *slot) + __ldg(p.b3);
+                            if (p.logits) p.logits[row] = logit;
+                            p.reward[row] = style_reward(logit, p.scale);
+                        }
+                    }
+                    dot[0] = dot[1] = dot[2] = dot[3] = 0.0f;
+                }
+            });
     }
 
     tcgen05_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
     if (warp == 1) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        if constexpr (PAIR)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -559,7 +749,10 @@ struct amp_disc {
     cudaStream_t side;            // the scaler/cast of chunk i+1 runs here, under the fused kernel of chunk i
     cudaEvent_t ev_start, ev_ready[2], ev_free[2];
     CUtensorMap tmap_w1, tmap_w2; // weights never move: encoded once
+    CUtensorMap tmap_w1_half, tmap_w2_half; // 128-row boxes: each CTA of a pair stages its half of a 256-row weight block
     CUtensorMap tmap_h_load, tmap_h_store;  // h1 workspace: 128-row loads, 32-row epilogue slab stores
+    long long *prof;                        // AMP_DISC_PROFILE builds: device counters (ws_ctas x 8)
+    bool use_pair;                          // CTA-pair (cta_group::2) kernel; AMP_B200_DISC_SINGLE_CTA=1 selects the 1-CTA kernel
     bool loaded;
 };
 
@@ -620,11 +813,20 @@ int amp_disc_create(int32_t in_features, int32_t h1, int32_t h2, int64_t max_row
     }
     int rc = make_tmap(&d->tmap_w1, d->W1, h1, d->Kp, d->Kp, BN);
     if (rc == AMP_OK) rc = make_tmap(&d->tmap_w2, d->W2, h2, h1, h1, BN);
+    if (rc == AMP_OK) rc = make_tmap(&d->tmap_w1_half, d->W1, h1, d->Kp, d->Kp, BN / 2);
+    if (rc == AMP_OK) rc = make_tmap(&d->tmap_w2_half, d->W2, h2, h1, h1, BN / 2);
     if (rc == AMP_OK) rc = make_tmap(&d->tmap_h_load, d->hid, (int64_t)d->ws_ctas * 2 * BM, h1, h1, BM);
     if (rc == AMP_OK) rc = make_tmap(&d->tmap_h_store, d->hid, (int64_t)d->ws_ctas * 2 * BM, h1, h1, 32);
     if (rc == AMP_OK) {
-        e = cudaFuncSetAttribute(disc_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM_BYTES);
+        e = cudaFuncSetAttribute(disc_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_smem_bytes(false));
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(disc_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_smem_bytes(true));
         if (e != cudaSuccess) rc = cuda_fail(e, "cudaFuncSetAttribute(disc_fused_kernel)");
+    #ifdef AMP_DISC_PROFILE
+        if (cudaMalloc((void **)&d->prof, (size_t)d->ws_ctas * 8 * sizeof(long long)) != cudaSuccess) d->prof = nullptr;
+#endif
+        const char *single = getenv("AMP_B200_DISC_SINGLE_CTA");
+        d->use_pair = !(single && single[0] == '1');
     }
     if (rc != AMP_OK) {
         amp_disc_destroy(d);
@@ -730,10 +932,50 @@ int amp_disc_style_reward(amp_disc_t *d, const float *x, int64_t x_stride, int64
         fp.scale = reward_scale;
         fp.reward = reward + r0;
         fp.logits = logits ? logits + r0 : nullptr;
-        disc_fused_kernel<<<grid, FUSED_THREADS, FUSED_SMEM_BYTES, st>>>(tm_x, d->tmap_w1, d->tmap_h_load, d->tmap_h_store, d->tmap_w2, fp);
+        fp.prof = d->prof;
+        if (d->use_pair && m_tiles >= 2) {
+            // CTA pairs: an even grid of at most ws_ctas CTAs, launched as clusters of 2
+            const int pair_blocks = (m_tiles + 1) / 2;
+            const int clusters = std::min(pair_blocks, std::min(sms, d->ws_ctas) / 2);
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(2 * clusters);
+            cfg.blockDim = dim3(FUSED_THREADS);
+            cfg.dynamicSmemBytes = fused_smem_bytes(true);
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            AMP_CUDA_TRY(cudaLaunchKernelEx(&cfg, disc_fused_kernel<true>, tm_x, d->tmap_w1_half, d->tmap_h_load, d->tmap_h_store,
+                                            d->tmap_w2_half, fp));
+        } else {
+            disc_fused_kernel<false><<<grid, FUSED_THREADS, fused_smem_bytes(false), st>>>(tm_x, d->tmap_w1, d->tmap_h_load,
+                                                                                           d->tmap_h_store, d->tmap_w2, fp);
+        }
         AMP_CUDA_TRY(cudaGetLastError());
         if (overlap) AMP_CUDA_TRY(cudaEventRecord(d->ev_free[b], st));
     }
+#ifdef AMP_DISC_PROFILE
+    if (d->prof) {  // developer build: dump the wait breakdown of the LAST chunk (synchronises!)
+        static long long host[1024 * 8];
+        cudaStreamSynchronize(st);
+        const int n = std::min(d->ws_ctas, 1024);
+        cudaMemcpy(host, d->prof, (size_t)n * 8 * sizeof(long long), cudaMemcpyDeviceToHost);
+        double acc[8] = {0};
+        int cnt = 0;
+        for (int i = 0; i < n; ++i) {
+            if (host[i * 8 + 0] <= 0) continue;
+            ++cnt;
+            for (int k = 0; k < 8; ++k) acc[k] += (double)host[i * 8 + k];
+        }
+        if (cnt)
+            fprintf(stderr, "[amp_disc profile] issuer CTAs=%d total=%.0f wait_full=%.0f wait_d1_empty=%.0f wait_d2_empty=%.0f | producer(all) wait_empty=%.0f wait_h1=%.0f (cycles, mean per CTA)\n",
+                    cnt, acc[0] / cnt, acc[1] / cnt, acc[2] / cnt, acc[3] / cnt, acc[4] / n, acc[5] / n);
+    }
+#endif
     return AMP_OK;
 }
 
