@@ -108,38 +108,72 @@ __global__ void frame_blend_kernel(LibView v, const double *__restrict__ times, 
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// amp_sample_full: one warp per output frame; lanes stride the columns of each of the six tensors.
+// amp_sample_full: a warp owns 32 consecutive output frames.
+//   phase 1  one lane per frame does the float64 index math (instead of every lane repeating it for one frame);
+//   phase 2  for each of the six tensors the warp walks the tile's elements FLAT (element e -> frame e / width, column
+//            e % width, by multiply-high with a precomputed reciprocal), so all 32 lanes are busy whatever the row width
+//            (a 33-float body_positions row would otherwise leave half of the second pass idle, an 11-quaternion
+//            body_rotations row two thirds of the slerp lanes) and the stores of a tile are one contiguous run.
 // ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void lerp_row(const float *__restrict__ src, int64_t i0, int64_t i1, int width, float omb,
-                                         float b, float *__restrict__ dst, int lane) {
-    const float *a = src + i0 * width, *c = src + i1 * width;
-    for (int j = lane; j < width; j += 32) __stcs(dst + j, lerp_w(omb, b, __ldg(a + j), __ldg(c + j)));
+constexpr int kSampleWarps = 8;
+
+struct SampleDivisors {
+    uint32_t dof, body3, body;  // ceil(2^32 / width) for width = D, 3B, B
+};
+
+__device__ __forceinline__ void lerp_tile(const float *__restrict__ src, float *__restrict__ dst, int width, uint32_t magic,
+                                          int nf, const int *s_i0, const int *s_i1, const float *s_b, int lane) {
+    const int total = nf * width;
+#pragma unroll 4
+    for (int e = lane; e < total; e += 32) {
+        const int fl = (int)__umulhi((uint32_t)e, magic);  // e / width, exact for e < 2^32 / width
+        const int c = e - fl * width;
+        const float b = s_b[fl];
+        const float a0 = __ldg(src + (int64_t)s_i0[fl] * width + c), a1 = __ldg(src + (int64_t)s_i1[fl] * width + c);
+        __stcs(dst + e, lerp(b, a0, a1));
+    }
 }
 
-__global__ void __launch_bounds__(256) sample_full_kernel(LibView v, const double *__restrict__ times,
-                                                           const int64_t *__restrict__ ids, int64_t S,
-                                                           float *__restrict__ dof_pos, float *__restrict__ dof_vel,
-                                                           float *__restrict__ body_pos, float *__restrict__ body_rot,
-                                                           float *__restrict__ body_lin, float *__restrict__ body_ang) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+__global__ void __launch_bounds__(kSampleWarps * 32) sample_full_kernel(LibView v, SampleDivisors dv,
+                                                                         const double *__restrict__ times,
+                                                                         const int64_t *__restrict__ ids, int64_t S,
+                                                                         float *__restrict__ dof_pos, float *__restrict__ dof_vel,
+                                                                         float *__restrict__ body_pos, float *__restrict__ body_rot,
+                                                                         float *__restrict__ body_lin, float *__restrict__ body_ang) {
+    __shared__ int s_i0_all[kSampleWarps][32], s_i1_all[kSampleWarps][32];
+    __shared__ float s_b_all[kSampleWarps][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int *s_i0 = s_i0_all[warp], *s_i1 = s_i1_all[warp];
+    float *s_b = s_b_all[warp];
     const int D = v.num_dofs, B = v.num_bodies;
-    for (int64_t f = warp; f < S; f += nwarps) {
-        // every lane evaluates the same scalar index math (identical inputs -> identical result, no shuffle needed)
-        const FrameBlend fb = lookup_frame(v, times[f], ids ? ids[f] : 0);
-        const float b = __double2float_rn(fb.blend), omb = __fsub_rn(1.0f, b);
-        if (dof_pos) lerp_row(v.dof_pos, fb.i0, fb.i1, D, omb, b, dof_pos + f * D, lane);
-        if (dof_vel) lerp_row(v.dof_vel, fb.i0, fb.i1, D, omb, b, dof_vel + f * D, lane);
-        if (body_pos) lerp_row(v.body_pos, fb.i0, fb.i1, B * 3, omb, b, body_pos + f * B * 3, lane);
-        if (body_lin) lerp_row(v.body_lin, fb.i0, fb.i1, B * 3, omb, b, body_lin + f * B * 3, lane);
-        if (body_ang) lerp_row(v.body_ang, fb.i0, fb.i1, B * 3, omb, b, body_ang + f * B * 3, lane);
-        if (body_rot) {
-            const float4 *q0 = reinterpret_cast<const float4 *>(v.body_rot) + fb.i0 * B;
-            const float4 *q1 = reinterpret_cast<const float4 *>(v.body_rot) + fb.i1 * B;
-            float4 *o = reinterpret_cast<float4 *>(body_rot) + f * B;
-            for (int j = lane; j < B; j += 32) __stcs(o + j, slerp(__ldg(q0 + j), __ldg(q1 + j), b));
+    const int64_t num_tiles = (S + 31) / 32;
+    for (int64_t tile = blockIdx.x * (int64_t)kSampleWarps + warp; tile < num_tiles; tile += (int64_t)gridDim.x * kSampleWarps) {
+        const int64_t f0 = tile * 32;
+        const int nf = (int)min((int64_t)32, S - f0);
+        if (lane < nf) {
+            const FrameBlend fb = lookup_frame(v, times[f0 + lane], ids ? ids[f0 + lane] : 0);
+            s_i0[lane] = (int)fb.i0;
+            s_i1[lane] = (int)fb.i1;
+            s_b[lane] = __double2float_rn(fb.blend);
         }
+        __syncwarp();
+        if (dof_pos) lerp_tile(v.dof_pos, dof_pos + f0 * D, D, dv.dof, nf, s_i0, s_i1, s_b, lane);
+        if (dof_vel) lerp_tile(v.dof_vel, dof_vel + f0 * D, D, dv.dof, nf, s_i0, s_i1, s_b, lane);
+        if (body_pos) lerp_tile(v.body_pos, body_pos + f0 * B * 3, B * 3, dv.body3, nf, s_i0, s_i1, s_b, lane);
+        if (body_lin) lerp_tile(v.body_lin, body_lin + f0 * B * 3, B * 3, dv.body3, nf, s_i0, s_i1, s_b, lane);
+        if (body_ang) lerp_tile(v.body_ang, body_ang + f0 * B * 3, B * 3, dv.body3, nf, s_i0, s_i1, s_b, lane);
+        if (body_rot) {
+            const float4 *rot = reinterpret_cast<const float4 *>(v.body_rot);
+            float4 *o = reinterpret_cast<float4 *>(body_rot) + f0 * B;
+            const int total = nf * B;
+#pragma unroll 2
+            for (int e = lane; e < total; e += 32) {
+                const int fl = (int)__umulhi((uint32_t)e, dv.body);
+                const int j = e - fl * B;
+                __stcs(o + e, slerp(__ldg(rot + (int64_t)s_i0[fl] * B + j), __ldg(rot + (int64_t)s_i1[fl] * B + j), s_b[fl]));
+            }
+        }
+        __syncwarp();
     }
 }
 
@@ -368,9 +402,12 @@ __global__ void tangent_normal_kernel(const float *__restrict__ q, int64_t n, fl
     }
 }
 
-// One warp per env.  Column c of env i: build the new observation value from simulator state, move history slot
-// s -> s+1 for s = K-2 .. 0 (oldest first, so nothing is overwritten before it is read; every lane touches only its
-// own column, so no cross-lane hazard), then write slot 0.  Reference g1_amp_env.py:176-193.
+// One warp per env, lane l owns columns l, l+32, ...  Which simulator tensor feeds a column does not depend on the env, so
+// every slot gets a (pointer, per-env stride) pair once and the env loop is: issue all state loads and all history loads,
+// then all stores.  History: slot s -> s+1 for s = K-2 .. 0 (oldest first, eight slots per trip: nothing is overwritten
+// before it is read; a lane touches only its own columns, so there is no cross-lane hazard), then slot 0 = the new row.
+// Reference g1_amp_env.py:176-193.
+template <int NSLOT>
 __global__ void __launch_bounds__(256)
 obs_step_kernel(const float *__restrict__ joint_pos, const float *__restrict__ joint_vel,
                 const float *__restrict__ body_pos, const float *__restrict__ body_quat,
@@ -381,37 +418,66 @@ obs_step_kernel(const float *__restrict__ joint_pos, const float *__restrict__ j
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int D2 = 2 * D, A = D2 + 13 + 3 * Kb, policy_width = A - 3 * Kb;
+
+    const float *src[NSLOT], *sub[NSLOT];  // value = src[i*stride] (- sub[i*3*Bsim] for key-body columns)
+    int64_t stride[NSLOT];
+    int tn_idx[NSLOT];                     // >= 0: the column is tangent/normal component tn_idx
+    bool active[NSLOT];
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) {
+        const int c = lane + 32 * s;
+        active[s] = c < A;
+        tn_idx[s] = -1;
+        sub[s] = nullptr;
+        src[s] = joint_pos;
+        stride[s] = 0;
+        if (c < D) { src[s] = joint_pos + c; stride[s] = D; }
+        else if (c < D2) { src[s] = joint_vel + (c - D); stride[s] = D; }
+        else if (c == D2) { src[s] = body_pos + ref * 3 + 2; stride[s] = (int64_t)Bsim * 3; }
+        else if (c < D2 + 7) { tn_idx[s] = c - D2 - 1; }
+        else if (c < D2 + 10) { src[s] = body_lin + ref * 3 + (c - D2 - 7); stride[s] = (int64_t)Bsim * 3; }
+        else if (c < D2 + 13) { src[s] = body_ang + ref * 3 + (c - D2 - 10); stride[s] = (int64_t)Bsim * 3; }
+        else if (c < A) {
+            const int e = c - D2 - 13, j = e / 3, a = e - 3 * j;
+            src[s] = body_pos + keys.k[j] * 3 + a;
+            sub[s] = body_pos + ref * 3 + a;
+            stride[s] = (int64_t)Bsim * 3;
+        }
+    }
+
     for (int64_t i = warp; i < N; i += nwarps) {
-        const int64_t rb = i * Bsim + ref;
-        const float4 q = __ldg(reinterpret_cast<const float4 *>(body_quat) + rb);
+        const float4 q = __ldg(reinterpret_cast<const float4 *>(body_quat) + i * Bsim + ref);
+        float val[NSLOT], minus[NSLOT];
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) {
+            val[s] = (active[s] && tn_idx[s] < 0) ? __ldg(src[s] + i * stride[s]) : 0.0f;
+            minus[s] = sub[s] ? __ldg(sub[s] + i * stride[s]) : 0.0f;
+        }
+        float *env = amp_buf + i * (int64_t)K * A + lane;
+        // history shift, oldest slots first, up to eight slots per trip with all loads ahead of the stores
+        for (int hi = K - 2; hi >= 0; hi -= 8) {
+            const int lo = max(hi - 7, 0);
+            float h[8][NSLOT];
+#pragma unroll
+            for (int t = 0; t < 8; ++t)
+#pragma unroll
+                for (int s = 0; s < NSLOT; ++s)
+                    if (hi - t >= lo && active[s]) h[t][s] = env[(int64_t)(hi - t) * A + 32 * s];
+#pragma unroll
+            for (int t = 0; t < 8; ++t)
+#pragma unroll
+                for (int s = 0; s < NSLOT; ++s)
+                    if (hi - t >= lo && active[s]) env[(int64_t)(hi - t + 1) * A + 32 * s] = h[t][s];
+        }
         float tn[6];
         tangent_normal(q, tn);
-        float *env = amp_buf + i * (int64_t)K * A;
-        for (int c = lane; c < A; c += 32) {
-            float val;
-            if (c < D) val = __ldg(joint_pos + i * D + c);
-            else if (c < D2) val = __ldg(joint_vel + i * D + c - D);
-            else if (c == D2) val = __ldg(body_pos + rb * 3 + 2);
-            else if (c < D2 + 7) val = pick6(tn, c - D2 - 1);
-            else if (c < D2 + 10) val = __ldg(body_lin + rb * 3 + c - D2 - 7);
-            else if (c < D2 + 13) val = __ldg(body_ang + rb * 3 + c - D2 - 10);
-            else {
-                const int e = c - D2 - 13, j = e / 3, a = e - 3 * j;
-                val = __fsub_rn(__ldg(body_pos + (i * Bsim + keys.k[j]) * 3 + a), __ldg(body_pos + rb * 3 + a));
-            }
-            float *col = env + c;
-            int s = K - 2;
-            for (; s >= 3; s -= 4) {  // four slots per trip: all loads issued before the stores
-                const float a0 = col[(int64_t)s * A], a1 = col[(int64_t)(s - 1) * A];
-                const float a2 = col[(int64_t)(s - 2) * A], a3 = col[(int64_t)(s - 3) * A];
-                col[(int64_t)(s + 1) * A] = a0;
-                col[(int64_t)s * A] = a1;
-                col[(int64_t)(s - 1) * A] = a2;
-                col[(int64_t)(s - 2) * A] = a3;
-            }
-            for (; s >= 0; --s) col[(int64_t)(s + 1) * A] = col[(int64_t)s * A];
-            col[0] = val;
-            if (policy_obs && c < policy_width) policy_obs[i * policy_stride + c] = val;
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) {
+            if (!active[s]) continue;
+            float r = sub[s] ? __fsub_rn(val[s], minus[s]) : val[s];
+            if (tn_idx[s] >= 0) r = pick6(tn, tn_idx[s]);
+            env[32 * s] = r;
+            if (policy_obs && lane + 32 * s < policy_width) policy_obs[i * policy_stride + lane + 32 * s] = r;
         }
     }
 }
@@ -576,8 +642,12 @@ int amp_sample_full(amp_lib_t *lib, const double *times, const int64_t *ids, int
     if (S == 0) return AMP_OK;
     AMP_REQUIRE(times, "amp_sample_full: NULL times");
     AMP_REQUIRE(!body_rot || aligned16(body_rot), "amp_sample_full: body_rot output must be 16-byte aligned");
-    sample_full_kernel<<<grid_for(S, 8, 8), 256, 0, as_stream(stream)>>>(lib->v, times, ids, S, dof_pos, dof_vel,
-                                                                         body_pos, body_rot, body_lin, body_ang);
+    AMP_REQUIRE(lib->v.num_frames < ((int64_t)1 << 31), "amp_sample_full: more than 2^31 frames");
+    AMP_REQUIRE(lib->v.num_bodies * 3 < 4096 && lib->v.num_dofs < 4096, "amp_sample_full: row wider than 4096 floats");
+    auto magic = [](int w) { return (uint32_t)((((uint64_t)1 << 32) + (uint64_t)w - 1) / (uint64_t)w); };
+    SampleDivisors dv{magic(lib->v.num_dofs), magic(lib->v.num_bodies * 3), magic(lib->v.num_bodies)};
+    sample_full_kernel<<<grid_for((S + 31) / 32, kSampleWarps, 8), kSampleWarps * 32, 0, as_stream(stream)>>>(
+        lib->v, dv, times, ids, S, dof_pos, dof_vel, body_pos, body_rot, body_lin, body_ang);
     AMP_CUDA_TRY(cudaGetLastError());
     return AMP_OK;
 }
@@ -725,9 +795,23 @@ int amp_obs_step(const float *joint_pos, const float *joint_vel, const float *bo
     }
     const int A = 2 * D + 13 + 3 * Kb;
     AMP_REQUIRE(!policy_obs || policy_stride >= A - 3 * Kb, "amp_obs_step: policy_stride too small");
-    obs_step_kernel<<<grid_for(N, 8, 8), 256, 0, as_stream(stream)>>>(joint_pos, joint_vel, body_pos_w, body_quat_w,
-                                                                      body_lin_vel_w, body_ang_vel_w, N, D, Bsim, ref_body,
-                                                                      keys, Kb, K, amp_buf, policy_obs, policy_stride);
+    const int grid = grid_for(N, 8, 8);
+    cudaStream_t st = as_stream(stream);
+#define AMP_LAUNCH_STEP(NS)                                                                                              \
+    obs_step_kernel<NS><<<grid, 256, 0, st>>>(joint_pos, joint_vel, body_pos_w, body_quat_w, body_lin_vel_w, body_ang_vel_w, \
+                                              N, D, Bsim, ref_body, keys, Kb, K, amp_buf, policy_obs, policy_stride)
+    switch ((A + 31) / 32) {
+        case 1: AMP_LAUNCH_STEP(1); break;
+        case 2: AMP_LAUNCH_STEP(2); break;
+        case 3: AMP_LAUNCH_STEP(3); break;
+        case 4: AMP_LAUNCH_STEP(4); break;
+        case 5: AMP_LAUNCH_STEP(5); break;
+        case 6: AMP_LAUNCH_STEP(6); break;
+        case 7: AMP_LAUNCH_STEP(7); break;
+        case 8: AMP_LAUNCH_STEP(8); break;
+        default: return fail(AMP_EINVAL, "amp_obs_step: observation width %d > 256 is not supported", A);
+    }
+#undef AMP_LAUNCH_STEP
     AMP_CUDA_TRY(cudaGetLastError());
     return AMP_OK;
 }

@@ -1,0 +1,120 @@
+#!/usr/bin/env python
+"""Per-entry-point micro-benchmark: achieved algorithmic GB/s (or TFLOP/s) of every kernel of the path at sizes larger than
+the 126 MB L2, CUDA events on the launching stream, 3 warm-ups + median of 10.  Output goes to profiles/."""
+
+from __future__ import annotations
+
+import json
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import bench  # noqa: E402
+import humanoid_amp_b200 as amp  # noqa: E402
+from humanoid_amp_b200.synthetic import skrl_style_discriminator_params, synthetic_sim_state  # noqa: E402
+
+PEAKS = bench.measured_peaks()
+DEV = torch.device("cuda", 0)
+
+
+def timed(fn, reps=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts))
+
+
+def row(name, ms, nbytes=None, flops=None, note=""):
+    out = {"kernel": name, "ms": round(ms, 4), "note": note}
+    if nbytes is not None:
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        out.update(algorithmic_MB=round(nbytes / 1e6, 1), GBps=round(gbs, 1), hbm_frac=round(gbs / PEAKS["hbm_gbs"], 3))
+    if flops is not None:
+        tf = flops / (ms * 1e-3) / 1e12
+        out.update(GFLOP=round(flops / 1e9, 1), TFLOPs=round(tf, 1), tensor_frac_sustained=round(tf / PEAKS["bf16_sustained"], 3))
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    tmp = tempfile.TemporaryDirectory()
+    loaders = {c: amp.MotionLoader(bench.make_clip_files(tmp.name, c), DEV) for c in ("G1_walk", "G1_dance", "pooled_humanoid")}
+
+    # ---- frame_blend ------------------------------------------------------------------------------------------------
+    ld = loaders["G1_walk"]
+    S = 8_000_000
+    ids_h, t_h = bench.host_inputs(ld.durations, S, 1)
+    t_d, i_d = torch.from_numpy(t_h).to(DEV), torch.from_numpy(ids_h).to(DEV)
+    ms = timed(lambda: ld.compute_frame_blend_device(t_d, i_d))
+    row("frame_blend_kernel", ms, S * (16 + 8 + 8 + 4), note=f"S={S}, f64 index math, i64 idx0/idx1 + f32 blend out")
+
+    # ---- sample_full (all bodies) -------------------------------------------------------------------------------------
+    for clip, S in (("G1_dance", 400_000), ("G1_walk", 1_500_000)):
+        ld = loaders[clip]
+        ids_h, t_h = bench.host_inputs(ld.durations, S, 2)
+        t_d, i_d = torch.from_numpy(t_h).to(DEV), torch.from_numpy(ids_h).to(DEV)
+        per = (2 * ld.num_dofs + 13 * ld.num_bodies) * 4
+        ms = timed(lambda: ld.sample(S, times=t_d, motion_ids=i_d))
+        row("sample_full_kernel", ms, S * (per + 16), note=f"{clip} S={S} ({per} B/frame out, incl. torch.empty of 6 outputs)")
+
+    # ---- fused collect -------------------------------------------------------------------------------------------------
+    for clip, n, K in (("G1_walk", 1_000_000, 2), ("G1_dance", 100_000, 10), ("pooled_humanoid", 1_000_000, 2), ("G1_walk", 4096, 2), ("G1_dance", 4096, 10)):
+        ld = loaders[clip]
+        robot = amp.robot_for_clip(ld.dof_names)
+        env = amp.AmpEnvPath(amp.AmpEnvCfg(motion_file="", num_envs=1, num_amp_observations=K, robot=robot), DEV, motion_loader=ld)
+        ids_h, t_h = bench.host_inputs(ld.durations, n, 3)
+        t_d, i_d = torch.from_numpy(t_h).to(DEV), torch.from_numpy(ids_h).to(DEV)
+        A = robot.amp_observation_space
+        out = torch.empty((n, K * A), device=DEV)
+        ms = timed(lambda: env.collect_reference_motions(n, t_d, i_d, out=out))
+        nbytes = n * K * A * 4 + n * 16 + ld.num_frames * ((A + 3) // 4 * 4) * 4
+        row("collect_reference_kernel", ms, nbytes, note=f"{clip} n={n} K={K} (table {ld.num_frames * ((A + 3) // 4 * 4) * 4 / 1e3:.0f} KB)")
+
+    # ---- env step --------------------------------------------------------------------------------------------------------
+    for n, K in ((1_000_000, 2), (65_536, 10), (4096, 10)):
+        ld = loaders["G1_dance"]
+        env = amp.AmpEnvPath(amp.AmpEnvCfg(motion_file="", num_envs=n, num_amp_observations=K, robot=amp.G1), DEV, motion_loader=ld)
+        state = synthetic_sim_state(n, amp.G1, DEV, seed=5)
+        ms = timed(lambda: env.update_amp_observations(*state))
+        per_env = (2 * 29 + 25) * 4 + (K - 1) * 83 * 4 + K * 83 * 4
+        row("obs_step_kernel", ms, n * per_env, note=f"G1 N={n} K={K} ({per_env} B/env)")
+        del env, state
+
+    # ---- compute_obs free function ---------------------------------------------------------------------------------------
+    n = 2_000_000
+    g = torch.Generator(device="cuda").manual_seed(0)
+    args = [torch.randn(n, 29, device=DEV, generator=g), torch.randn(n, 29, device=DEV, generator=g), torch.randn(n, 3, device=DEV, generator=g),
+            torch.nn.functional.normalize(torch.randn(n, 4, device=DEV, generator=g), dim=-1), torch.randn(n, 3, device=DEV, generator=g),
+            torch.randn(n, 3, device=DEV, generator=g), torch.randn(n, 4, 3, device=DEV, generator=g)]  # fmt: skip
+    ms = timed(lambda: amp.compute_obs(*args))
+    row("compute_obs_kernel", ms, n * (83 * 4 + 83 * 4 + 4), note=f"n={n}, incl. torch.empty")
+    del args
+
+    # ---- discriminator ---------------------------------------------------------------------------------------------------
+    for width, M in ((166, 1_000_000), (830, 262_144), (166, 65_536), (830, 65_536), (166, 4096)):
+        W, b = skrl_style_discriminator_params(width, seed=42, logit_gain=5.0)
+        disc = amp.AmpDiscriminator(width, device=DEV, max_rows=M)
+        disc.load(W, b, torch.zeros(width, dtype=torch.float64), torch.ones(width, dtype=torch.float64))
+        x = torch.randn(M, width, device=DEV)
+        r = torch.empty(M, device=DEV)
+        ms = timed(lambda: disc.style_reward(x, out=r))
+        row("disc style reward (cast + fused tcgen05)", ms, flops=M * bench.flops_per_row(width), note=f"K*A={width} M={M}")
+        del disc, x
+    tmp.cleanup()
+
+
+if __name__ == "__main__":
+    main()
