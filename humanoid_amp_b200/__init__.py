@@ -18,5 +18,6 @@ from .motion_loader import MotionLoader, _resolve_motion_files  # noqa: F401
 from .amp_env import AmpEnvCfg, AmpEnvPath, compute_obs, quaternion_to_tangent_and_normal  # noqa: F401
 from .discriminator import AmpDiscriminator, style_reward_from_logits  # noqa: F401
 from .distributed import reduce_parameters, shard_envs  # noqa: F401
+from .graphs import capture_step  # noqa: F401
 
 __version__ = "0.1.0"

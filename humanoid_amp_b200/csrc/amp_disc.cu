@@ -782,11 +782,18 @@ int amp_disc_create(int32_t in_features, int32_t h1, int32_t h2, int64_t max_row
     d->Kp = (in_features + BK - 1) / BK * BK;
     d->h1 = h1;
     d->h2 = h2;
-    // Rows per launch ("chunk"): the bf16 x_hat of a chunk should stay L2-resident between the cast kernel that writes it
-    // and the fused kernel that reads it (<= ~64 MB), in whole waves of 128-row tiles: 8 tiles per SM at K*A = 166.
-    const int64_t per_wave_bytes = (int64_t)sm_count() * BM * d->Kp * 2;
-    const int64_t tiles_per_cta = std::max<int64_t>(1, std::min<int64_t>(8, ((int64_t)64 << 20) / per_wave_bytes));
-    d->chunk_rows = std::min<int64_t>((max_rows + BM - 1) / BM * BM, (int64_t)sm_count() * BM * tiles_per_cta);
+    // Rows per launch ("chunk").  Measured (tools/sweep_disc.py, 1 M rows): 2 / 4 / 8 / 16 / 32 tiles per CTA per launch give
+    // 1.83 / 1.63 / 1.51 / 1.46 / 1.43 ms -- every launch pays an un-overlapped layer-1 prologue and a layer-2 tail, while
+    // keeping x_hat L2-resident buys nothing (the fused kernel is not DRAM-bound).  So chunks are as large as a 256 MB x_hat
+    // buffer allows, but a big batch is still cut in two so the cast of the second half overlaps the first fused launch.
+    const int64_t wave_rows = (int64_t)sm_count() * BM;
+    const int64_t per_wave_bytes = wave_rows * d->Kp * 2;
+    int64_t tiles_per_cta = std::max<int64_t>(1, std::min<int64_t>(32, ((int64_t)256 << 20) / per_wave_bytes));
+    if (const char *t = getenv("AMP_B200_DISC_TILES_PER_CTA")) tiles_per_cta = std::max(1, atoi(t));  // tuning knob
+    const int64_t rows_padded = (max_rows + BM - 1) / BM * BM;
+    d->chunk_rows = std::min<int64_t>(rows_padded, wave_rows * tiles_per_cta);
+    if (rows_padded >= 4 * wave_rows && rows_padded <= 2 * d->chunk_rows)  // two balanced chunks instead of one (+ a sliver)
+        d->chunk_rows = ((rows_padded + 1) / 2 + wave_rows - 1) / wave_rows * wave_rows;
     d->ws_ctas = sm_count();  // h1 workspace: two 128-row slots per persistent CTA, L2-resident
     auto alloc = [&](void **p, size_t bytes) { return cudaMalloc(p, bytes); };
     cudaError_t e = cudaSuccess;
