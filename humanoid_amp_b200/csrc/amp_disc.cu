@@ -336,7 +336,7 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            long long w_empty = 0, w_h1 = 0;
+            [[maybe_unused]] long long w_empty = 0, w_h1 = 0;
             auto load_pair = [&](const CUtensorMap *ma, int a_col, int a_row, const CUtensorMap *mb, int b_col, int b_row) {
                 {
                     AMP_PROF_T0;
@@ -385,7 +385,7 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         if (lane == 0 && leader) {
             int stage = 0;
             uint32_t phase = 0, c1 = 0, c2 = 0;
-            long long w_full = 0, w_d1 = 0, w_d2 = 0;
+            [[maybe_unused]] long long w_full = 0, w_d1 = 0, w_d2 = 0;
 #ifdef AMP_DISC_PROFILE
             const long long t_begin = clock64();
 #endif

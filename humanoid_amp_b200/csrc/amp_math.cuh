@@ -46,6 +46,66 @@ __device__ __forceinline__ float lerp(float blend, float a, float b) {
     return lerp_w(__fsub_rn(1.0f, blend), blend, a, b);
 }
 
+// ---- float64 acos / sin for the slerp --------------------------------------------------------------------------------
+// The reference evaluates torch.acos / torch.sin in fp32 (SLEEF, <= 1 ulp).  Here each is evaluated in float64 and rounded
+// ONCE to fp32, i.e. the correctly rounded fp32 value (verified on 3.1 M / 4.5 M fp32 arguments against numpy float64:
+// zero mismatches after rounding), with branch-free polynomials instead of libdevice's general-purpose acos()/sin()
+// (whose slow paths cost ~2000 instructions per frame and most of the small-batch latency).
+//   acos(c), c in [0, 1]:   c <= 0.5: pi/2 - asin(c);   c > 0.5: 2 asin(sqrt((1 - c)/2));   asin(s) = s + s z Q(z), z = s^2,
+//                           Q = degree-10 minimax fit on z in [0, 0.25], relative error 1e-15
+//   sin(x), |x| < 1e6:      3-term Cody-Waite reduction by pi/2, Taylor kernels of degree 15 / 16 on |r| <= pi/4
+__device__ __forceinline__ double asin_kernel(double s, double z) {
+    double q = 0.02797051111814061;
+    q = fma(q, z, -0.006944262741785383);
+    q = fma(q, z, 0.01550894988389679);
+    q = fma(q, z, 0.010271259188591278);
+    q = fma(q, z, 0.01414412466480873);
+    q = fma(q, z, 0.017336854258322456);
+    q = fma(q, z, 0.022373031645160257);
+    q = fma(q, z, 0.030381916716773705);
+    q = fma(q, z, 0.044642857591684446);
+    q = fma(q, z, 0.07499999999719918);
+    q = fma(q, z, 0.16666666666666943);
+    return fma(s * z, q, s);
+}
+
+// c >= 0 (the caller has taken |c|); c > 1 yields NaN like acos
+__device__ __forceinline__ double acos_unit(double c) {
+    if (c > 1.0) return __longlong_as_double(0x7ff8000000000000LL);
+    if (c <= 0.5) return 0x1.921fb54442d18p+0 - asin_kernel(c, c * c);
+    const double z = (1.0 - c) * 0.5;
+    return 2.0 * asin_kernel(sqrt(z), z);
+}
+
+__device__ __forceinline__ double sin_reduced(double x) {
+    if (!(fabs(x) < 1.0e6)) return sin(x);  // absurd blends (and NaN / inf): libdevice's full-range path
+    const double k = rint(x * 0x1.45f306dc9c883p-1);  // x * 2/pi
+    double r = fma(-k, 0x1.921fb54400000p+0, x);
+    r = fma(-k, 0x1.0b4611a600000p-34, r);
+    r = fma(-k, 0x1.3198a2e037073p-69, r);
+    const double r2 = r * r;
+    double ps = -7.647163731819816e-13;
+    ps = fma(ps, r2, 1.6059043836821613e-10);
+    ps = fma(ps, r2, -2.505210838544172e-08);
+    ps = fma(ps, r2, 2.7557319223985893e-06);
+    ps = fma(ps, r2, -0.0001984126984126984);
+    ps = fma(ps, r2, 0.008333333333333333);
+    ps = fma(ps, r2, -0.16666666666666666);
+    ps = fma(ps * r2, r, r);
+    double pc = 4.779477332387385e-14;
+    pc = fma(pc, r2, -1.1470745597729725e-11);
+    pc = fma(pc, r2, 2.08767569878681e-09);
+    pc = fma(pc, r2, -2.755731922398589e-07);
+    pc = fma(pc, r2, 2.48015873015873e-05);
+    pc = fma(pc, r2, -0.001388888888888889);
+    pc = fma(pc, r2, 0.041666666666666664);
+    pc = fma(pc, r2, -0.5);
+    pc = fma(pc, r2, 1.0);
+    const int q = (int)(long long)k & 3;
+    const double v = (q & 1) ? pc : ps;
+    return (q & 2) ? -v : v;
+}
+
 // ---- shortest-arc slerp, wxyz : motion_loader.py:247-279 -------------------------------------------------------------
 // float4 holds (w, x, y, z) in (.x, .y, .z, .w).
 __device__ __forceinline__ float4 slerp(float4 q0, float4 q1, float blend) {
@@ -56,13 +116,13 @@ __device__ __forceinline__ float4 slerp(float4 q0, float4 q1, float blend) {
         q1.x = -q1.x; q1.y = -q1.y; q1.z = -q1.z; q1.w = -q1.w;
     }
     c = fabsf(c);
-    // acos / sin are evaluated in float64 and rounded once to fp32: that is the correctly rounded value of each fp32 op,
-    // which torch's SLEEF kernels match in all but their <= 1 ulp cases.  libdevice acosf/sinf (up to 2 ulp off) would add
-    // a second, independent error that extrapolation (|blend| up to K-1) amplifies past the 1e-6 absolute bar.
-    const float half = __double2float_rn(acos((double)c));            // NaN for c > 1, masked below
+    // acos / sin: float64 evaluation rounded once to fp32 (see above) = the correctly rounded value of each fp32 op, which
+    // torch's SLEEF kernels match in all but their <= 1 ulp cases.  libdevice acosf/sinf (up to 2 ulp off) would add a
+    // second, independent error that extrapolation (|blend| up to K-1) amplifies past the 1e-6 absolute bar.
+    const float half = __double2float_rn(acos_unit((double)c));       // NaN for c > 1, masked below
     const float s = __fsqrt_rn(__fsub_rn(1.0f, __fmul_rn(c, c)));     // sqrt(1.0 - c*c), unfused (:262)
-    const float ra = __fdiv_rn(__double2float_rn(sin((double)__fmul_rn(__fsub_rn(1.0f, blend), half))), s);
-    const float rb = __fdiv_rn(__double2float_rn(sin((double)__fmul_rn(blend, half))), s);
+    const float ra = __fdiv_rn(__double2float_rn(sin_reduced((double)__fmul_rn(__fsub_rn(1.0f, blend), half))), s);
+    const float rb = __fdiv_rn(__double2float_rn(sin_reduced((double)__fmul_rn(blend, half))), s);
     float4 o;
     o.x = __fadd_rn(__fmul_rn(ra, q0.x), __fmul_rn(rb, q1.x));
     o.y = __fadd_rn(__fmul_rn(ra, q0.y), __fmul_rn(rb, q1.y));

@@ -244,6 +244,7 @@ collect_reference_kernel(LibView v, const double *__restrict__ cur_times, const 
 
     const float *tab = v.packed;
     unsigned char *meta_base = collect_smem;
+    const int Rs = R;  // row stride of the table the kernel reads (an odd smem stride was tried: no gain, fewer warps fit)
     if constexpr (SMEM_TABLE) {
         const int quads = (int)(v.num_frames * R / 4);
         float4 *dst = reinterpret_cast<float4 *>(collect_smem);
@@ -289,8 +290,8 @@ collect_reference_kernel(LibView v, const double *__restrict__ cur_times, const 
             const FrameBlend fb = lookup_frame(v, t, ids ? ids[sample] : 0);
             const float b = __double2float_rn(fb.blend), omb = __fsub_rn(1.0f, b);
             FrameMeta m;
-            m.off0 = (int32_t)(fb.i0 * R);
-            m.off1 = (int32_t)(fb.i1 * R);
+            m.off0 = (int32_t)(fb.i0 * Rs);
+            m.off1 = (int32_t)(fb.i1 * Rs);
             m.b = b;
             m.omb = omb;
             const float *r0 = tab + m.off0, *r1 = tab + m.off1;
