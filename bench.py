@@ -331,7 +331,8 @@ def run_ours(args, spec, rank, world, local_rank):
         if state is not None:
             env.update_amp_observations(*state)
         r = disc.style_reward(o if spec["reward_mult"] == 1 else rows_for_reward, out=reward)
-        reward_host.copy_(r.view(-1), non_blocking=False)  # D2H of the step's result
+        reward_host.copy_(r.view(-1), non_blocking=True)  # D2H of the step's result into pinned memory ...
+        torch.cuda.current_stream(dev).synchronize()  # ... which the host then reads: one sync per step
 
     for _ in range(max(2, args.warmup // 2)):
         step_e2e()

@@ -37,9 +37,11 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
 constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KiB
 constexpr int NUM_EPI_THREADS = 256;  // eight epilogue warps
 constexpr int TMEM_COLS = 512;
-// bf16 staging area for the h1 TMA stores: per E1 warp two 32-row x 64-column slabs (4 KiB each)
-constexpr int STORE_SLAB_BYTES = 32 * BK * 2;
-constexpr int STORE_STAGING_BYTES = 8 * 2 * STORE_SLAB_BYTES;  // 64 KiB: eight epilogue warps, two slabs each
+// bf16 staging area for the h1 TMA stores: every epilogue warp owns two 32-row x 32-column slabs (2 KiB each, 64-byte rows
+// in the 64B-swizzled layout) -- small enough that a fourth operand stage still fits next to them
+constexpr int SLAB_COLS = 32;
+constexpr int STORE_SLAB_BYTES = 32 * SLAB_COLS * 2;
+constexpr int STORE_STAGING_BYTES = 8 * 2 * STORE_SLAB_BYTES;  // 32 KiB
 
 // ---- PTX wrappers --------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -187,22 +189,20 @@ constexpr uint32_t kInstrDescPair = (1u << 4) | (1u << 7) | (1u << 10) | ((uint3
 // Fused two-layer kernel: layer 1 and layer 2 share ONE persistent launch and keep the tensor pipe busy.
 //
 // Why not keep h1 on chip: one 128-row tile needs h1 = 128 x 1024 bf16 = 256 KB (> 227 KB smem) for the K loop of layer 2,
-// and its accumulator D2 = 128 x 512 fp32 already fills all 512 TMEM columns.  So the accumulators are halved
-// (D1 = columns [0,256), D2 = [256,512)) and h1 makes a round trip through a per-CTA, double-buffered workspace that
-// never leaves the L2 (148 CTAs x 2 slots x 256 KB = 77.6 MB), written with TMA stores and read back with TMA loads.
+// and a layer-2 accumulator of 128 x 512 fp32 alone fills all 512 TMEM columns.  So accumulator tiles are 128 x 256 (two
+// TMEM regions) and h1 makes a round trip through a per-CTA, double-buffered workspace that stays in the 126 MB L2
+// (148 CTAs x 2 slots x 256 KB = 77.6 MB), written with TMA stores and read back with TMA loads.
 //
-// The single MMA-issuing thread interleaves the two GEMMs in a static software pipeline over the CTA's row tiles:
-//     prologue   G1(t0, nt = 0..3)
-//     iteration i, group g = 0..3:   G1(t[i+1], nt = g)  then  G2(t[i]) units [8g, 8g+8)        (unit = one 64-wide K block
-//                                                                                                of one 256-column N tile)
-// so while the epilogue warps E1 drain D1 (bias + ReLU + bf16 + swizzled st.shared + TMA store; ~3k cycles, the slow part of
-// the split version) the tensor pipe runs 8 units = 4096 cycles of layer-2 MMAs, and while E2 drains D2 it runs a layer-1
-// tile.  Per row tile the pipe is busy 4*1536 + 32*512 = 22528 cycles, the MMA-bound floor of the two layers together.
+// The single MMA-issuing thread runs a static software pipeline over the CTA's row tiles (walk_schedule below): the four
+// layer-1 tiles of row tile i+1, then the two layer-2 tiles of row tile i; accumulator tiles ping-pong between the two
+// TMEM regions so every drain (bias + ReLU + bf16 + swizzled st.shared + TMA store for layer 1; bias + ReLU + dot with w3
+// for layer 2) overlaps the MMAs of the next tile.  Per row tile the pipe has 4*12 + 2*64 = 176 MMAs = 22.5 k cycles of
+// work; measured (in-kernel cycle counters, AMP_DISC_PROFILE build) ~35 k cycles per tile: ~10 k waiting for operands
+// (TMA delivery + shared-memory bandwidth: a 128x256x16 MMA reads 12 KB of smem per 128 cycles while TMA refills the ring
+// at the same rate) and ~2 k for accumulator hand-offs.
 //
 // Warp roles (320 threads): 0 TMA producer, 1 TMEM alloc + MMA issuer, 2..9 epilogue (warps w and w+4 share a TMEM lane
-// quarter and split the accumulator columns).  Producer, issuer and epilogue warps all walk the same static schedule
-// (walk_schedule).
-// =====================================================================================================================
+// quarter and split the accumulator columns).  Producer, issuer and epilogue warps all walk the same static schedule.
 // =====================================================================================================================
 // PAIR = true runs the same pipeline on a CTA pair (cluster of 2, tcgen05 cta_group::2): one MMA covers 256 rows (128 per
 // CTA) and each CTA stages only ITS half of the 256-row weight block, so the operand bytes delivered per SM per MMA drop
@@ -210,26 +210,30 @@ constexpr uint32_t kInstrDescPair = (1u << 4) | (1u << 7) | (1u << 10) | ((uint3
 // every SM (2.57 GB per 151 552 rows, ~51 B/cycle/SM) with the tensor pipe 55 % active: operand delivery, not math, is
 // the limiter, and a CTA pair is the only way to shrink it without more TMEM.
 constexpr int FUSED_THREADS = 320;
-constexpr uint32_t D1_COL = 0, D2_COL = 256;
-__host__ __device__ constexpr int fused_stages(bool pair) { return pair ? 5 : 3; }
+constexpr uint32_t ACC_COLS = 256;  // two accumulator regions: TMEM columns [0,256) and [256,512)
+__host__ __device__ constexpr int fused_stages(bool pair) { return pair ? 6 : 4; }
 __host__ __device__ constexpr int fused_b_bytes(bool pair) { return pair ? B_STAGE_BYTES / 2 : B_STAGE_BYTES; }
 __host__ __device__ constexpr int fused_smem_bytes(bool pair) {
     return fused_stages(pair) * (A_STAGE_BYTES + fused_b_bytes(pair)) + STORE_STAGING_BYTES + 256 /*barriers*/ +
            1024 /*partial dots*/ + 1024 /*alignment slack*/;
 }
 
+// Schedule shared by producer, issuer and epilogue warps.  Accumulator tiles are numbered in issue order and ping-pong
+// between the two 256-column TMEM regions (tile q -> region q & 1), whatever layer they belong to:
+//     prologue      G1(t0): N1 tiles 0..3
+//     iteration i   G1(t[i+1]): N1 tiles 0..3,   then   G2(t[i]): N2 tile 0 (16 units), N2 tile 1 (16 units)
+// so the drain of an accumulator always overlaps the MMAs of the NEXT tile, and the two long layer-2 tiles (8192 cycles
+// each) cover the drains that matter most.  (The first version interleaved one G1 tile with eight G2 units and kept D1 / D2
+// in fixed regions: every accumulator hand-off then sat on the issuer's critical path -- ~30 % of its time went to waiting
+// for drains, more with a CTA pair where a hand-off crosses the cluster twice.)
 template <class G1, class G2>
 __device__ __forceinline__ void walk_schedule(int T, int n1_tiles, int units, G1 &&g1, G2 &&g2) {
     if (T <= 0) return;
     for (int nt = 0; nt < n1_tiles; ++nt) g1(0, nt);
-    const int per_group = (units + n1_tiles - 1) / n1_tiles;
     for (int i = 0; i < T; ++i) {
-        int u = 0;
-        for (int g = 0; g < n1_tiles; ++g) {
-            if (i + 1 < T) g1(i + 1, g);
-            const int end = min(units, u + per_group);
-            for (; u < end; ++u) g2(i, u);
-        }
+        if (i + 1 < T)
+            for (int nt = 0; nt < n1_tiles; ++nt) g1(i + 1, nt);
+        for (int u = 0; u < units; ++u) g2(i, u);
     }
 }
 
@@ -272,8 +276,8 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     const uint32_t staging = smem_b + STAGES * B_BYTES;
     const uint32_t bars = staging + STORE_STAGING_BYTES;
     const uint32_t full_bar = bars, empty_bar = bars + 8 * STAGES;
-    const uint32_t d1_full = bars + 16 * STAGES, d1_empty = d1_full + 8, d2_full = d1_full + 16, d2_empty = d1_full + 24;
-    const uint32_t h1_ready = d1_full + 32;  // 2 x 8 B
+    const uint32_t acc_full = bars + 16 * STAGES, acc_empty = acc_full + 16;  // 2 x 8 B each, one per accumulator region
+    const uint32_t h1_ready = acc_full + 32;  // 2 x 8 B
     const uint32_t tmem_slot = h1_ready + 16;
     const uint32_t part_smem = bars + 256;  // 2 x 4 x 32 floats
     uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
@@ -303,10 +307,10 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             mbar_init(full_bar + 8 * i, 1);
             mbar_init(empty_bar + 8 * i, 1);
         }
-        mbar_init(d1_full, 1);
-        mbar_init(d1_empty, EPI_ARRIVALS);
-        mbar_init(d2_full, 1);
-        mbar_init(d2_empty, EPI_ARRIVALS);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(acc_full + 8 * i, 1);
+            mbar_init(acc_empty + 8 * i, EPI_ARRIVALS);
+        }
         mbar_init(h1_ready, 8);  // one arrival per epilogue warp
         mbar_init(h1_ready + 8, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -325,8 +329,7 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
     // accumulator-drained barriers live in the leader CTA; the epilogue threads of both CTAs arrive there
-    const uint32_t d1_empty_at_leader = PAIR ? mapa_rank(d1_empty, 0) : d1_empty;
-    const uint32_t d2_empty_at_leader = PAIR ? mapa_rank(d2_empty, 0) : d2_empty;
+    const uint32_t acc_empty_at_leader = PAIR ? mapa_rank(acc_empty, 0) : acc_empty;  // + 8 * region
     auto arrive_drained = [&](uint32_t addr) {
         if constexpr (PAIR) mbar_arrive_cluster(addr); else mbar_arrive(addr);
     };
@@ -384,7 +387,7 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         // ================= MMA issuer (one thread; for a pair, one thread of the leader CTA drives both SMs) =============
         if (lane == 0 && leader) {
             int stage = 0;
-            uint32_t phase = 0, c1 = 0, c2 = 0;
+            uint32_t phase = 0;
             [[maybe_unused]] long long w_full = 0, w_d1 = 0, w_d2 = 0;
 #ifdef AMP_DISC_PROFILE
             const long long t_begin = clock64();
@@ -409,33 +412,28 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                 commit(empty_bar + 8 * stage);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             };
+            uint32_t q = 0;  // accumulator tiles issued so far: tile q uses region q & 1, its (q >> 1)-th use
+            auto acquire_acc = [&](long long &w) {
+                AMP_PROF_T0;
+                mbar_wait(acc_empty + 8 * (q & 1), ((q >> 1) & 1) ^ 1);  // the epilogue (of both CTAs) has drained it
+                AMP_PROF_ADD(w);
+                tcgen05_fence_after();
+            };
             walk_schedule(
                 T, p.n1_tiles, units,
                 [&](int, int) {
-                    {
-                        AMP_PROF_T0;
-                        mbar_wait(d1_empty, (c1 & 1) ^ 1);  // E1 (of both CTAs) has drained D1
-                        AMP_PROF_ADD(w_d1);
-                    }
-                    tcgen05_fence_after();
-                    for (int kb = 0; kb < p.kb1; ++kb) mma_block(tmem_base + D1_COL, kb == 0);
-                    commit(d1_full);
-                    ++c1;
+                    acquire_acc(w_d1);
+                    for (int kb = 0; kb < p.kb1; ++kb) mma_block(tmem_base + (q & 1) * ACC_COLS, kb == 0);
+                    commit(acc_full + 8 * (q & 1));
+                    ++q;
                 },
                 [&](int, int u) {
                     const int kb = u % kb2;
-                    if (kb == 0) {
-                        {
-                            AMP_PROF_T0;
-                            mbar_wait(d2_empty, (c2 & 1) ^ 1);  // E2 (of both CTAs) has drained D2
-                            AMP_PROF_ADD(w_d2);
-                        }
-                        tcgen05_fence_after();
-                    }
-                    mma_block(tmem_base + D2_COL, kb == 0);
+                    if (kb == 0) acquire_acc(w_d2);
+                    mma_block(tmem_base + (q & 1) * ACC_COLS, kb == 0);
                     if (kb == kb2 - 1) {
-                        commit(d2_full);
-                        ++c2;
+                        commit(acc_full + 8 * (q & 1));
+                        ++q;
                     }
                 });
 #ifdef AMP_DISC_PROFILE
@@ -462,42 +460,39 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
         const uint32_t col_base = (uint32_t)(colhalf * (BN / 2));
         float *part = reinterpret_cast<float *>(smem_raw + (part_smem - smem_u32(smem_raw)));  // [2][4][32] partial dots
-        uint32_t c1 = 0, c2 = 0, store_it = 0;
+        uint32_t q = 0, store_it = 0;  // q: accumulator tiles drained so far (same numbering as the issuer)
         float dot[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         walk_schedule(
             T, p.n1_tiles, units,
             [&](int ti, int nt) {
                 // ---- D1 (ti, nt): this warp's 128 columns = two 64-column slabs ----
                 const int row0 = slot_row0 + (ti & 1) * BM + quarter * 32;
-                mbar_wait(d1_full, c1 & 1);
+                const uint32_t acc = tmem_base + lane_base + (q & 1) * ACC_COLS + col_base;
+                mbar_wait(acc_full + 8 * (q & 1), (q >> 1) & 1);
                 tcgen05_fence_after();
                 uint32_t v[2][32];
-                tmem_ld_32x32(tmem_base + lane_base + D1_COL + col_base, v[0]);
-                uint32_t slab = 0;
+                tmem_ld_32x32(acc, v[0]);
 #pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                    const int half = h & 1;
+                for (int h = 0; h < 4; ++h) {  // four steps of 32 columns = four slabs
                     const int col = nt * BN + (int)col_base + h * 32;  // h1 column of this step
                     const float4 *bias4 = reinterpret_cast<const float4 *>(p.b1 + col);
                     float4 bb[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) bb[j] = __ldg(bias4 + j);
-                    if (half == 0) {
-                        slab = staging + (uint32_t)((ew * 2 + (store_it & 1)) * STORE_SLAB_BYTES);
-                        if (lane == 0) bulk_wait_read<1>();  // the store that last read this slab has drained it
-                        __syncwarp();
-                    }
+                    const uint32_t slab = staging + (uint32_t)((ew * 2 + (store_it & 1)) * STORE_SLAB_BYTES);
+                    if (lane == 0) bulk_wait_read<1>();  // the store that last read this slab has drained it
+                    __syncwarp();
                     tmem_ld_wait();  // v[h & 1] has landed
                     if (h + 1 < 4) {
-                        tmem_ld_32x32(tmem_base + lane_base + D1_COL + col_base + (uint32_t)((h + 1) * 32), v[(h + 1) & 1]);
-                    } else {  // last TMEM read of this accumulator by this warp: release D1 to the issuer now
+                        tmem_ld_32x32(acc + (uint32_t)((h + 1) * 32), v[(h + 1) & 1]);
+                    } else {  // last TMEM read of this accumulator by this warp: release the region to the issuer now
                         tcgen05_fence_before();
                         __syncwarp();
-                        if (lane == 0) arrive_drained(d1_empty_at_leader);
+                        if (lane == 0) arrive_drained(acc_empty_at_leader + 8 * (q & 1));
                     }
                     const uint32_t(&cur)[32] = v[h & 1];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {  // 16-byte chunk (half*4 + j) of this thread's 128-byte slab row
+                    for (int j = 0; j < 4; ++j) {  // 16-byte chunk j of this thread's 64-byte slab row
                         const float4 b0 = bb[2 * j], b1v = bb[2 * j + 1];
                         const __nv_bfloat162 p0 = __floats2bfloat162_rn(fmaxf(__uint_as_float(cur[8 * j + 0]) + b0.x, 0.0f),
                                                                         fmaxf(__uint_as_float(cur[8 * j + 1]) + b0.y, 0.0f));
@@ -507,22 +502,21 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                                                                         fmaxf(__uint_as_float(cur[8 * j + 5]) + b1v.y, 0.0f));
                         const __nv_bfloat162 p3 = __floats2bfloat162_rn(fmaxf(__uint_as_float(cur[8 * j + 6]) + b1v.z, 0.0f),
                                                                         fmaxf(__uint_as_float(cur[8 * j + 7]) + b1v.w, 0.0f));
-                        const int chunk = (half * 4 + j) ^ (lane & 7);  // SWIZZLE_128B: chunk index XOR (row % 8)
-                        st_shared_v4(slab + (uint32_t)(lane * 128 + chunk * 16), *reinterpret_cast<const uint32_t *>(&p0),
+                        // SWIZZLE_64B: 16-byte chunk index XOR address bits [7,9) = (row >> 1) & 3 (rows are 64 bytes)
+                        const int chunk = j ^ ((lane >> 1) & 3);
+                        st_shared_v4(slab + (uint32_t)(lane * 64 + chunk * 16), *reinterpret_cast<const uint32_t *>(&p0),
                                      *reinterpret_cast<const uint32_t *>(&p1), *reinterpret_cast<const uint32_t *>(&p2),
                                      *reinterpret_cast<const uint32_t *>(&p3));
                     }
-                    if (half == 1) {
-                        fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA (async proxy)
-                        __syncwarp();
-                        if (lane == 0) {
-                            tma_store_2d(&tmap_h_store, slab, col - 32, row0);
-                            bulk_commit();
-                        }
-                        ++store_it;
+                    fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA (async proxy)
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmap_h_store, slab, col, row0);
+                        bulk_commit();
                     }
+                    ++store_it;
                 }
-                ++c1;
+                ++q;
                 if (nt == p.n1_tiles - 1 && lane == 0) {  // this warp's part of h1(ti) is complete in the workspace
                     bulk_wait_all();
                     mbar_arrive(h1_ready + 8 * (ti & 1));
@@ -532,10 +526,11 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                 const int n2 = u / kb2;
                 if (u - n2 * kb2 != kb2 - 1) return;  // D2 (ti, n2) is complete after the last K block of the N tile
                 // ---- D2 (ti, n2): this warp's 128 columns ----
-                mbar_wait(d2_full, c2 & 1);
+                const uint32_t acc = tmem_base + lane_base + (q & 1) * ACC_COLS + col_base;
+                mbar_wait(acc_full + 8 * (q & 1), (q >> 1) & 1);
                 tcgen05_fence_after();
                 uint32_t v[2][32];
-                tmem_ld_32x32(tmem_base + lane_base + D2_COL + col_base, v[0]);
+                tmem_ld_32x32(acc, v[0]);
 #pragma unroll
                 for (int chunk = 0; chunk < 4; ++chunk) {
                     const int col0 = n2 * BN + (int)col_base + chunk * 32;
@@ -549,11 +544,11 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                     }
                     tmem_ld_wait();  // v[chunk & 1] has landed
                     if (chunk + 1 < 4) {
-                        tmem_ld_32x32(tmem_base + lane_base + D2_COL + col_base + (uint32_t)((chunk + 1) * 32), v[(chunk + 1) & 1]);
-                    } else {  // last TMEM read: hand D2 back before finishing the arithmetic
+                        tmem_ld_32x32(acc + (uint32_t)((chunk + 1) * 32), v[(chunk + 1) & 1]);
+                    } else {  // last TMEM read: hand the region back before finishing the arithmetic
                         tcgen05_fence_before();
                         __syncwarp();
-                        if (lane == 0) arrive_drained(d2_empty_at_leader);
+                        if (lane == 0) arrive_drained(acc_empty_at_leader + 8 * (q & 1));
                     }
                     const uint32_t(&cur)[32] = v[chunk & 1];
 #pragma unroll
@@ -564,7 +559,7 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                         dot[3] = fmaf(fmaxf(__uint_as_float(cur[4 * j + 3]) + bb[j].w, 0.0f), ww[j].w, dot[3]);
                     }
                 }
-                ++c2;
+                ++q;
                 if (n2 == p.n2_tiles - 1) {
                     // combine the two column halves of this row: the upper-half warp hands its partial sum over through
                     // shared memory (double-buffered by tile parity), a 64-thread named barrier orders the exchange
@@ -720,15 +715,16 @@ static EncodeTiledFn encode_fn() {
 }
 
 // (rows, cols) bf16 row-major with pitch `pitch` elements; box = [box_rows x 64 cols], 128B swizzle, OOB rows read as 0
-static int make_tmap(CUtensorMap *map, const void *ptr, int64_t rows, int64_t cols, int64_t pitch, int box_rows) {
+static int make_tmap(CUtensorMap *map, const void *ptr, int64_t rows, int64_t cols, int64_t pitch, int box_rows,
+                     int box_cols = BK, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(AMP_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)pitch * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(AMP_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return AMP_OK;
@@ -752,7 +748,7 @@ struct amp_disc {
     CUtensorMap tmap_w1_half, tmap_w2_half; // 128-row boxes: each CTA of a pair stages its half of a 256-row weight block
     CUtensorMap tmap_h_load, tmap_h_store;  // h1 workspace: 128-row loads, 32-row epilogue slab stores
     long long *prof;                        // AMP_DISC_PROFILE builds: device counters (ws_ctas x 8)
-    bool use_pair;                          // CTA-pair (cta_group::2) kernel; AMP_B200_DISC_SINGLE_CTA=1 selects the 1-CTA kernel
+    bool use_pair;                          // CTA-pair (cta_group::2) kernel, opt-in with AMP_B200_DISC_PAIR=1
     bool loaded;
 };
 
@@ -823,7 +819,8 @@ int amp_disc_create(int32_t in_features, int32_t h1, int32_t h2, int64_t max_row
     if (rc == AMP_OK) rc = make_tmap(&d->tmap_w1_half, d->W1, h1, d->Kp, d->Kp, BN / 2);
     if (rc == AMP_OK) rc = make_tmap(&d->tmap_w2_half, d->W2, h2, h1, h1, BN / 2);
     if (rc == AMP_OK) rc = make_tmap(&d->tmap_h_load, d->hid, (int64_t)d->ws_ctas * 2 * BM, h1, h1, BM);
-    if (rc == AMP_OK) rc = make_tmap(&d->tmap_h_store, d->hid, (int64_t)d->ws_ctas * 2 * BM, h1, h1, 32);
+    // epilogue slabs: 32 rows x 32 columns (64-byte rows, 64B swizzle)
+    if (rc == AMP_OK) rc = make_tmap(&d->tmap_h_store, d->hid, (int64_t)d->ws_ctas * 2 * BM, h1, h1, 32, SLAB_COLS, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc == AMP_OK) {
         e = cudaFuncSetAttribute(disc_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_smem_bytes(false));
         if (e == cudaSuccess)
@@ -832,8 +829,11 @@ int amp_disc_create(int32_t in_features, int32_t h1, int32_t h2, int64_t max_row
     #ifdef AMP_DISC_PROFILE
         if (cudaMalloc((void **)&d->prof, (size_t)d->ws_ctas * 8 * sizeof(long long)) != cudaSuccess) d->prof = nullptr;
 #endif
-        const char *single = getenv("AMP_B200_DISC_SINGLE_CTA");
-        d->use_pair = !(single && single[0] == '1');
+        // Measured on the 1 M-row bench (B200, sustained, sw_power_cap active): single-CTA 1.61 ms, CTA pair 1.68 ms.  The pair
+        // halves the weight bytes each SM ingests but every accumulator hand-off crosses the cluster twice; it is kept as
+        // an opt-in (AMP_B200_DISC_PAIR=1) and covered by the GPU tests.
+        const char *pair = getenv("AMP_B200_DISC_PAIR");
+        d->use_pair = pair && pair[0] == '1';
     }
     if (rc != AMP_OK) {
         amp_disc_destroy(d);

@@ -206,7 +206,9 @@ class MotionLoader:
     def _times_to_device(self, times) -> torch.Tensor:
         if isinstance(times, torch.Tensor):
             if times.device != self.device or times.dtype != torch.float64:
-                times = times.to(device=self.device, dtype=torch.float64)
+                # a pinned host tensor is copied asynchronously on the current stream (the caller keeps it alive, as with
+                # any non_blocking copy); pageable memory falls back to torch's staged synchronous copy
+                times = times.to(device=self.device, dtype=torch.float64, non_blocking=times.device.type == "cpu" and times.is_pinned())
             return times.contiguous().view(-1)
         host = np.ascontiguousarray(np.asarray(times, dtype=np.float64).reshape(-1))
         return torch.from_numpy(host).to(self.device, non_blocking=False)
@@ -216,7 +218,8 @@ class MotionLoader:
         if motion_ids is None:
             return None
         if isinstance(motion_ids, torch.Tensor):
-            ids = motion_ids.to(device=self.device, dtype=torch.int64).contiguous().view(-1)
+            pinned = motion_ids.device.type == "cpu" and motion_ids.is_pinned()
+            ids = motion_ids.to(device=self.device, dtype=torch.int64, non_blocking=pinned).contiguous().view(-1)
         else:
             host = np.asarray(motion_ids).reshape(-1)
             if host.size and not np.issubdtype(host.dtype, np.integer):

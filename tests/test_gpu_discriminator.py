@@ -19,6 +19,14 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["single_cta", "cta_pair"], autouse=True)
+def kernel_variant(request, monkeypatch):
+    """Every test runs against both fused-kernel variants: the default single-CTA kernel and the cta_group::2 CTA-pair
+    kernel (opt-in; the variant is chosen when an AmpDiscriminator is created)."""
+    monkeypatch.setenv("AMP_B200_DISC_PAIR", "1" if request.param == "cta_pair" else "0")
+    return request.param
+
+
 def build(in_features, gain, seed=42, max_rows=65536):
     import humanoid_amp_b200 as amp
     from humanoid_amp_b200.synthetic import skrl_style_discriminator_params

@@ -8,7 +8,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for tiles in (2, 4, 8, 16, 32):
     for single in (0, 1):
-        env = dict(os.environ, AMP_B200_DISC_TILES_PER_CTA=str(tiles), AMP_B200_DISC_SINGLE_CTA=str(single))
+        env = dict(os.environ, AMP_B200_DISC_TILES_PER_CTA=str(tiles), AMP_B200_DISC_PAIR=str(1 - single))
         out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "20", "--warmup", "5", "--no-cpu-baseline"],
                              capture_output=True, text=True, env=env, timeout=300)
         line = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
