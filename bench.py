@@ -368,7 +368,7 @@ def run_ours(args, spec, rank, world, local_rank):
     disc_tflops = disc_flops / (disc_ms / args.steps * 1e-3) / 1e12
     tensor_peak = peaks["bf16_sustained"]
     roofline = {
-        "kernel": "disc_gemm_kernel (tcgen05 discriminator + style reward: 3 launches per chunk)", "bound": "tensor",
+        "kernel": "disc_fused_kernel (tcgen05 two-layer discriminator + style reward) + normalise_cast_kernel: 2 launches per chunk", "bound": "tensor",
         "achieved": disc_tflops, "peak": tensor_peak, "unit": "TFLOP/s", "frac": disc_tflops / tensor_peak, "traffic": None,
         "algorithmic_flops_per_launch_group": disc_flops, "ms": disc_ms / args.steps, "peak_source": peaks["source"] + ", sustained bf16",
     }
