@@ -47,6 +47,9 @@ struct LibView {
     const double *durations; // [num_traj]
     const float *dof_pos, *dof_vel, *body_pos, *body_rot, *body_lin, *body_ang;
     const float *packed;     // (F, R) packed AMP rows, see amp_motion.cu
+    const float *lerp_rows;  // (F, lerp_stride) all linearly interpolated columns of a frame side by side, or NULL
+    int32_t lerp_width;      // W = 2*D_clip + 9*B
+    int32_t lerp_stride;     // W rounded up to a multiple of 4
     uint32_t *flags;         // sticky error bits
 };
 

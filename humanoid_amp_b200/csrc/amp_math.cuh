@@ -77,13 +77,7 @@ __device__ __forceinline__ double acos_unit(double c) {
     return 2.0 * asin_kernel(sqrt(z), z);
 }
 
-__device__ __forceinline__ double sin_reduced(double x) {
-    if (!(fabs(x) < 1.0e6)) return sin(x);  // absurd blends (and NaN / inf): libdevice's full-range path
-    const double k = rint(x * 0x1.45f306dc9c883p-1);  // x * 2/pi
-    double r = fma(-k, 0x1.921fb54400000p+0, x);
-    r = fma(-k, 0x1.0b4611a600000p-34, r);
-    r = fma(-k, 0x1.3198a2e037073p-69, r);
-    const double r2 = r * r;
+__device__ __forceinline__ double sin_poly(double r, double r2) {  // sin(r), |r| <= pi/4
     double ps = -7.647163731819816e-13;
     ps = fma(ps, r2, 1.6059043836821613e-10);
     ps = fma(ps, r2, -2.505210838544172e-08);
@@ -91,18 +85,36 @@ __device__ __forceinline__ double sin_reduced(double x) {
     ps = fma(ps, r2, -0.0001984126984126984);
     ps = fma(ps, r2, 0.008333333333333333);
     ps = fma(ps, r2, -0.16666666666666666);
-    ps = fma(ps * r2, r, r);
-    double pc = 4.779477332387385e-14;
-    pc = fma(pc, r2, -1.1470745597729725e-11);
-    pc = fma(pc, r2, 2.08767569878681e-09);
-    pc = fma(pc, r2, -2.755731922398589e-07);
-    pc = fma(pc, r2, 2.48015873015873e-05);
-    pc = fma(pc, r2, -0.001388888888888889);
-    pc = fma(pc, r2, 0.041666666666666664);
-    pc = fma(pc, r2, -0.5);
-    pc = fma(pc, r2, 1.0);
+    return fma(ps * r2, r, r);
+}
+
+__device__ __forceinline__ double sin_reduced(double x) {
+    // Warp-uniform fast path: consecutive frames differ by small rotations, so for interpolation every lane's argument
+    // is within pi/4 and neither the range reduction nor the cosine kernel is needed.  (For |x| <= pi/4 the general path
+    // also gets k = 0, r = x and the same polynomial, so which path a warp takes does not change the value -- only within
+    // an ulp of the boundary could k be 1, where the two kernels agree to 1e-16, far below the fp32 rounding that follows.)
+    if (__all_sync(__activemask(), fabs(x) <= 0x1.921fb54442d18p-1)) return sin_poly(x, x * x);
+    if (!(fabs(x) < 1.0e6)) return sin(x);  // absurd blends (and NaN / inf): libdevice's full-range path
+    const double k = rint(x * 0x1.45f306dc9c883p-1);  // x * 2/pi
+    double r = fma(-k, 0x1.921fb54400000p+0, x);
+    r = fma(-k, 0x1.0b4611a600000p-34, r);
+    r = fma(-k, 0x1.3198a2e037073p-69, r);
+    const double r2 = r * r;
     const int q = (int)(long long)k & 3;
-    const double v = (q & 1) ? pc : ps;
+    double v;
+    if (q & 1) {
+        double pc = 4.779477332387385e-14;
+        pc = fma(pc, r2, -1.1470745597729725e-11);
+        pc = fma(pc, r2, 2.08767569878681e-09);
+        pc = fma(pc, r2, -2.755731922398589e-07);
+        pc = fma(pc, r2, 2.48015873015873e-05);
+        pc = fma(pc, r2, -0.001388888888888889);
+        pc = fma(pc, r2, 0.041666666666666664);
+        pc = fma(pc, r2, -0.5);
+        v = fma(pc, r2, 1.0);
+    } else {
+        v = sin_poly(r, r2);
+    }
     return (q & 2) ? -v : v;
 }
 

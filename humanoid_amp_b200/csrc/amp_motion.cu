@@ -178,6 +178,105 @@ __global__ void __launch_bounds__(kSampleWarps * 32) sample_full_kernel(LibView 
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Row-table variant of amp_sample_full (used when the library owns a "lerp row" table, i.e. for MotionLoader.sample):
+// the five linearly interpolated tensors of a frame are staged side by side as ONE row
+//   [dof_pos D | dof_vel D | body_pos 3B | body_lin 3B | body_ang 3B]      (W = 2D + 9B floats)
+// so the lerp part becomes the same "lane = column, two row reads, one store" loop as the fused AMP kernel: per frame
+// ceil(W/32) slots instead of a per-element divide + three shared-memory look-ups.  Where a column goes (which output
+// tensor, which offset, which row pitch) is frame-invariant and hoisted.  Rotations keep the flat (frame, body) walk.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void pack_lerp_rows_kernel(LibView v, float *__restrict__ rows) {
+    const int D = v.num_dofs, B3 = v.num_bodies * 3, W = v.lerp_width, Ws = v.lerp_stride;
+    const int64_t total = v.num_frames * (int64_t)Ws;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t f = e / Ws;
+        const int c = (int)(e - f * Ws);
+        float val = 0.0f;
+        if (c < D) val = v.dof_pos[f * D + c];
+        else if (c < 2 * D) val = v.dof_vel[f * D + c - D];
+        else if (c < 2 * D + B3) val = v.body_pos[f * B3 + c - 2 * D];
+        else if (c < 2 * D + 2 * B3) val = v.body_lin[f * B3 + c - 2 * D - B3];
+        else if (c < W) val = v.body_ang[f * B3 + c - 2 * D - 2 * B3];
+        rows[e] = val;
+    }
+}
+
+template <int NSLOT>
+__global__ void __launch_bounds__(kSampleWarps * 32) sample_rows_kernel(LibView v, uint32_t magic_body,
+                                                                         const double *__restrict__ times,
+                                                                         const int64_t *__restrict__ ids, int64_t S,
+                                                                         float *__restrict__ dof_pos, float *__restrict__ dof_vel,
+                                                                         float *__restrict__ body_pos, float *__restrict__ body_rot,
+                                                                         float *__restrict__ body_lin, float *__restrict__ body_ang) {
+    __shared__ int s_i0_all[kSampleWarps][32], s_i1_all[kSampleWarps][32];
+    __shared__ float s_b_all[kSampleWarps][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int *s_i0 = s_i0_all[warp], *s_i1 = s_i1_all[warp];
+    float *s_b = s_b_all[warp];
+    const int D = v.num_dofs, B = v.num_bodies, B3 = 3 * B, W = v.lerp_width, Ws = v.lerp_stride;
+    const float *__restrict__ rows = v.lerp_rows;
+
+    float *dst[NSLOT];   // where column lane + 32 s of frame 0 goes
+    int pitch[NSLOT];    // floats between consecutive frames in that output tensor
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) {
+        const int c = lane + 32 * s;
+        dst[s] = nullptr;
+        pitch[s] = 0;
+        if (c < D) { dst[s] = dof_pos + c; pitch[s] = D; }
+        else if (c < 2 * D) { dst[s] = dof_vel + (c - D); pitch[s] = D; }
+        else if (c < 2 * D + B3) { dst[s] = body_pos + (c - 2 * D); pitch[s] = B3; }
+        else if (c < 2 * D + 2 * B3) { dst[s] = body_lin + (c - 2 * D - B3); pitch[s] = B3; }
+        else if (c < W) { dst[s] = body_ang + (c - 2 * D - 2 * B3); pitch[s] = B3; }
+    }
+
+    const int64_t num_tiles = (S + 31) / 32;
+    for (int64_t tile = blockIdx.x * (int64_t)kSampleWarps + warp; tile < num_tiles; tile += (int64_t)gridDim.x * kSampleWarps) {
+        const int64_t f0 = tile * 32;
+        const int nf = (int)min((int64_t)32, S - f0);
+        if (lane < nf) {
+            const FrameBlend fb = lookup_frame(v, times[f0 + lane], ids ? ids[f0 + lane] : 0);
+            s_i0[lane] = (int)fb.i0;
+            s_i1[lane] = (int)fb.i1;
+            s_b[lane] = __double2float_rn(fb.blend);
+        }
+        __syncwarp();
+        constexpr int G = NSLOT < 4 ? NSLOT : 4;  // slots per batch: all loads of a batch are issued before its stores
+#pragma unroll 1
+        for (int f = 0; f < nf; ++f) {
+            const float b = s_b[f], omb = __fsub_rn(1.0f, b);
+            const float *p0 = rows + (int64_t)s_i0[f] * Ws + lane, *p1 = rows + (int64_t)s_i1[f] * Ws + lane;
+#pragma unroll
+            for (int g = 0; g < NSLOT; g += G) {  // the table is padded: rows may be over-read, only stores are guarded
+                float a0[G], a1[G];
+#pragma unroll
+                for (int t = 0; t < G; ++t) {
+                    if (g + t < NSLOT) {
+                        a0[t] = __ldg(p0 + 32 * (g + t));
+                        a1[t] = __ldg(p1 + 32 * (g + t));
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < G; ++t)
+                    if (g + t < NSLOT && dst[g + t]) __stcs(dst[g + t] + (f0 + f) * pitch[g + t], lerp_w(omb, b, a0[t], a1[t]));
+            }
+        }
+        {
+            const float4 *rot = reinterpret_cast<const float4 *>(v.body_rot);
+            float4 *o = reinterpret_cast<float4 *>(body_rot) + f0 * B;
+            const int total = nf * B;
+#pragma unroll 2
+            for (int e = lane; e < total; e += 32) {
+                const int fl = (int)__umulhi((uint32_t)e, magic_body);
+                const int j = e - fl * B;
+                __stcs(o + e, slerp(__ldg(rot + (int64_t)s_i0[fl] * B + j), __ldg(rot + (int64_t)s_i1[fl] * B + j), s_b[fl]));
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // amp_lerp / amp_slerp with explicit end points
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void lerp_kernel(const float *__restrict__ a, const float *__restrict__ b, const float *__restrict__ blend,
@@ -361,6 +460,9 @@ __device__ __forceinline__ float pick6(const float tn[6], int i) {
     return r;
 }
 
+// compute_obs on seven contiguous caller tensors: one warp per row, lane l owns columns l, l+32, ...; where a column
+// comes from is row-invariant, so every slot gets a (pointer, per-row stride) pair once and the row loop is branch-free.
+template <int NSLOT>
 __global__ void __launch_bounds__(256) compute_obs_kernel(const float *__restrict__ dof_pos,
                                                            const float *__restrict__ dof_vel,
                                                            const float *__restrict__ root_pos,
@@ -373,23 +475,47 @@ __global__ void __launch_bounds__(256) compute_obs_kernel(const float *__restric
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int D2 = 2 * D, A = D2 + 13 + 3 * Kb;
+    const float *src[NSLOT], *sub[NSLOT];
+    int stride[NSLOT], tn_idx[NSLOT];
+    bool active[NSLOT];
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) {
+        const int c = lane + 32 * s;
+        active[s] = c < A;
+        tn_idx[s] = -1;
+        sub[s] = nullptr;
+        src[s] = root_pos;
+        stride[s] = 0;
+        if (c < D) { src[s] = dof_pos + c; stride[s] = D; }
+        else if (c < D2) { src[s] = dof_vel + (c - D); stride[s] = D; }
+        else if (c == D2) { src[s] = root_pos + 2; stride[s] = 3; }
+        else if (c < D2 + 7) { tn_idx[s] = c - D2 - 1; }
+        else if (c < D2 + 10) { src[s] = root_lin + (c - D2 - 7); stride[s] = 3; }
+        else if (c < D2 + 13) { src[s] = root_ang + (c - D2 - 10); stride[s] = 3; }
+        else if (c < A) {
+            const int e = c - D2 - 13;
+            src[s] = key_pos + e;
+            stride[s] = 3 * Kb;
+            sub[s] = root_pos + e % 3;
+        }
+    }
     for (int64_t i = warp; i < n; i += nwarps) {
-        const float4 q = make_float4(root_rot[i * 4], root_rot[i * 4 + 1], root_rot[i * 4 + 2], root_rot[i * 4 + 3]);
+        const float4 q = make_float4(__ldg(root_rot + i * 4), __ldg(root_rot + i * 4 + 1), __ldg(root_rot + i * 4 + 2),
+                                     __ldg(root_rot + i * 4 + 3));
+        float val[NSLOT], minus[NSLOT];
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) {
+            val[s] = (active[s] && tn_idx[s] < 0) ? __ldg(src[s] + i * stride[s]) : 0.0f;
+            minus[s] = sub[s] ? __ldg(sub[s] + i * 3) : 0.0f;
+        }
         float tn[6];
         tangent_normal(q, tn);
-        for (int c = lane; c < A; c += 32) {
-            float val;
-            if (c < D) val = dof_pos[i * D + c];
-            else if (c < D2) val = dof_vel[i * D + c - D];
-            else if (c == D2) val = root_pos[i * 3 + 2];
-            else if (c < D2 + 7) val = pick6(tn, c - D2 - 1);
-            else if (c < D2 + 10) val = root_lin[i * 3 + c - D2 - 7];
-            else if (c < D2 + 13) val = root_ang[i * 3 + c - D2 - 10];
-            else {
-                const int e = c - D2 - 13;
-                val = __fsub_rn(key_pos[i * Kb * 3 + e], root_pos[i * 3 + e % 3]);
-            }
-            out[i * A + c] = val;
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) {
+            if (!active[s]) continue;
+            float r = sub[s] ? __fsub_rn(val[s], minus[s]) : val[s];
+            if (tn_idx[s] >= 0) r = pick6(tn, tn_idx[s]);
+            __stcs(out + i * A + lane + 32 * s, r);
         }
     }
 }
@@ -601,6 +727,23 @@ int amp_lib_create(const amp_lib_desc_t *d, void *stream, amp_lib_t **out) {
         e = cudaGetLastError();
         if (e != cudaSuccess) return bail(cuda_fail(e, "pack_rows_kernel launch"));
     }
+    if (!with_env) {
+        // plain handle (MotionLoader.sample): stage the lerp row table for the row-table sample kernel
+        v.lerp_width = 2 * v.num_dofs + 9 * v.num_bodies;
+        v.lerp_stride = (v.lerp_width + 3) & ~3;
+        if (v.lerp_width <= 32 * 16 && v.num_frames * (int64_t)v.lerp_stride < ((int64_t)1 << 40)) {
+            void *rows = nullptr;
+            // + 2 KiB: a row is read in 32-float slots without a bounds check
+            cudaError_t e2 = cudaMalloc(&rows, (size_t)v.num_frames * v.lerp_stride * sizeof(float) + 2048);
+            if (e2 != cudaSuccess) return bail(cuda_fail(e2, "cudaMalloc(lerp rows)"));
+            lib->owned[lib->n_owned++] = rows;
+            const int64_t total = v.num_frames * (int64_t)v.lerp_stride;
+            pack_lerp_rows_kernel<<<grid_for(total, 256, 8), 256, 0, st>>>(v, static_cast<float *>(rows));
+            e2 = cudaGetLastError();
+            if (e2 != cudaSuccess) return bail(cuda_fail(e2, "pack_lerp_rows_kernel launch"));
+            v.lerp_rows = static_cast<float *>(rows);
+        }
+    }
     // host arrays of the descriptor are read by the async copies above: finish them before returning
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return bail(cuda_fail(e, "cudaStreamSynchronize(amp_lib_create)"));
@@ -647,8 +790,26 @@ int amp_sample_full(amp_lib_t *lib, const double *times, const int64_t *ids, int
     AMP_REQUIRE(lib->v.num_bodies * 3 < 4096 && lib->v.num_dofs < 4096, "amp_sample_full: row wider than 4096 floats");
     auto magic = [](int w) { return (uint32_t)((((uint64_t)1 << 32) + (uint64_t)w - 1) / (uint64_t)w); };
     SampleDivisors dv{magic(lib->v.num_dofs), magic(lib->v.num_bodies * 3), magic(lib->v.num_bodies)};
-    sample_full_kernel<<<grid_for((S + 31) / 32, kSampleWarps, 8), kSampleWarps * 32, 0, as_stream(stream)>>>(
-        lib->v, dv, times, ids, S, dof_pos, dof_vel, body_pos, body_rot, body_lin, body_ang);
+    const int grid = grid_for((S + 31) / 32, kSampleWarps, 8);
+    cudaStream_t st = as_stream(stream);
+    const bool all_outputs = dof_pos && dof_vel && body_pos && body_rot && body_lin && body_ang;
+    if (lib->v.lerp_rows && all_outputs) {
+#define AMP_LAUNCH_ROWS(NS)                                                                                             \
+    case NS:                                                                                                            \
+        sample_rows_kernel<NS><<<grid, kSampleWarps * 32, 0, st>>>(lib->v, dv.body, times, ids, S, dof_pos, dof_vel, body_pos, \
+                                                                   body_rot, body_lin, body_ang);                      \
+        break
+        switch ((lib->v.lerp_width + 31) / 32) {
+            AMP_LAUNCH_ROWS(1); AMP_LAUNCH_ROWS(2); AMP_LAUNCH_ROWS(3); AMP_LAUNCH_ROWS(4); AMP_LAUNCH_ROWS(5); AMP_LAUNCH_ROWS(6);
+            AMP_LAUNCH_ROWS(7); AMP_LAUNCH_ROWS(8); AMP_LAUNCH_ROWS(9); AMP_LAUNCH_ROWS(10); AMP_LAUNCH_ROWS(11); AMP_LAUNCH_ROWS(12);
+            AMP_LAUNCH_ROWS(13); AMP_LAUNCH_ROWS(14); AMP_LAUNCH_ROWS(15); AMP_LAUNCH_ROWS(16);
+            default: return fail(AMP_EINVAL, "amp_sample_full: internal: lerp row width %d", lib->v.lerp_width);
+        }
+#undef AMP_LAUNCH_ROWS
+    } else {
+        sample_full_kernel<<<grid, kSampleWarps * 32, 0, st>>>(lib->v, dv, times, ids, S, dof_pos, dof_vel, body_pos, body_rot,
+                                                               body_lin, body_ang);
+    }
     AMP_CUDA_TRY(cudaGetLastError());
     return AMP_OK;
 }
@@ -763,8 +924,20 @@ int amp_compute_obs(const float *dof_pos, const float *dof_vel, const float *roo
     if (n == 0) return AMP_OK;
     AMP_REQUIRE((D == 0 || (dof_pos && dof_vel)) && root_pos && root_rot && root_lin && root_ang && (Kb == 0 || key_pos) && out,
                 "amp_compute_obs: NULL buffer");
-    compute_obs_kernel<<<grid_for(n, 8, 8), 256, 0, as_stream(stream)>>>(dof_pos, dof_vel, root_pos, root_rot, root_lin,
-                                                                         root_ang, key_pos, n, D, Kb, out);
+    const int A = 2 * D + 13 + 3 * Kb;
+    const int grid = grid_for(n, 8, 8);
+    cudaStream_t st = as_stream(stream);
+#define AMP_LAUNCH_OBS(NS)                                                                                              \
+    case NS:                                                                                                            \
+        compute_obs_kernel<NS><<<grid, 256, 0, st>>>(dof_pos, dof_vel, root_pos, root_rot, root_lin, root_ang, key_pos, n, D, \
+                                                     Kb, out);                                                          \
+        break
+    switch ((A + 31) / 32) {
+        AMP_LAUNCH_OBS(1); AMP_LAUNCH_OBS(2); AMP_LAUNCH_OBS(3); AMP_LAUNCH_OBS(4); AMP_LAUNCH_OBS(5); AMP_LAUNCH_OBS(6);
+        AMP_LAUNCH_OBS(7); AMP_LAUNCH_OBS(8);
+        default: return fail(AMP_EINVAL, "amp_compute_obs: observation width %d > 256 is not supported", A);
+    }
+#undef AMP_LAUNCH_OBS
     AMP_CUDA_TRY(cudaGetLastError());
     return AMP_OK;
 }
