@@ -535,7 +535,7 @@ __global__ void tangent_normal_kernel(const float *__restrict__ q, int64_t n, fl
 // before it is read; a lane touches only its own columns, so there is no cross-lane hazard), then slot 0 = the new row.
 // Reference g1_amp_env.py:176-193.
 template <int NSLOT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, NSLOT <= 3 ? 4 : 2)
 obs_step_kernel(const float *__restrict__ joint_pos, const float *__restrict__ joint_vel,
                 const float *__restrict__ body_pos, const float *__restrict__ body_quat,
                 const float *__restrict__ body_lin, const float *__restrict__ body_ang, int64_t N, int D, int Bsim,
@@ -547,7 +547,7 @@ obs_step_kernel(const float *__restrict__ joint_pos, const float *__restrict__ j
     const int D2 = 2 * D, A = D2 + 13 + 3 * Kb, policy_width = A - 3 * Kb;
 
     const float *src[NSLOT], *sub[NSLOT];  // value = src[i*stride] (- sub[i*3*Bsim] for key-body columns)
-    int64_t stride[NSLOT];
+    int stride[NSLOT];
     int tn_idx[NSLOT];                     // >= 0: the column is tangent/normal component tn_idx
     bool active[NSLOT];
 #pragma unroll
@@ -560,15 +560,15 @@ obs_step_kernel(const float *__restrict__ joint_pos, const float *__restrict__ j
         stride[s] = 0;
         if (c < D) { src[s] = joint_pos + c; stride[s] = D; }
         else if (c < D2) { src[s] = joint_vel + (c - D); stride[s] = D; }
-        else if (c == D2) { src[s] = body_pos + ref * 3 + 2; stride[s] = (int64_t)Bsim * 3; }
+        else if (c == D2) { src[s] = body_pos + ref * 3 + 2; stride[s] = Bsim * 3; }
         else if (c < D2 + 7) { tn_idx[s] = c - D2 - 1; }
-        else if (c < D2 + 10) { src[s] = body_lin + ref * 3 + (c - D2 - 7); stride[s] = (int64_t)Bsim * 3; }
-        else if (c < D2 + 13) { src[s] = body_ang + ref * 3 + (c - D2 - 10); stride[s] = (int64_t)Bsim * 3; }
+        else if (c < D2 + 10) { src[s] = body_lin + ref * 3 + (c - D2 - 7); stride[s] = Bsim * 3; }
+        else if (c < D2 + 13) { src[s] = body_ang + ref * 3 + (c - D2 - 10); stride[s] = Bsim * 3; }
         else if (c < A) {
             const int e = c - D2 - 13, j = e / 3, a = e - 3 * j;
             src[s] = body_pos + keys.k[j] * 3 + a;
             sub[s] = body_pos + ref * 3 + a;
-            stride[s] = (int64_t)Bsim * 3;
+            stride[s] = Bsim * 3;
         }
     }
 
@@ -581,17 +581,18 @@ obs_step_kernel(const float *__restrict__ joint_pos, const float *__restrict__ j
             minus[s] = sub[s] ? __ldg(sub[s] + i * stride[s]) : 0.0f;
         }
         float *env = amp_buf + i * (int64_t)K * A + lane;
-        // history shift, oldest slots first, up to eight slots per trip with all loads ahead of the stores
-        for (int hi = K - 2; hi >= 0; hi -= 8) {
-            const int lo = max(hi - 7, 0);
-            float h[8][NSLOT];
+        // history shift, oldest slots first, up to four slots per trip with all loads ahead of the stores
+        constexpr int HB = 4;
+        for (int hi = K - 2; hi >= 0; hi -= HB) {
+            const int lo = max(hi - (HB - 1), 0);
+            float h[HB][NSLOT];
 #pragma unroll
-            for (int t = 0; t < 8; ++t)
+            for (int t = 0; t < HB; ++t)
 #pragma unroll
                 for (int s = 0; s < NSLOT; ++s)
                     if (hi - t >= lo && active[s]) h[t][s] = env[(int64_t)(hi - t) * A + 32 * s];
 #pragma unroll
-            for (int t = 0; t < 8; ++t)
+            for (int t = 0; t < HB; ++t)
 #pragma unroll
                 for (int s = 0; s < NSLOT; ++s)
                     if (hi - t >= lo && active[s]) env[(int64_t)(hi - t + 1) * A + 32 * s] = h[t][s];
