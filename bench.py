@@ -44,6 +44,13 @@ if ROOT not in sys.path:
 METRIC = "amp_obs_samples_per_s(sample+obs+disc_reward)"
 UNIT = "samples/s"
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of the DEFAULT workload
+# (profiles/r01_ncu_full_v4_collect_cast.metrics.txt, profiles/r01_ncu_fused_dram_with_l2_hints.csv); None for other workloads
+NCU_TRAFFIC_BYTES = {
+    "collect_reference_kernel": 16_283_392 + 605_972_736,  # 1 M samples x K=2 (algorithmic 680 MB; the tail still sat in L2)
+    "disc_fused_kernel": 278_443_520 + 534_667_520,        # one 500 k-row launch: x_hat read + h1 slot write-backs
+}
+
 WORKLOADS = {
     # name: clip shape, samples per GPU, history K, reward rows multiplier, flush L2, extra stages
     "refill_1m": dict(clip="G1_walk", n=1_000_000, K=2, reward_mult=1, flush=False, env_step=False, allreduce=False, strong=False),
@@ -189,8 +196,8 @@ def run_reference(args, spec, rank, world):
         torch.set_num_threads(os.cpu_count() or 1)
     with tempfile.TemporaryDirectory() as tmp:
         clip_files = make_clip_files(tmp, spec["clip"])
-        n_cpu = min(spec["n"], 32768)
-        steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+        n_cpu = min(spec["n"], 262144)  # bounded sample of the workload per step
+        steps, warmup = max(1, min(args.steps, 20)), max(1, min(args.warmup, 2))
         value, ms, threads, sample = cpu_reference_pass(spec, clip_files, n_cpu, steps, warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
@@ -369,20 +376,23 @@ def run_ours(args, spec, rank, world, local_rank):
     tensor_peak = peaks["bf16_sustained"]
     roofline = {
         "kernel": "disc_fused_kernel (tcgen05 two-layer discriminator + style reward) + normalise_cast_kernel: 2 launches per chunk", "bound": "tensor",
-        "achieved": disc_tflops, "peak": tensor_peak, "unit": "TFLOP/s", "frac": disc_tflops / tensor_peak, "traffic": None,
+        "achieved": disc_tflops, "peak": tensor_peak, "unit": "TFLOP/s", "frac": disc_tflops / tensor_peak,
+        "traffic": NCU_TRAFFIC_BYTES["disc_fused_kernel"] if args.workload == "refill_1m" and not args.samples else None,
+        "traffic_note": "DRAM bytes of ONE fused launch (500 k rows; two per step), ncu --set full",
         "algorithmic_flops_per_launch_group": disc_flops, "ms": disc_ms / args.steps, "peak_source": peaks["source"] + ", sustained bf16",
     }
     roofline_hbm = {
         "kernel": "collect_reference_kernel (+ obs_step_kernel)" if state is not None else "collect_reference_kernel", "bound": "hbm",
-        "achieved": obs_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": obs_gbs / peaks["hbm_gbs"], "traffic": None,
+        "achieved": obs_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": obs_gbs / peaks["hbm_gbs"],
+        "traffic": NCU_TRAFFIC_BYTES["collect_reference_kernel"] if args.workload == "refill_1m" and not args.samples else None,
         "algorithmic_bytes_per_launch": obs_bytes, "ms": obs_ms / args.steps, "us_per_call": obs_ms / args.steps * 1e3, "peak_source": peaks["source"],
     }
 
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            n_cpu = min(n, 32768)
-            v, ms, threads, sample = cpu_reference_pass(spec, clip_files, n_cpu, steps=3, warmup=1)
+            n_cpu = min(n, 262144)  # bounded sample: ~0.6 s per step on 16 cores -> ~6-10 s of CPU work in total
+            v, ms, threads, sample = cpu_reference_pass(spec, clip_files, n_cpu, steps=10 if n_cpu >= 65536 else 30, warmup=1)
             cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "ms_per_step": ms}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
