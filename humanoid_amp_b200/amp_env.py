@@ -76,6 +76,11 @@ class AmpEnvCfg:
     num_envs: int = 4096
     num_amp_observations: int = 2
     robot: RobotSpec = G1
+    # policy-observation fields (g1_amp_env_cfg.py:32, 43, 47, 173-184); only used by get_observations()
+    num_actor_observations: int = 1
+    rew_track_vel: float = 0.0  # > 0: the 2-d velocity command is part of the actor observation
+    history_include_last_actions: bool = True
+    history_include_command: bool = True
 
     @property
     def amp_observation_space(self) -> int:
@@ -84,6 +89,25 @@ class AmpEnvCfg:
     @property
     def reference_body(self) -> str:
         return self.robot.reference_body
+
+    @property
+    def action_space(self) -> int:
+        return self.robot.num_joints
+
+    @property
+    def command_size(self) -> int:
+        return 2 if self.rew_track_vel > 0.0 else 0
+
+    @property
+    def hist_frame_size(self) -> int:
+        base = self.amp_observation_space - 3 * len(self.robot.key_body_names)
+        return base + (self.action_space if self.history_include_last_actions else 0) + (self.command_size if self.history_include_command else 0)
+
+    @property
+    def observation_space(self) -> int:
+        """Actor observation width, as ``__post_init__`` sizes it (g1_amp_env_cfg.py:186-206)."""
+        cur = self.amp_observation_space - 3 * len(self.robot.key_body_names) + self.action_space + self.command_size
+        return cur + max(self.num_actor_observations - 1, 0) * self.hist_frame_size
 
 
 class AmpEnvPath:
@@ -116,6 +140,16 @@ class AmpEnvPath:
         )
         assert self._handle.obs_width == cfg.amp_observation_space
         self._key_idx_host = np.ascontiguousarray(self.key_body_indexes, dtype=np.int32)
+        # policy-observation state (g1_amp_env.py:75-119)
+        self.key_body_obs_size = len(key_body_names) * 3
+        self.last_actions = torch.zeros((self.num_envs, cfg.action_space), device=self.device)
+        self.command_target_speed = torch.zeros((self.num_envs, 2), device=self.device, dtype=torch.float32)
+        if cfg.num_actor_observations > 1:
+            self.actor_obs_hist_per_frame = cfg.hist_frame_size
+            self.actor_obs_history_buffer = torch.zeros(
+                (self.num_envs, cfg.num_actor_observations - 1, self.actor_obs_hist_per_frame), device=self.device
+            )
+            self._just_reset_mask = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
 
     # ---- reference motions (skrl calls this with one argument) ------------------------------------------------------
     def collect_reference_motions(self, num_samples: int, current_times=None, motion_ids=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -194,6 +228,35 @@ class AmpEnvPath:
         self.extras = {"amp_obs": self.amp_observation_buffer.view(-1, self.amp_observation_size)}
         return self.extras["amp_obs"]
 
+    # ---- policy observation (reference _get_observations :195-242) ---------------------------------
+    def get_observations(self, joint_pos, joint_vel, body_pos_w, body_quat_w, body_lin_vel_w, body_ang_vel_w, out: Optional[torch.Tensor] = None) -> dict:
+        """The whole ``_get_observations``: AMP history update (``extras["amp_obs"]``) and ``{"policy": actor_obs}``.
+
+        Uses ``self.last_actions``, ``self.command_target_speed`` (when ``cfg.rew_track_vel > 0``), the actor history
+        buffer and ``self._just_reset_mask`` exactly as the reference does; two kernel launches in total."""
+        self.update_amp_observations(joint_pos, joint_vel, body_pos_w, body_quat_w, body_lin_vel_w, body_ang_vel_w)
+        cfg = self.cfg
+        n = cfg.num_actor_observations
+        width = cfg.observation_space
+        if out is None:
+            out = torch.empty((self.num_envs, width), dtype=torch.float32, device=self.device)
+        if out.dtype != torch.float32 or out.stride(-1) != 1 or out.shape[-1] < width:
+            raise RuntimeError("actor observation output must be float32 rows of at least observation_space columns")
+        cmd = self.command_target_speed if cfg.command_size else None
+        hist = self.actor_obs_history_buffer if n > 1 else None
+        mask = self._just_reset_mask if n > 1 else None
+        actions = _f32c(self.last_actions, self.device)
+        lib, stream = _lib.enter(self.device)
+        _lib.check(
+            lib.amp_actor_obs_step(
+                _lib.ptr(self.amp_observation_buffer), self.num_envs, cfg.num_amp_observations, cfg.amp_observation_space,
+                cfg.amp_observation_space - self.key_body_obs_size, _lib.ptr(actions), cfg.action_space, _lib.ptr(cmd),
+                cfg.command_size, n, int(cfg.history_include_last_actions), int(cfg.history_include_command), _lib.ptr(hist),
+                _lib.ptr(mask), _lib.ptr(out), out.stride(0), stream,
+            )  # fmt: skip
+        )
+        return {"policy": out[:, :width]}
+
     # ---- reset (reference _reset_strategy_random :371-419, AMP part) -------------------------------------------------
     def reset_amp_history(self, env_ids, times, motion_ids) -> None:
         """Reset envs receive their reference history: fused collect + scatter into ``amp_observation_buffer[env_ids]``."""
@@ -205,6 +268,33 @@ class AmpEnvPath:
         if rows.numel() != n:
             raise RuntimeError("env_ids and times must have the same length")
         self._launch_collect(t, ids, n, self.amp_observation_buffer.view(self.num_envs, -1), row_index=rows)
+
+    def reset_strategy_random(self, env_ids, default_root_state: torch.Tensor, env_origins: torch.Tensor, start: bool = False):
+        """Reference ``_reset_strategy_random`` (``g1_amp_env.py:371-419``) without the simulator writes and the command
+        resampling: draws (motion id, time) per env with the reference's host RNG stream, samples the frame, builds
+        ``root_state (n, 13)`` (position + env origin, z lifted by 0.05, rotation, linear / angular velocity of the
+        ``pelvis``), the robot-order dof state, and fills ``amp_observation_buffer[env_ids]`` with the reference history
+        (fused collect + scatter).  Returns ``(root_state, dof_pos, dof_vel, motion_ids, times)``.
+
+        The root/dof assembly is a handful of torch index ops on the sampled tensors (reset-time glue, SURVEY 8f item 3);
+        sampling and the history fill run in ``libamp_b200.so``."""
+        loader = self._motion_loader
+        ids_dev = torch.as_tensor(env_ids, device=self.device, dtype=torch.int64).view(-1)
+        n = ids_dev.numel()
+        motion_ids, times = loader.sample_times(n, start=start)
+        dof_p, dof_v, body_p, body_r, body_lv, body_av = loader.sample(num_samples=n, times=times, motion_ids=motion_ids)
+        torso = loader.get_body_index(["pelvis"])[0] if "pelvis" in loader.body_names else self.motion_ref_body_index
+        root_state = default_root_state.to(self.device, torch.float32).clone()
+        root_state[:, 0:3] = body_p[:, torso] + env_origins.to(self.device, torch.float32)
+        root_state[:, 2] += 0.05
+        root_state[:, 3:7] = body_r[:, torso]
+        root_state[:, 7:10] = body_lv[:, torso]
+        root_state[:, 10:13] = body_av[:, torso]
+        self.reset_amp_history(ids_dev, times, motion_ids)
+        self.last_actions[ids_dev] = 0.0
+        if self.cfg.num_actor_observations > 1:
+            self._just_reset_mask[ids_dev] = True
+        return root_state, dof_p[:, self.motion_dof_indexes], dof_v[:, self.motion_dof_indexes], motion_ids, times
 
     def poll_flags(self) -> int:
         lib, stream = _lib.enter(self.device)

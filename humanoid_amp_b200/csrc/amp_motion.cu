@@ -610,6 +610,49 @@ obs_step_kernel(const float *__restrict__ joint_pos, const float *__restrict__ j
     }
 }
 
+// Actor observation + its history (g1_amp_env.py:195-242): one warp per env, lanes stride the columns.
+__global__ void __launch_bounds__(256)
+actor_obs_kernel(const float *__restrict__ amp_buf, int64_t N, int K, int A, int base, const float *__restrict__ last_actions,
+                 int act, const float *__restrict__ command, int cmd, int n_hist /* n - 1 */, int inc_act, int inc_cmd,
+                 float *__restrict__ hist_buf, uint8_t *__restrict__ just_reset, float *__restrict__ actor_obs,
+                 int64_t actor_stride) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int cur = base + act + cmd;
+    const int hact = inc_act ? act : 0, hcmd = inc_cmd ? cmd : 0, P = base + hact + hcmd;
+    for (int64_t i = warp; i < N; i += nwarps) {
+        const float *obs0 = amp_buf + i * (int64_t)K * A;  // slot 0 = newest
+        float *arow = actor_obs + i * actor_stride;
+        for (int c = lane; c < cur; c += 32) {
+            float val;
+            if (c < base) val = obs0[c];
+            else if (c < base + act) val = __ldg(last_actions + i * act + (c - base));
+            else val = __ldg(command + i * cmd + (c - base - act));
+            arow[c] = val;
+        }
+        if (n_hist <= 0) continue;
+        const bool reset = just_reset && just_reset[i] != 0;
+        float *hist = hist_buf + i * (int64_t)n_hist * P;
+        for (int pc = lane; pc < P; pc += 32) {
+            float frame;
+            if (pc < base) frame = obs0[pc];
+            else if (pc < base + hact) frame = __ldg(last_actions + i * act + (pc - base));
+            else frame = __ldg(command + i * cmd + (pc - base - hact));
+            // slots from the oldest down: slot s takes slot s-1 (or the new frame everywhere after a reset)
+            for (int sl = n_hist - 1; sl >= 1; --sl) {
+                const float moved = reset ? frame : hist[(int64_t)(sl - 1) * P + pc];
+                hist[(int64_t)sl * P + pc] = moved;
+                arow[cur + (int64_t)sl * P + pc] = moved;
+            }
+            hist[pc] = frame;
+            arow[cur + pc] = frame;
+        }
+        __syncwarp();
+        if (reset && lane == 0) just_reset[i] = 0;
+    }
+}
+
 // ---- host helpers -------------------------------------------------------------------------------------------------
 static int grid_for(int64_t items, int per_block, int ctas_per_sm) {
     const int64_t want = (items + per_block - 1) / per_block;
@@ -987,6 +1030,26 @@ int amp_obs_step(const float *joint_pos, const float *joint_vel, const float *bo
         default: return fail(AMP_EINVAL, "amp_obs_step: observation width %d > 256 is not supported", A);
     }
 #undef AMP_LAUNCH_STEP
+    AMP_CUDA_TRY(cudaGetLastError());
+    return AMP_OK;
+}
+
+int amp_actor_obs_step(const float *amp_buf, int64_t N, int32_t K, int32_t A, int32_t base_width, const float *last_actions,
+                       int32_t act, const float *command, int32_t cmd, int32_t num_actor_observations,
+                       int32_t hist_include_actions, int32_t hist_include_command, float *hist_buf, uint8_t *just_reset,
+                       float *actor_obs, int64_t actor_stride, void *stream) {
+    AMP_REQUIRE(N >= 0 && K >= 1 && A >= 1 && base_width >= 1 && base_width <= A && act >= 0 && cmd >= 0,
+                "amp_actor_obs_step: bad sizes");
+    AMP_REQUIRE(num_actor_observations >= 1, "amp_actor_obs_step: num_actor_observations must be >= 1");
+    if (N == 0) return AMP_OK;
+    AMP_REQUIRE(amp_buf && actor_obs && (act == 0 || last_actions) && (cmd == 0 || command), "amp_actor_obs_step: NULL buffer");
+    const int n_hist = num_actor_observations - 1;
+    AMP_REQUIRE(n_hist == 0 || hist_buf, "amp_actor_obs_step: history buffer required when num_actor_observations > 1");
+    const int P = base_width + (hist_include_actions ? act : 0) + (hist_include_command ? cmd : 0);
+    AMP_REQUIRE(actor_stride >= base_width + act + cmd + (int64_t)n_hist * P, "amp_actor_obs_step: actor_stride too small");
+    actor_obs_kernel<<<grid_for(N, 8, 8), 256, 0, as_stream(stream)>>>(amp_buf, N, K, A, base_width, last_actions, act, command, cmd,
+                                                                       n_hist, hist_include_actions, hist_include_command, hist_buf,
+                                                                       just_reset, actor_obs, actor_stride);
     AMP_CUDA_TRY(cudaGetLastError());
     return AMP_OK;
 }

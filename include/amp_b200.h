@@ -147,6 +147,19 @@ AMP_API int amp_obs_step(const float *joint_pos, const float *joint_vel, const f
                  int32_t ref_body, const int32_t *key_bodies, int32_t Kb, int32_t K, float *amp_buf, float *policy_obs,
                  int64_t policy_stride, void *stream);
 
+/* Policy ("actor") observation of G1AmpEnv._get_observations (g1_amp_env.py:195-242) -- SURVEY.md section 8f item 1.
+ *   amp_buf (N,K,A): slot 0 holds this step's compute_obs row (written by amp_obs_step); base = its first `base_width`
+ *   columns (A - 3*Kb).  last_actions (N, act).  command (N, cmd) or NULL with cmd = 0 (cfg.rew_track_vel <= 0).
+ *   n = num_actor_observations.  n == 1: actor_obs = [base | last_actions | command].
+ *   n  > 1: current = [base | last_actions | command]; history frame = [base | last_actions? | command?] (the two include
+ *   flags); hist_buf (N, n-1, P) is updated in place: envs whose just_reset byte is set get every slot = the new history
+ *   frame (warm start) and the byte is cleared, the others shift slot i -> i+1 and take the new frame in slot 0;
+ *   actor_obs = [current | hist_buf flattened].  actor_obs rows are actor_stride floats apart. */
+AMP_API int amp_actor_obs_step(const float *amp_buf, int64_t N, int32_t K, int32_t A, int32_t base_width,
+                               const float *last_actions, int32_t act, const float *command, int32_t cmd,
+                               int32_t num_actor_observations, int32_t hist_include_actions, int32_t hist_include_command,
+                               float *hist_buf, uint8_t *just_reset, float *actor_obs, int64_t actor_stride, void *stream);
+
 /* ---- discriminator style reward (skrl AMP._update; cfg agents/skrl_g1_dance_amp_cfg.yaml:31-39, 80, 94-95) ------ */
 /* Network Linear(in,h1)-ReLU-Linear(h1,h2)-ReLU-Linear(h2,1) on RunningStandardScaler-normalised input.
  * h1, h2 must be multiples of 128 (reference: 1024, 512); in_features any value >= 1 (padded to 64 internally). */

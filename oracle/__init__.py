@@ -36,5 +36,7 @@ from .env_oracle import (  # noqa: F401
     history_times,
     shift_and_write_history,
     reset_fill,
+    actor_observations,
+    reset_root_and_dof_state,
 )
 from .disc_oracle import OracleDiscriminator, running_standard_scaler_eval, style_reward_from_logits  # noqa: F401

@@ -7,6 +7,7 @@ Follows ``/root/reference/g1_amp_env.py`` (the 28-DoF humanoid env ``humanoid_am
 * ``collect_reference_motions`` .......... ``:445-486``
 * history shift + slot-0 write ........... ``:187-193``
 * reset-time history fill ................ ``:414-419``
+* actor observation + its history ........ ``:195-242`` (the first "next" row)
 
 ``quat_apply`` is upstream ``isaaclab.utils.math.quat_apply`` (Isaac Lab 2.2.0, not vendored; call sites
 ``g1_amp_env.py:16, 495-496``): restated from its published form, PARITY UNPINNED for that function alone.
@@ -105,3 +106,50 @@ def shift_and_write_history(buffer: torch.Tensor, obs: torch.Tensor) -> torch.Te
 def reset_fill(buffer: torch.Tensor, env_ids: torch.Tensor, amp_observations: torch.Tensor) -> None:
     """Reference ``g1_amp_env.py:417-419``: reset envs receive the reference history rows.  In place."""
     buffer[env_ids] = amp_observations.view(env_ids.shape[0], buffer.shape[1], -1)
+
+
+def actor_observations(obs, last_actions, command, history_buffer, just_reset_mask, num_actor_observations, key_body_obs_size=12,
+                       history_include_last_actions=True, history_include_command=True):
+    """Reference ``g1_amp_env.py:195-242`` (policy observation of ``_get_observations``).
+
+    ``obs`` is this step's ``compute_obs`` row; ``command`` is ``None`` when ``cfg.rew_track_vel <= 0``.  With history
+    (``num_actor_observations > 1``) ``history_buffer`` is ``(N, n-1, P)`` and ``just_reset_mask`` ``(N,) bool``; both are
+    updated in place exactly like the reference: warm start of just-reset envs, shift, slot 0 = the new history frame.
+    """
+    base = obs[:, :-key_body_obs_size]
+    if num_actor_observations > 1:
+        current_parts = [base, last_actions]
+        if command is not None:
+            current_parts.append(command)
+        current_frame = torch.cat(current_parts, dim=-1)
+        hist_parts = [base]
+        if history_include_last_actions:
+            hist_parts.append(last_actions)
+        if history_include_command and command is not None:
+            hist_parts.append(command)
+        hist_frame = torch.cat(hist_parts, dim=-1)
+        if just_reset_mask.any():
+            for i in range(num_actor_observations - 1):
+                history_buffer[just_reset_mask, i] = hist_frame[just_reset_mask]
+            just_reset_mask[:] = False
+        for i in reversed(range(num_actor_observations - 2)):
+            history_buffer[:, i + 1] = history_buffer[:, i]
+        history_buffer[:, 0] = hist_frame
+        return torch.cat([current_frame, history_buffer.view(obs.shape[0], -1)], dim=-1)
+    actor_obs = torch.cat([base, last_actions], dim=-1)
+    if command is not None:
+        actor_obs = torch.cat([actor_obs, command], dim=-1)
+    return actor_obs
+
+
+def reset_root_and_dof_state(loader, times, motion_ids, default_root_state, env_origins, motion_dof_indexes, torso_index):
+    """Reference ``g1_amp_env.py:386-411`` (state part of ``_reset_strategy_random``): root pose / velocity and dof state of
+    the sampled frame; the root is lifted by 0.05 to avoid ground collisions."""
+    dof_p, dof_v, body_p, body_r, body_lv, body_av = loader.sample(num_samples=len(times), times=times, motion_ids=motion_ids)
+    root_state = default_root_state.clone()
+    root_state[:, 0:3] = body_p[:, torso_index] + env_origins
+    root_state[:, 2] += 0.05
+    root_state[:, 3:7] = body_r[:, torso_index]
+    root_state[:, 7:10] = body_lv[:, torso_index]
+    root_state[:, 10:13] = body_av[:, torso_index]
+    return root_state, dof_p[:, motion_dof_indexes], dof_v[:, motion_dof_indexes]

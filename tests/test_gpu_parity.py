@@ -282,6 +282,78 @@ def test_env_step_history_vs_oracle(loaders, amp, K, robot_name):
     assert env.extras["amp_obs"].shape == (N, K * robot.amp_observation_space)
 
 
+@pytest.mark.parametrize("n_actor,track,inc_act,inc_cmd", [(1, 0.0, True, True), (1, 1.0, True, True), (2, 1.0, True, True),
+                                                         (4, 1.0, False, True), (3, 1.0, True, False), (5, 0.0, True, True)])
+def test_actor_observation_history_vs_oracle(loaders, amp, n_actor, track, inc_act, inc_cmd):
+    """the policy observation of ``_get_observations`` (g1_amp_env.py:195-242) incl. warm start."""
+    from oracle import env_oracle
+    from humanoid_amp_b200.synthetic import synthetic_sim_state
+
+    loader = loaders("G1_dance")
+    N, K = 200, 3
+    cfg = amp.AmpEnvCfg(motion_file="<preloaded>", num_envs=N, num_amp_observations=K, robot=amp.G1, num_actor_observations=n_actor,
+                        rew_track_vel=track, history_include_last_actions=inc_act, history_include_command=inc_cmd)
+    env = amp.AmpEnvPath(cfg, "cuda:0", motion_loader=loader)
+    P = cfg.hist_frame_size
+    ref_hist = torch.zeros(N, max(n_actor - 1, 1), P)
+    ref_mask = torch.zeros(N, dtype=torch.bool)
+    g = torch.Generator().manual_seed(n_actor * 7 + int(track))
+    for step in range(n_actor + 3):
+        state = synthetic_sim_state(N, amp.G1, "cpu", seed=300 + step)
+        jp, jv, bp, bq, bl, ba = state
+        actions = torch.randn(N, 29, generator=g)
+        command = torch.rand(N, 2, generator=g) * 2 - 1
+        if step in (0, 2):  # some envs were reset before this step
+            picked = torch.rand(N, generator=g) < 0.3
+            ref_mask |= picked
+            if n_actor > 1:
+                env._just_reset_mask |= picked.cuda()
+        env.last_actions.copy_(actions)
+        env.command_target_speed.copy_(command)
+        obs = env_oracle.compute_obs(jp, jv, bp[:, env.ref_body_index], bq[:, env.ref_body_index], bl[:, env.ref_body_index],
+                                     ba[:, env.ref_body_index], bp[:, env.key_body_indexes])  # fmt: skip
+        want = env_oracle.actor_observations(obs, actions, command if track > 0 else None, ref_hist, ref_mask, n_actor,
+                                             history_include_last_actions=inc_act, history_include_command=inc_cmd)  # fmt: skip
+        got = env.get_observations(*[t.cuda() for t in state])["policy"]
+        assert got.shape == want.shape == (N, cfg.observation_space)
+        close(got, want)  # the six tangent/normal columns differ from torch by <= 1 ulp, everything else is a copy
+        if n_actor > 1:
+            close(env.actor_obs_history_buffer, ref_hist)
+            assert not env._just_reset_mask.any() and not ref_mask.any()
+
+
+def test_reset_strategy_random_state_vs_oracle(loaders, amp):
+    """SURVEY 8f item 3 (reset-state write, g1_amp_env.py:371-419): same host RNG stream, same root / dof state, and the
+    reset envs' AMP history rows."""
+    from oracle import OracleMotionLoader, env_oracle
+
+    loader = loaders("G1_walk")
+    ora = OracleMotionLoader([clip_path("G1_walk")])
+    N, K = 96, 10
+    env = make_env(amp, loader, K, num_envs=N)
+    robot = env.cfg.robot
+    g = torch.Generator().manual_seed(2)
+    default_root = torch.randn(N, 13, generator=g)
+    origins = torch.randn(N, 3, generator=g) * 5
+    env_ids = torch.arange(0, N, 3)
+    np.random.seed(99)
+    root, dof_p, dof_v, mids, times = env.reset_strategy_random(env_ids, default_root[env_ids].cuda(), origins[env_ids].cuda())
+    np.random.seed(99)
+    want_ids, want_times = ora.sample_times(len(env_ids))
+    assert np.array_equal(mids, want_ids) and np.array_equal(times, want_times)
+    w_root, w_dp, w_dv = env_oracle.reset_root_and_dof_state(ora, want_times, want_ids, default_root[env_ids], origins[env_ids],
+                                                            ora.get_dof_index(robot.joint_names), ora.get_body_index(["pelvis"])[0])  # fmt: skip
+    close(root, w_root)
+    bit_equal(dof_p, w_dp)
+    bit_equal(dof_v, w_dv)
+    rows = env_oracle.collect_reference_motions(ora, len(env_ids), K, ora.get_dof_index(robot.joint_names), 0,
+                                                ora.get_body_index(robot.key_body_names), current_times=want_times, motion_ids=want_ids)  # fmt: skip
+    close(env.amp_observation_buffer[env_ids.cuda()].view(len(env_ids), -1), rows)
+    untouched = torch.ones(N, dtype=torch.bool)
+    untouched[env_ids] = False
+    assert not env.amp_observation_buffer[untouched.cuda()].any()
+
+
 def test_reset_fill_scatter_and_ring_memory(loaders, amp):
     from oracle import OracleMotionLoader, env_oracle
 
