@@ -75,6 +75,7 @@ SIGNATURES = {
     "amp_tangent_normal": (C.c_int, [_P, _I64, _P, _P]),
     "amp_obs_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _I32, _I32, _P, _P, _I64, _P]),
     "amp_actor_obs_step": (C.c_int, [_P, _I64, _I32, _I32, _I32, _P, _I32, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _I64, _P]),
+    "amp_task_reward": (C.c_int, [_P, _P, _P, _I32, _P, _P, _P, _P, _I32, _P, _P, _I32, _I32, _P, _I64, _P, _P, _P, _P]),
     "amp_disc_create": (C.c_int, [_I32, _I32, _I32, _I64, _P, C.POINTER(_P)]),
     "amp_disc_destroy": (C.c_int, [_P]),
     "amp_disc_chunk_rows": (C.c_int64, [_P]),

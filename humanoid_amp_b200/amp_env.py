@@ -79,6 +79,12 @@ class AmpEnvCfg:
     # policy-observation fields (g1_amp_env_cfg.py:32, 43, 47, 173-184); only used by get_observations()
     num_actor_observations: int = 1
     rew_track_vel: float = 0.0  # > 0: the 2-d velocity command is part of the actor observation
+    # task-reward scales (g1_amp_env_cfg.py:27-31, 86-90); only used by get_rewards()
+    rew_termination: float = 0.0
+    rew_action_l2: float = 0.0
+    rew_joint_pos_limits: float = 0.0
+    rew_joint_acc_l2: float = 0.0
+    rew_joint_vel_l2: float = 0.0
     history_include_last_actions: bool = True
     history_include_command: bool = True
 
@@ -256,6 +262,35 @@ class AmpEnvPath:
             )  # fmt: skip
         )
         return {"policy": out[:, :width]}
+
+    # ---- task reward (reference _get_rewards :246-319) ----------------------------------------------
+    def get_rewards(self, reset_terminated, actions, joint_pos, soft_joint_pos_limits, joint_acc, joint_vel, body_lin_vel_w=None,
+                    body_quat_w=None, return_terms: bool = False):
+        """``basic_reward + rew_track_vel`` in one kernel.  ``return_terms=True`` also returns the ``(N, 6)`` per-term tensor
+        (termination, action_l2, joint_pos_limits, joint_acc_l2, joint_vel_l2, track_vel) and the tracking error, from
+        which the reference's ``extras["log"]`` means follow without a host sync per term."""
+        cfg, dev = self.cfg, self.device
+        term = reset_terminated.to(dev).to(torch.uint8).contiguous()
+        args = [_f32c(t, dev) for t in (actions, joint_pos, soft_joint_pos_limits, joint_acc, joint_vel)]
+        N, D = args[1].shape
+        scales = np.array([cfg.rew_termination, cfg.rew_action_l2, cfg.rew_joint_pos_limits, cfg.rew_joint_acc_l2,
+                           cfg.rew_joint_vel_l2, cfg.rew_track_vel], dtype=np.float32)  # fmt: skip
+        track = cfg.rew_track_vel > 0.0
+        lin = _f32c(body_lin_vel_w, dev) if track else None
+        quat = _f32c(body_quat_w, dev) if track else None
+        cmd = _f32c(self.command_target_speed, dev) if track else None
+        total = torch.empty(N, dtype=torch.float32, device=dev)
+        terms = torch.empty((N, 6), dtype=torch.float32, device=dev) if return_terms else None
+        err = torch.empty(N, dtype=torch.float32, device=dev) if return_terms else None
+        lib, stream = _lib.enter(dev)
+        _lib.check(
+            lib.amp_task_reward(
+                _lib.ptr(scales), _lib.ptr(term), _lib.ptr(args[0]), args[0].shape[1], _lib.ptr(args[1]), _lib.ptr(args[2]),
+                _lib.ptr(args[3]), _lib.ptr(args[4]), D, _lib.ptr(lin), _lib.ptr(quat), quat.shape[1] if track else 0,
+                self.ref_body_index, _lib.ptr(cmd), N, _lib.ptr(total), _lib.ptr(terms), _lib.ptr(err), stream,
+            )  # fmt: skip
+        )
+        return (total, terms, err) if return_terms else total
 
     # ---- reset (reference _reset_strategy_random :371-419, AMP part) -------------------------------------------------
     def reset_amp_history(self, env_ids, times, motion_ids) -> None:

@@ -16,6 +16,7 @@
 //
 // Compile with -fmad=false (see amp_math.cuh).
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <new>
 
@@ -653,6 +654,77 @@ actor_obs_kernel(const float *__restrict__ amp_buf, int64_t N, int K, int A, int
     }
 }
 
+// Task reward (g1_amp_env.py:246-288, 500-532, 564-606): one warp per env; the per-joint sums are lane-strided partial sums
+// combined with a fixed shuffle tree (deterministic), lane 0 finishes the scalar part.
+struct RewardScales {
+    float termination, action_l2, joint_pos_limits, joint_acc_l2, joint_vel_l2, track_vel;
+    float exp_at_floor, linear_slope;  // weight*exp(-floor), weight/sigma^2*exp(-floor), evaluated in double on the host
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(256)
+task_reward_kernel(RewardScales sc, const uint8_t *__restrict__ terminated, const float *__restrict__ actions, int act,
+                   const float *__restrict__ joint_pos, const float *__restrict__ limits, const float *__restrict__ joint_acc,
+                   const float *__restrict__ joint_vel, int D, const float *__restrict__ body_lin, const float *__restrict__ body_quat,
+                   int Bsim, int ref, const float *__restrict__ command, int64_t N, float *__restrict__ total,
+                   float *__restrict__ terms, float *__restrict__ track_err) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp; i < N; i += nwarps) {
+        float s_act = 0.0f, s_lim = 0.0f, s_acc = 0.0f, s_vel = 0.0f;
+        for (int j = lane; j < act; j += 32) {
+            const float a = __ldg(actions + i * act + j);
+            s_act += a * a;
+        }
+        for (int j = lane; j < D; j += 32) {
+            const float p = __ldg(joint_pos + i * D + j);
+            const float2 lim = __ldg(reinterpret_cast<const float2 *>(limits) + i * D + j);
+            s_lim += -fminf(p - lim.x, 0.0f) + fmaxf(p - lim.y, 0.0f);
+            const float a = __ldg(joint_acc + i * D + j), w = __ldg(joint_vel + i * D + j);
+            s_acc += a * a;
+            s_vel += w * w;
+        }
+        s_act = warp_sum(s_act);
+        s_lim = warp_sum(s_lim);
+        s_acc = warp_sum(s_acc);
+        s_vel = warp_sum(s_vel);
+        if (lane == 0) {
+            const float r_term = sc.termination * (terminated[i] ? 1.0f : 0.0f);
+            const float r_act = sc.action_l2 * s_act, r_lim = sc.joint_pos_limits * s_lim;
+            const float r_acc = sc.joint_acc_l2 * s_acc, r_vel = sc.joint_vel_l2 * s_vel;
+            float r_track = 0.0f, err = 0.0f;
+            if (sc.track_vel > 0.0f) {
+                const float4 q = __ldg(reinterpret_cast<const float4 *>(body_quat) + i * Bsim + ref);  // w x y z
+                const float *vp = body_lin + (i * Bsim + ref) * 3;
+                const float vx = __ldg(vp), vy = __ldg(vp + 1), vz = __ldg(vp + 2);
+                // quat_rotate_inverse: v*(2w^2-1) - 2w (xyz x v) + 2 xyz (xyz . v); only x and y are needed
+                const float k = 2.0f * (q.x * q.x) - 1.0f;
+                const float cx = q.z * vz - q.w * vy, cy = q.w * vx - q.y * vz;  // (xyz x v).x, .y
+                const float dotv = q.y * vx + q.z * vy + q.w * vz;
+                const float bx = vx * k - cx * q.x * 2.0f + q.y * dotv * 2.0f;
+                const float by = vy * k - cy * q.x * 2.0f + q.z * dotv * 2.0f;
+                const float dx = bx - __ldg(command + i * 2), dy = by - __ldg(command + i * 2 + 1);
+                err = sqrtf(dx * dx + dy * dy);
+                const float e2 = err * err;
+                // exp_reward_with_floor(e2, weight, sigma = 0.5, floor = 4.0): threshold = floor * sigma^2 = 1.0
+                r_track = e2 > 1.0f ? sc.exp_at_floor - sc.linear_slope * (e2 - 1.0f) : sc.track_vel * expf(-e2 / 0.25f);
+            }
+            total[i] = ((((r_term + r_act) + r_lim) + r_acc) + r_vel) + r_track;
+            if (terms) {
+                float *t = terms + i * 6;
+                t[0] = r_term; t[1] = r_act; t[2] = r_lim; t[3] = r_acc; t[4] = r_vel; t[5] = r_track;
+            }
+            if (track_err) track_err[i] = err;
+        }
+    }
+}
+
 // ---- host helpers -------------------------------------------------------------------------------------------------
 static int grid_for(int64_t items, int per_block, int ctas_per_sm) {
     const int64_t want = (items + per_block - 1) / per_block;
@@ -1050,6 +1122,37 @@ int amp_actor_obs_step(const float *amp_buf, int64_t N, int32_t K, int32_t A, in
     actor_obs_kernel<<<grid_for(N, 8, 8), 256, 0, as_stream(stream)>>>(amp_buf, N, K, A, base_width, last_actions, act, command, cmd,
                                                                        n_hist, hist_include_actions, hist_include_command, hist_buf,
                                                                        just_reset, actor_obs, actor_stride);
+    AMP_CUDA_TRY(cudaGetLastError());
+    return AMP_OK;
+}
+
+int amp_task_reward(const float *scales, const uint8_t *reset_terminated, const float *actions, int32_t act, const float *joint_pos,
+                    const float *soft_limits, const float *joint_acc, const float *joint_vel, int32_t D, const float *body_lin_vel_w,
+                    const float *body_quat_w, int32_t Bsim, int32_t ref_body, const float *command, int64_t N, float *total,
+                    float *terms, float *track_err, void *stream) {
+    AMP_REQUIRE(scales && N >= 0 && act >= 0 && D >= 0, "amp_task_reward: bad arguments");
+    if (N == 0) return AMP_OK;
+    AMP_REQUIRE(reset_terminated && total && (act == 0 || actions) && (D == 0 || (joint_pos && soft_limits && joint_acc && joint_vel)),
+                "amp_task_reward: NULL buffer");
+    RewardScales sc{};
+    sc.termination = scales[0];
+    sc.action_l2 = scales[1];
+    sc.joint_pos_limits = scales[2];
+    sc.joint_acc_l2 = scales[3];
+    sc.joint_vel_l2 = scales[4];
+    sc.track_vel = scales[5];
+    if (sc.track_vel > 0.0f) {
+        AMP_REQUIRE(body_lin_vel_w && body_quat_w && command && Bsim >= 1 && ref_body >= 0 && ref_body < Bsim,
+                    "amp_task_reward: velocity tracking needs body_lin_vel_w, body_quat_w, command and a valid reference body");
+        AMP_REQUIRE(aligned16(body_quat_w), "amp_task_reward: body_quat_w must be 16-byte aligned");
+        const double w = (double)scales[5], sigma_sq = 0.25, floor_v = 4.0;  // the scripted reference evaluates these in double
+        sc.exp_at_floor = (float)(w * std::exp(-floor_v));
+        sc.linear_slope = (float)(w / sigma_sq * std::exp(-floor_v));
+    }
+    AMP_REQUIRE(D == 0 || (reinterpret_cast<uintptr_t>(soft_limits) & 7u) == 0, "amp_task_reward: soft_limits must be 8-byte aligned");
+    task_reward_kernel<<<grid_for(N, 8, 8), 256, 0, as_stream(stream)>>>(sc, reset_terminated, actions, act, joint_pos, soft_limits,
+                                                                         joint_acc, joint_vel, D, body_lin_vel_w, body_quat_w, Bsim,
+                                                                         ref_body, command, N, total, terms, track_err);
     AMP_CUDA_TRY(cudaGetLastError());
     return AMP_OK;
 }

@@ -160,6 +160,17 @@ AMP_API int amp_actor_obs_step(const float *amp_buf, int64_t N, int32_t K, int32
                                int32_t num_actor_observations, int32_t hist_include_actions, int32_t hist_include_command,
                                float *hist_buf, uint8_t *just_reset, float *actor_obs, int64_t actor_stride, void *stream);
 
+/* Task reward of G1AmpEnv._get_rewards (g1_amp_env.py:246-288) with compute_rewards (:564-606) and
+ * exp_reward_with_floor (:500-532, sigma 0.5, floor 4.0) -- SURVEY.md section 8f item 1.
+ *   scales host [6]: rew_termination, rew_action_l2, rew_joint_pos_limits, rew_joint_acc_l2, rew_joint_vel_l2, rew_track_vel
+ *   reset_terminated (N) bytes; actions (N,act); joint_pos / joint_acc / joint_vel (N,D); soft_limits (N,D,2);
+ *   body_lin_vel_w (N,Bsim,3), body_quat_w (N,Bsim,4), command (N,2): only read when rew_track_vel > 0.
+ *   total (N); terms (N,6) or NULL (the six terms in the order of `scales`); track_err (N) or NULL. */
+AMP_API int amp_task_reward(const float *scales, const uint8_t *reset_terminated, const float *actions, int32_t act,
+                            const float *joint_pos, const float *soft_limits, const float *joint_acc, const float *joint_vel,
+                            int32_t D, const float *body_lin_vel_w, const float *body_quat_w, int32_t Bsim, int32_t ref_body,
+                            const float *command, int64_t N, float *total, float *terms, float *track_err, void *stream);
+
 /* ---- discriminator style reward (skrl AMP._update; cfg agents/skrl_g1_dance_amp_cfg.yaml:31-39, 80, 94-95) ------ */
 /* Network Linear(in,h1)-ReLU-Linear(h1,h2)-ReLU-Linear(h2,1) on RunningStandardScaler-normalised input.
  * h1, h2 must be multiples of 128 (reference: 1024, 512); in_features any value >= 1 (padded to 64 internally). */

@@ -38,5 +38,8 @@ from .env_oracle import (  # noqa: F401
     reset_fill,
     actor_observations,
     reset_root_and_dof_state,
+    quat_rotate_inverse,
+    exp_reward_with_floor,
+    task_rewards,
 )
 from .disc_oracle import OracleDiscriminator, running_standard_scaler_eval, style_reward_from_logits  # noqa: F401

@@ -8,6 +8,7 @@ Follows ``/root/reference/g1_amp_env.py`` (the 28-DoF humanoid env ``humanoid_am
 * history shift + slot-0 write ........... ``:187-193``
 * reset-time history fill ................ ``:414-419``
 * actor observation + its history ........ ``:195-242`` (the first "next" row)
+* task reward ............................ ``:246-288, 500-532, 564-606`` (same row)
 
 ``quat_apply`` is upstream ``isaaclab.utils.math.quat_apply`` (Isaac Lab 2.2.0, not vendored; call sites
 ``g1_amp_env.py:16, 495-496``): restated from its published form, PARITY UNPINNED for that function alone.
@@ -153,3 +154,55 @@ def reset_root_and_dof_state(loader, times, motion_ids, default_root_state, env_
     root_state[:, 7:10] = body_lv[:, torso_index]
     root_state[:, 10:13] = body_av[:, torso_index]
     return root_state, dof_p[:, motion_dof_indexes], dof_v[:, motion_dof_indexes]
+
+
+def quat_rotate_inverse(q: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+    """Upstream ``isaaclab.utils.math.quat_rotate_inverse`` (Isaac Lab 2.2.0, not vendored; call site ``g1_amp_env.py:253``),
+    restated from its published form -- PARITY UNPINNED: ``v*(2w^2-1) - 2w (xyz x v) + 2 xyz (xyz . v)``."""
+    q_w = q[..., 0]
+    q_vec = q[..., 1:]
+    a = v * (2.0 * q_w**2 - 1.0).unsqueeze(-1)
+    b = torch.cross(q_vec, v, dim=-1) * q_w.unsqueeze(-1) * 2.0
+    c = q_vec * torch.bmm(q_vec.view(q.shape[0], 1, 3), v.view(q.shape[0], 3, 1)).squeeze(-1) * 2.0
+    return a - b + c
+
+
+def exp_reward_with_floor(error: torch.Tensor, weight: float, sigma: float, floor: float = 3.0) -> torch.Tensor:
+    """Reference ``g1_amp_env.py:500-532``: exponential reward that continues linearly (C1) beyond ``floor * sigma^2``.
+    The threshold constants are Python floats (double) in the scripted reference and enter the tensor ops as scalars."""
+    import math
+
+    sigma_sq = sigma * sigma
+    threshold = floor * sigma_sq
+    exp_val_at_threshold = weight * math.exp(-floor)
+    linear_slope = weight / sigma_sq * math.exp(-floor)
+    linear_reward = exp_val_at_threshold - linear_slope * (error - threshold)
+    exp_reward = weight * torch.exp(-error / sigma_sq)
+    return torch.where(error > threshold, linear_reward, exp_reward)
+
+
+def task_rewards(scales, reset_terminated, actions, joint_pos, soft_joint_pos_limits, joint_acc, joint_vel, root_lin_vel_w=None,
+                 root_quat_w=None, command=None):
+    """Reference ``_get_rewards`` (``g1_amp_env.py:246-288``) + ``compute_rewards`` (``:564-606``).
+
+    ``scales`` = dict(rew_termination, rew_action_l2, rew_joint_pos_limits, rew_joint_acc_l2, rew_joint_vel_l2, rew_track_vel).
+    Returns ``(total, terms)`` with ``terms`` an ``(N, 6)`` tensor in that order plus the tracking error ``(N,)``.
+    """
+    n = actions.shape[0]
+    if scales["rew_track_vel"] > 0.0:
+        speed = quat_rotate_inverse(root_quat_w, root_lin_vel_w)[:, :2]
+        track_err = torch.norm(speed - command, dim=-1)
+        rew_track = exp_reward_with_floor(torch.square(track_err), scales["rew_track_vel"], 0.5, floor=4.0)
+    else:
+        track_err = torch.zeros(n)
+        rew_track = torch.zeros(n, dtype=torch.float)
+    r_term = scales["rew_termination"] * reset_terminated.float()
+    r_act = scales["rew_action_l2"] * torch.sum(torch.square(actions), dim=1)
+    out_of_limits = -(joint_pos - soft_joint_pos_limits[:, :, 0]).clip(max=0.0)
+    out_of_limits += (joint_pos - soft_joint_pos_limits[:, :, 1]).clip(min=0.0)
+    r_lim = scales["rew_joint_pos_limits"] * torch.sum(out_of_limits, dim=1)
+    r_acc = scales["rew_joint_acc_l2"] * torch.sum(torch.square(joint_acc), dim=1)
+    r_vel = scales["rew_joint_vel_l2"] * torch.sum(torch.square(joint_vel), dim=1)
+    basic = r_term + r_act + r_lim + r_acc + r_vel
+    total = basic + rew_track
+    return total, torch.stack([r_term, r_act, r_lim, r_acc, r_vel, rew_track], dim=1), track_err

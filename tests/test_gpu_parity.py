@@ -322,6 +322,43 @@ def test_actor_observation_history_vs_oracle(loaders, amp, n_actor, track, inc_a
             assert not env._just_reset_mask.any() and not ref_mask.any()
 
 
+@pytest.mark.parametrize("track", [0.0, 1.0])
+def test_task_reward_vs_oracle(loaders, amp, track):
+    """``_get_rewards`` (g1_amp_env.py:246-288) with compute_rewards / exp_reward_with_floor."""
+    from oracle import env_oracle
+    from humanoid_amp_b200.synthetic import synthetic_sim_state
+
+    loader = loaders("G1_dance")
+    N = 777
+    scales = dict(rew_termination=-1.0, rew_action_l2=-0.1, rew_joint_pos_limits=-10.0, rew_joint_acc_l2=-1.0e-06,
+                  rew_joint_vel_l2=-0.001, rew_track_vel=track)  # the _CUSTOM cfg values (g1_amp_env_cfg.py:86-91)
+    cfg = amp.AmpEnvCfg(motion_file="<preloaded>", num_envs=N, num_amp_observations=2, robot=amp.G1, **scales)
+    env = amp.AmpEnvPath(cfg, "cuda:0", motion_loader=loader)
+    g = torch.Generator().manual_seed(11)
+    jp, jv, bp, bq, bl, ba = synthetic_sim_state(N, amp.G1, "cpu", seed=77)
+    actions = torch.randn(N, 29, generator=g)
+    acc = torch.randn(N, 29, generator=g) * 50
+    lo = torch.rand(N, 29, generator=g) * -2.0
+    limits = torch.stack([lo, lo + torch.rand(N, 29, generator=g) * 3.0], dim=-1)  # some joints outside their soft limits
+    terminated = torch.rand(N, generator=g) < 0.2
+    command = torch.rand(N, 2, generator=g) * 2 - 1
+    bl = bl * 0.5
+    bl[::5] *= 4  # a share of envs beyond the exp/linear threshold of the tracking reward
+    env.command_target_speed.copy_(command)
+    want_total, want_terms, want_err = env_oracle.task_rewards(scales, terminated, actions, jp, limits, acc, jv,
+                                                               bl[:, env.ref_body_index], bq[:, env.ref_body_index], command)  # fmt: skip
+    total, terms, err = env.get_rewards(terminated.cuda(), actions.cuda(), jp.cuda(), limits.cuda(), acc.cuda(), jv.cuda(),
+                                        bl.cuda(), bq.cuda(), return_terms=True)  # fmt: skip
+    # per-joint sums are accumulated in a different (fixed shuffle-tree) order than torch.sum: 29 fp32 addends
+    close(terms, want_terms, rtol=2e-5, atol=1e-6)
+    close(total, want_total, rtol=2e-5, atol=2e-6)
+    if track > 0:
+        close(err, want_err, rtol=1e-5, atol=1e-6)
+        assert (want_err**2 > 1.0).any() and (want_err**2 < 1.0).any()  # both branches of exp_reward_with_floor exercised
+    only_total = env.get_rewards(terminated.cuda(), actions.cuda(), jp.cuda(), limits.cuda(), acc.cuda(), jv.cuda(), bl.cuda(), bq.cuda())
+    assert torch.equal(only_total, total)
+
+
 def test_reset_strategy_random_state_vs_oracle(loaders, amp):
     """SURVEY 8f item 3 (reset-state write, g1_amp_env.py:371-419): same host RNG stream, same root / dof state, and the
     reset envs' AMP history rows."""
