@@ -126,3 +126,52 @@ def test_weight_refresh_changes_result():
     ora.weights = W
     want = ora.style_reward(x.cpu())
     assert (after.cpu() - want).abs().max() <= 2e-2 * max(1.0, float(ora.logits(x.cpu()).abs().max()))
+
+
+def test_cuda_graph_capture_of_a_whole_step(tmp_path):
+    """A step (fused collect -> env-step history -> multi-chunk style reward, which forks onto the handle's side stream)
+    captured once with ``capture_step`` and replayed gives the same bits as eager launches, also after the inputs change."""
+    import humanoid_amp_b200 as amp
+    from humanoid_amp_b200.synthetic import skrl_style_discriminator_params, synthetic_sim_state, write_synthetic_clip
+
+    path = write_synthetic_clip(str(tmp_path / "walk.npz"), "G1_walk", seed=3)
+    n, K = 4096, 2
+    env = amp.AmpEnvPath(amp.AmpEnvCfg(motion_file=path, num_envs=n, num_amp_observations=K, robot=amp.G1), "cuda:0")
+    width = K * 83
+    W, b = skrl_style_discriminator_params(width, seed=1, logit_gain=3.0)
+    import os
+
+    os.environ["AMP_B200_DISC_TILES_PER_CTA"] = "1"  # force several chunks (148 x 128 rows each) at a small batch
+    try:
+        disc = amp.AmpDiscriminator(width, device="cuda:0", max_rows=16 * n)
+    finally:
+        del os.environ["AMP_B200_DISC_TILES_PER_CTA"]
+    assert disc.chunk_rows < 16 * n
+    disc.load(W, b, torch.zeros(width, dtype=torch.float64), torch.ones(width, dtype=torch.float64))
+    g = torch.Generator(device="cuda").manual_seed(5)
+    ids, times = env._motion_loader.sample_times_device(n, generator=g)
+    state = [t.clone() for t in synthetic_sim_state(n, amp.G1, "cuda:0", seed=9)]
+    obs = torch.empty((n, width), device="cuda")
+    rollout = torch.randn(16 * n, width, device="cuda")
+    reward = torch.empty(16 * n, device="cuda")
+
+    def step():
+        env.collect_reference_motions(n, times, ids, out=obs)
+        env.update_amp_observations(*state)
+        disc.style_reward(rollout, out=reward)
+
+    graph = amp.capture_step(step, "cuda:0")
+    for trial in range(2):
+        if trial:  # new inputs in the same buffers
+            times.mul_(0.5)
+            rollout.normal_()
+            state[0].add_(0.25)
+        env.amp_observation_buffer.zero_()
+        step()
+        want = (obs.clone(), env.amp_observation_buffer.clone(), reward.clone())
+        env.amp_observation_buffer.zero_()
+        obs.zero_()
+        reward.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(obs, want[0]) and torch.equal(env.amp_observation_buffer, want[1]) and torch.equal(reward, want[2])
