@@ -93,6 +93,29 @@ def main():
         row("obs_step_kernel", ms, n * per_env, note=f"G1 N={n} K={K} ({per_env} B/env)")
         del env, state
 
+    # ---- actor observation + task reward ------------------------------------------------------------------
+    for n, n_actor in ((65_536, 2), (1_000_000, 1)):
+        ld = loaders["G1_dance"]
+        cfg = amp.AmpEnvCfg(motion_file="", num_envs=n, num_amp_observations=2, robot=amp.G1, num_actor_observations=n_actor, rew_track_vel=1.0,
+                            rew_termination=-1.0, rew_action_l2=-0.1, rew_joint_pos_limits=-10.0, rew_joint_acc_l2=-1e-6, rew_joint_vel_l2=-1e-3)
+        env = amp.AmpEnvPath(cfg, DEV, motion_loader=ld)
+        state = synthetic_sim_state(n, amp.G1, DEV, seed=6)
+        out = torch.empty((n, cfg.observation_space), device=DEV)
+        env.update_amp_observations(*state)
+        lib_call = lambda: env.get_observations(*state, out=out)  # noqa: E731
+        ms_both = timed(lib_call)
+        ms_amp = timed(lambda: env.update_amp_observations(*state))
+        P, cur = cfg.hist_frame_size, 71 + 29 + 2
+        nbytes = n * ((cur + max(n_actor - 2, 0) * P) * 4 + ((n_actor - 1) * P + cfg.observation_space) * 4)
+        row("actor_obs_kernel", max(ms_both - ms_amp, 1e-4), nbytes, note=f"G1 N={n} n_actor={n_actor} (get_observations minus the AMP-history launch)")
+        g = torch.Generator(device="cuda").manual_seed(1)
+        acts, acc = torch.randn(n, 29, device=DEV, generator=g), torch.randn(n, 29, device=DEV, generator=g)
+        lim = torch.randn(n, 29, 2, device=DEV, generator=g)
+        term = torch.zeros(n, dtype=torch.bool, device=DEV)
+        ms = timed(lambda: env.get_rewards(term, acts, state[0], lim, acc, state[1], state[4], state[3]))
+        row("task_reward_kernel", ms, n * ((29 * 6 + 9) * 4 + 1 + 4), note=f"G1 N={n}, velocity tracking on")
+        del env, state, out
+
     # ---- compute_obs free function ---------------------------------------------------------------------------------------
     n = 2_000_000
     g = torch.Generator(device="cuda").manual_seed(0)
