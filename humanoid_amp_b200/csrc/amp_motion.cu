@@ -17,6 +17,7 @@
 // Compile with -fmad=false (see amp_math.cuh).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -419,22 +420,36 @@ collect_reference_kernel(LibView v, const double *__restrict__ cur_times, const 
         // ---- phase 2: stream the rows out ----------------------------------------------------------------------
         // Lane l reads table[off + l + 32 s] unconditionally (the allocation is padded so the last row may be
         // over-read) and only the store of the last slot is predicated.
+        // Consecutive history frames of a sample are one frame period apart, so frame k+1 normally interpolates rows
+        // (i0-1, i0) where frame k used (i0, i0+1): the lower row of the previous frame is kept in registers and becomes
+        // the upper row (11 row reads instead of 20 per sample at K = 10).  The test is warp-uniform (the offsets come
+        // from the broadcast FrameMeta read) and only skips loads -- the values are the same either way.
+        float lo[NSLOT], hi[NSLOT];
+        int prev_off0 = -1, prev_off1 = -1;
 #pragma unroll 2
         for (int f = 0; f < nf; ++f) {
             const float *mf = reinterpret_cast<const float *>(&meta[f]);
             const int4 head = *reinterpret_cast<const int4 *>(mf);  // off0, off1, b, omb in one broadcast read
             const float b = __int_as_float(head.z), omb = __int_as_float(head.w);
-            const float *p0 = tab + head.x + lane, *p1 = tab + head.y + lane;
             float *o = out + *reinterpret_cast<const int64_t *>(mf + 14) + lane;
-            float a0[NSLOT], a1[NSLOT];
+            if (head.y == prev_off0) {
 #pragma unroll
-            for (int s = 0; s < NSLOT; ++s) {
-                a0[s] = table_ld<SMEM_TABLE>(p0 + 32 * s);
-                a1[s] = table_ld<SMEM_TABLE>(p1 + 32 * s);
+                for (int s = 0; s < NSLOT; ++s) hi[s] = lo[s];
+            } else if (head.y != prev_off1) {
+                const float *p1 = tab + head.y + lane;
+#pragma unroll
+                for (int s = 0; s < NSLOT; ++s) hi[s] = table_ld<SMEM_TABLE>(p1 + 32 * s);
             }
+            if (head.x != prev_off0) {
+                const float *p0 = tab + head.x + lane;
+#pragma unroll
+                for (int s = 0; s < NSLOT; ++s) lo[s] = table_ld<SMEM_TABLE>(p0 + 32 * s);
+            }
+            prev_off0 = head.x;
+            prev_off1 = head.y;
 #pragma unroll
             for (int s = 0; s < NSLOT; ++s) {
-                float val = lerp_w(omb, b, a0[s], a1[s]);
+                float val = lerp_w(omb, b, lo[s], hi[s]);
                 if (special[s]) {  // warp-uniform branch
                     const float w = mf[fix_idx[s]];
                     const float d = __fsub_rn(val, w);
@@ -978,7 +993,13 @@ int amp_collect_reference(amp_lib_t *lib, const double *cur_times, const int64_t
     const size_t per_warp = (size_t)tile_cap * sizeof(FrameMeta);
     int smem_warps = table_bytes + 8 * per_warp <= (size_t)kMaxSmemOptin ? (int)std::min<size_t>(32, (kMaxSmemOptin - table_bytes) / per_warp) : 0;
     const int64_t full_tiles = (n + max_tile - 1) / max_tile;
-    const bool use_smem = smem_warps >= 8 && full_tiles >= (int64_t)2 * sms * smem_warps;
+    static const int force_variant = [] {  // developer knob: AMP_B200_COLLECT_TABLE=global|smem overrides the heuristic
+        const char *e = getenv("AMP_B200_COLLECT_TABLE");
+        return !e ? 0 : (e[0] == 'g' ? 1 : (e[0] == 's' ? 2 : 0));
+    }();
+    bool use_smem = smem_warps >= 8 && full_tiles >= (int64_t)2 * sms * smem_warps;
+    if (force_variant == 1) use_smem = false;
+    if (force_variant == 2 && smem_warps >= 1) use_smem = true;
 
     int tile_samples, grid, threads;
     int64_t tiles;
