@@ -249,22 +249,26 @@ __host__ __device__ constexpr int fused_smem_bytes(bool pair) {
            1024 /*partial dots*/ + 1024 /*alignment slack*/;
 }
 
-// Schedule shared by producer, issuer and epilogue warps.  Accumulator tiles are numbered in issue order and ping-pong
-// between the two 256-column TMEM regions (tile q -> region q & 1), whatever layer they belong to:
-//     prologue      G1(t0): N1 tiles 0..3
-//     iteration i   G1(t[i+1]): N1 tiles 0..3,   then   G2(t[i]): N2 tile 0 (16 units), N2 tile 1 (16 units)
-// so the drain of an accumulator always overlaps the MMAs of the NEXT tile, and the two long layer-2 tiles (8192 cycles
-// each) cover the drains that matter most.  (The first version interleaved one G1 tile with eight G2 units and kept D1 / D2
-// in fixed regions: every accumulator hand-off then sat on the issuer's critical path -- ~30 % of its time went to waiting
-// for drains, more with a CTA pair where a hand-off crosses the cluster twice.)
+// Schedule shared by producer, issuer and epilogue warps.  Every accumulator tile is told which of the two 256-column
+// TMEM regions it uses; issuer and epilogue keep one use counter per region (mbarrier parity = counter & 1).
+//     prologue      G1(t0): N1 tiles 0..3, alternating regions
+//     iteration i   G1(t[i+1]) tile 0 -> region 0,  8 units of G2(t[i]) -> region 1,  G1 tile 1,  8 units, ...
+// i.e. the short layer-1 tiles (12 MMAs = 1.5 k cycles each, ~2 k cycles to drain) are spread between the halves of the two
+// long layer-2 tiles (64 MMAs = 8.2 k cycles each): a layer-1 drain has 4 k cycles of layer-2 MMAs to hide under, a
+// layer-2 drain has the next layer-1 tile, and h1(t[i]) is complete 5.6 k cycles before its first layer-2 unit needs it.
+// (Back-to-back layer-1 tiles -- the previous schedule -- left the issuer waiting ~20 % of its time for drains, in-kernel
+// counters of the AMP_DISC_PROFILE build; so did the very first version whose 4-warp drains took longer than 8 units.)
 template <class G1, class G2>
 __device__ __forceinline__ void walk_schedule(int T, int n1_tiles, int units, G1 &&g1, G2 &&g2) {
     if (T <= 0) return;
-    for (int nt = 0; nt < n1_tiles; ++nt) g1(0, nt);
+    for (int nt = 0; nt < n1_tiles; ++nt) g1(0, nt, nt & 1);
+    const int seg = (units + n1_tiles - 1) / n1_tiles;
     for (int i = 0; i < T; ++i) {
-        if (i + 1 < T)
-            for (int nt = 0; nt < n1_tiles; ++nt) g1(i + 1, nt);
-        for (int u = 0; u < units; ++u) g2(i, u);
+        int u = 0;
+        for (int nt = 0; nt < n1_tiles; ++nt) {
+            if (i + 1 < T) g1(i + 1, nt, 0);
+            for (const int e = min(units, u + seg); u < e; ++u) g2(i, u, 1);
+        }
     }
 }
 
@@ -278,6 +282,7 @@ struct FusedParams {
     float *reward;  // [M]
     float *logits;  // [M] or NULL
     long long *prof;  // AMP_DISC_PROFILE builds only: per-CTA cycle counters of the producer / issuer waits, else NULL
+    int prof_mode;    // AMP_DISC_PROFILE builds only: bit 0 = skip the h1 staging + TMA store (timing experiment, wrong results)
 };
 
 #ifdef AMP_DISC_PROFILE
@@ -394,13 +399,13 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             };
             walk_schedule(
                 T, p.n1_tiles, units,
-                [&](int ti, int nt) {
+                [&](int ti, int nt, int) {
                     const int m = tile_of(ti);
                     // x_hat is read by the four N1 tiles of this row tile and never again: stream it on the last pass
                     for (int kb = 0; kb < p.kb1; ++kb)
                         load_pair(&tmap_x, kb * BK, m * BM, nt == p.n1_tiles - 1 ? stream : keep, &tmap_w1, kb * BK, nt * BN);
                 },
-                [&](int ti, int u) {
+                [&](int ti, int u, int) {
                     const int n2 = u / kb2, kb = u - n2 * kb2;
                     if (u == 0) {  // h1 of this row tile has been written (all four E1 warps' TMA stores completed)
                         AMP_PROF_T0;
@@ -426,6 +431,8 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             [[maybe_unused]] long long w_full = 0, w_d1 = 0, w_d2 = 0;
 #ifdef AMP_DISC_PROFILE
             const long long t_begin = clock64();
+            unsigned long long ns_begin;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_begin));
 #endif
             auto commit = [&](uint32_t bar) {
                 if constexpr (PAIR) umma_commit_pair(bar, (uint16_t)0x3); else umma_commit(bar);
@@ -447,28 +454,28 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                 commit(empty_bar + 8 * stage);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             };
-            uint32_t q = 0;  // accumulator tiles issued so far: tile q uses region q & 1, its (q >> 1)-th use
-            auto acquire_acc = [&](long long &w) {
+            uint32_t uses = 0;  // bit r = parity of the number of accumulator tiles issued so far into TMEM region r
+            auto acquire_acc = [&](int r, long long &w) {
                 AMP_PROF_T0;
-                mbar_wait(acc_empty + 8 * (q & 1), ((q >> 1) & 1) ^ 1);  // the epilogue (of both CTAs) has drained it
+                mbar_wait(acc_empty + 8 * r, ((uses >> r) & 1) ^ 1);  // the epilogue (of both CTAs) has drained its last tile
                 AMP_PROF_ADD(w);
                 tcgen05_fence_after();
             };
             walk_schedule(
                 T, p.n1_tiles, units,
-                [&](int, int) {
-                    acquire_acc(w_d1);
-                    for (int kb = 0; kb < p.kb1; ++kb) mma_block(tmem_base + (q & 1) * ACC_COLS, kb == 0);
-                    commit(acc_full + 8 * (q & 1));
-                    ++q;
+                [&](int, int, int r) {
+                    acquire_acc(r, w_d1);
+                    for (int kb = 0; kb < p.kb1; ++kb) mma_block(tmem_base + r * ACC_COLS, kb == 0);
+                    commit(acc_full + 8 * r);
+                    uses ^= 1u << r;
                 },
-                [&](int, int u) {
+                [&](int, int u, int r) {
                     const int kb = u % kb2;
-                    if (kb == 0) acquire_acc(w_d2);
-                    mma_block(tmem_base + (q & 1) * ACC_COLS, kb == 0);
+                    if (kb == 0) acquire_acc(r, w_d2);
+                    mma_block(tmem_base + r * ACC_COLS, kb == 0);
                     if (kb == kb2 - 1) {
-                        commit(acc_full + 8 * (q & 1));
-                        ++q;
+                        commit(acc_full + 8 * r);
+                        uses ^= 1u << r;
                     }
                 });
 #ifdef AMP_DISC_PROFILE
@@ -477,6 +484,9 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                 p.prof[blockIdx.x * 8 + 1] = w_full;
                 p.prof[blockIdx.x * 8 + 2] = w_d1;
                 p.prof[blockIdx.x * 8 + 3] = w_d2;
+                unsigned long long ns_end;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_end));
+                p.prof[blockIdx.x * 8 + 6] = (long long)(ns_end - ns_begin);
             }
 #endif
         }
@@ -495,16 +505,24 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
         const uint32_t col_base = (uint32_t)(colhalf * (BN / 2));
         float *part = reinterpret_cast<float *>(smem_raw + (part_smem - smem_u32(smem_raw)));  // [2][4][32] partial dots
-        uint32_t q = 0, store_it = 0;  // q: accumulator tiles drained so far (same numbering as the issuer)
+        uint32_t uses = 0, store_it = 0;  // uses bit r: parity of the tiles drained so far from region r (as the issuer counts)
         const uint64_t h1_keep = l2_policy_evict_last();
         float dot[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        [[maybe_unused]] long long e_wait1 = 0, e_drain1 = 0, e_post1 = 0, e_wait2 = 0, e_drain2 = 0, e_post2 = 0, e_slab = 0;
         walk_schedule(
             T, p.n1_tiles, units,
-            [&](int ti, int nt) {
-                // ---- D1 (ti, nt): this warp's 128 columns = two 64-column slabs ----
+            [&](int ti, int nt, int r) {
+                // ---- D1 (ti, nt): this warp's 128 columns = four 32-column slabs ----
                 const int row0 = slot_row0 + (ti & 1) * BM + quarter * 32;
-                const uint32_t acc = tmem_base + lane_base + (q & 1) * ACC_COLS + col_base;
-                mbar_wait(acc_full + 8 * (q & 1), (q >> 1) & 1);
+                const uint32_t acc = tmem_base + lane_base + r * ACC_COLS + col_base;
+#ifdef AMP_DISC_PROFILE
+                const long long e_t0 = clock64();
+                long long e_t2 = 0;
+#endif
+                mbar_wait(acc_full + 8 * r, (uses >> r) & 1);
+#ifdef AMP_DISC_PROFILE
+                const long long e_t1 = clock64();
+#endif
                 tcgen05_fence_after();
                 uint32_t v[2][32];
                 tmem_ld_32x32(acc, v[0]);
@@ -513,20 +531,38 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                     const int col = nt * BN + (int)col_base + h * 32;  // h1 column of this step
                     const float4 *bias4 = reinterpret_cast<const float4 *>(p.b1 + col);
                     float4 bb[8];
+#ifdef AMP_DISC_PROFILE
+                    if (p.prof_mode & 2) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) bb[j] = __ldg(bias4 + j);
+                        for (int j = 0; j < 8; ++j) bb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    } else
+#endif
+                    {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) bb[j] = __ldg(bias4 + j);
+                    }
                     const uint32_t slab = staging + (uint32_t)((ew * 2 + (store_it & 1)) * STORE_SLAB_BYTES);
-                    if (lane == 0) bulk_wait_read<1>();  // the store that last read this slab has drained it
-                    __syncwarp();
+                    {
+                        AMP_PROF_T0;
+                        if (lane == 0) bulk_wait_read<1>();  // the store that last read this slab has drained it
+                        __syncwarp();
+                        AMP_PROF_ADD(e_slab);
+                    }
                     tmem_ld_wait();  // v[h & 1] has landed
                     if (h + 1 < 4) {
                         tmem_ld_32x32(acc + (uint32_t)((h + 1) * 32), v[(h + 1) & 1]);
                     } else {  // last TMEM read of this accumulator by this warp: release the region to the issuer now
                         tcgen05_fence_before();
                         __syncwarp();
-                        if (lane == 0) arrive_drained(acc_empty_at_leader + 8 * (q & 1));
+                        if (lane == 0) arrive_drained(acc_empty_at_leader + 8 * r);
+#ifdef AMP_DISC_PROFILE
+                        e_t2 = clock64();
+#endif
                     }
                     const uint32_t(&cur)[32] = v[h & 1];
+#ifdef AMP_DISC_PROFILE
+                    if (p.prof_mode & 1) { ++store_it; continue; }
+#endif
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {  // 16-byte chunk j of this thread's 64-byte slab row
                         const float4 b0 = bb[2 * j], b1v = bb[2 * j + 1];
@@ -552,18 +588,30 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                     }
                     ++store_it;
                 }
-                ++q;
+#ifdef AMP_DISC_PROFILE
+                e_wait1 += e_t1 - e_t0;
+                e_drain1 += e_t2 - e_t1;
+                e_post1 += clock64() - e_t2;
+#endif
+                uses ^= 1u << r;
                 if (nt == p.n1_tiles - 1 && lane == 0) {  // this warp's part of h1(ti) is complete in the workspace
                     bulk_wait_all();
                     mbar_arrive(h1_ready + 8 * (ti & 1));
                 }
             },
-            [&](int ti, int u) {
+            [&](int ti, int u, int r) {
                 const int n2 = u / kb2;
                 if (u - n2 * kb2 != kb2 - 1) return;  // D2 (ti, n2) is complete after the last K block of the N tile
                 // ---- D2 (ti, n2): this warp's 128 columns ----
-                const uint32_t acc = tmem_base + lane_base + (q & 1) * ACC_COLS + col_base;
-                mbar_wait(acc_full + 8 * (q & 1), (q >> 1) & 1);
+                const uint32_t acc = tmem_base + lane_base + r * ACC_COLS + col_base;
+#ifdef AMP_DISC_PROFILE
+                const long long e_t0 = clock64();
+                long long e_t2 = 0;
+#endif
+                mbar_wait(acc_full + 8 * r, (uses >> r) & 1);
+#ifdef AMP_DISC_PROFILE
+                const long long e_t1 = clock64();
+#endif
                 tcgen05_fence_after();
                 uint32_t v[2][32];
                 tmem_ld_32x32(acc, v[0]);
@@ -573,10 +621,18 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                     const float4 *bias4 = reinterpret_cast<const float4 *>(p.b2 + col0);
                     const float4 *w4 = reinterpret_cast<const float4 *>(p.w3 + col0);
                     float4 bb[8], ww[8];
+#ifdef AMP_DISC_PROFILE
+                    if (p.prof_mode & 2) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        bb[j] = __ldg(bias4 + j);
-                        ww[j] = __ldg(w4 + j);
+                        for (int j = 0; j < 8; ++j) bb[j] = ww[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    } else
+#endif
+                    {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            bb[j] = __ldg(bias4 + j);
+                            ww[j] = __ldg(w4 + j);
+                        }
                     }
                     tmem_ld_wait();  // v[chunk & 1] has landed
                     if (chunk + 1 < 4) {
@@ -584,7 +640,10 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                     } else {  // last TMEM read: hand the region back before finishing the arithmetic
                         tcgen05_fence_before();
                         __syncwarp();
-                        if (lane == 0) arrive_drained(acc_empty_at_leader + 8 * (q & 1));
+                        if (lane == 0) arrive_drained(acc_empty_at_leader + 8 * r);
+#ifdef AMP_DISC_PROFILE
+                        e_t2 = clock64();
+#endif
                     }
                     const uint32_t(&cur)[32] = v[chunk & 1];
 #pragma unroll
@@ -595,7 +654,12 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                         dot[3] = fmaf(fmaxf(__uint_as_float(cur[4 * j + 3]) + bb[j].w, 0.0f), ww[j].w, dot[3]);
                     }
                 }
-                ++q;
+#ifdef AMP_DISC_PROFILE
+                e_wait2 += e_t1 - e_t0;
+                e_drain2 += e_t2 - e_t1;
+                e_post2 += clock64() - e_t2;
+#endif
+                uses ^= 1u << r;
                 if (n2 == p.n2_tiles - 1) {
                     // combine the two column halves of this row: the upper-half warp hands its partial sum over through
                     // shared memory (double-buffered by tile parity), a 64-thread named barrier orders the exchange
@@ -614,6 +678,12 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                     dot[0] = dot[1] = dot[2] = dot[3] = 0.0f;
                 }
             });
+#ifdef AMP_DISC_PROFILE
+        if (p.prof && ew == 0 && lane == 0) {
+            long long *e = p.prof + (size_t)gridDim.x * 8 + blockIdx.x * 8;
+            e[0] = e_wait1; e[1] = e_drain1; e[2] = e_post1; e[3] = e_wait2; e[4] = e_drain2; e[5] = e_post2; e[6] = e_slab;
+        }
+#endif
     }
 
     tcgen05_fence_before();
@@ -863,7 +933,7 @@ int amp_disc_create(int32_t in_features, int32_t h1, int32_t h2, int64_t max_row
             e = cudaFuncSetAttribute(disc_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_smem_bytes(true));
         if (e != cudaSuccess) rc = cuda_fail(e, "cudaFuncSetAttribute(disc_fused_kernel)");
     #ifdef AMP_DISC_PROFILE
-        if (cudaMalloc((void **)&d->prof, (size_t)d->ws_ctas * 8 * sizeof(long long)) != cudaSuccess) d->prof = nullptr;
+        if (cudaMalloc((void **)&d->prof, (size_t)d->ws_ctas * 16 * sizeof(long long)) != cudaSuccess) d->prof = nullptr;
 #endif
         // Measured on the 1 M-row bench (B200, sustained, sw_power_cap active): single-CTA 1.61 ms, CTA pair 1.68 ms.  The pair
         // halves the weight bytes each SM ingests but every accumulator hand-off crosses the cluster twice; it is kept as
@@ -976,6 +1046,9 @@ int amp_disc_style_reward(amp_disc_t *d, const float *x, int64_t x_stride, int64
         fp.reward = reward + r0;
         fp.logits = logits ? logits + r0 : nullptr;
         fp.prof = d->prof;
+#ifdef AMP_DISC_PROFILE
+        if (const char *m = getenv("AMP_DISC_PROF_MODE")) fp.prof_mode = atoi(m);
+#endif
         if (d->use_pair && m_tiles >= 2) {
             // CTA pairs: an even grid of at most ws_ctas CTAs, launched as clusters of 2
             const int pair_blocks = (m_tiles + 1) / 2;
@@ -1003,10 +1076,19 @@ int amp_disc_style_reward(amp_disc_t *d, const float *x, int64_t x_stride, int64
     }
 #ifdef AMP_DISC_PROFILE
     if (d->prof) {  // developer build: dump the wait breakdown of the LAST chunk (synchronises!)
-        static long long host[1024 * 8];
+        static long long host[1024 * 16];
         cudaStreamSynchronize(st);
         const int n = std::min(d->ws_ctas, 1024);
-        cudaMemcpy(host, d->prof, (size_t)n * 8 * sizeof(long long), cudaMemcpyDeviceToHost);
+        cudaMemcpy(host, d->prof, (size_t)n * 16 * sizeof(long long), cudaMemcpyDeviceToHost);
+        {  // epilogue warp 2 of every CTA (for a pair: even CTAs = leaders, odd = peers); assumes the grid used all ws_ctas CTAs
+            double ea[2][8] = {{0}};
+            for (int i = 0; i < n; ++i)
+                for (int k = 0; k < 8; ++k) ea[d->use_pair ? (i & 1) : 0][k] += (double)host[n * 8 + i * 8 + k];
+            const double div = d->use_pair ? n / 2.0 : (double)n;
+            for (int rk = 0; rk < (d->use_pair ? 2 : 1); ++rk)
+                fprintf(stderr, "[amp_disc profile] epilogue rank %d: D1 wait=%.0f drain=%.0f post=%.0f slab_wait=%.0f | D2 wait=%.0f drain=%.0f post=%.0f\n", rk,
+                        ea[rk][0] / div, ea[rk][1] / div, ea[rk][2] / div, ea[rk][6] / div, ea[rk][3] / div, ea[rk][4] / div, ea[rk][5] / div);
+        }
         double acc[8] = {0};
         int cnt = 0;
         for (int i = 0; i < n; ++i) {
@@ -1015,8 +1097,9 @@ int amp_disc_style_reward(amp_disc_t *d, const float *x, int64_t x_stride, int64
             for (int k = 0; k < 8; ++k) acc[k] += (double)host[i * 8 + k];
         }
         if (cnt)
-            fprintf(stderr, "[amp_disc profile] issuer CTAs=%d total=%.0f wait_full=%.0f wait_d1_empty=%.0f wait_d2_empty=%.0f | producer(all) wait_empty=%.0f wait_h1=%.0f (cycles, mean per CTA)\n",
-                    cnt, acc[0] / cnt, acc[1] / cnt, acc[2] / cnt, acc[3] / cnt, acc[4] / n, acc[5] / n);
+            fprintf(stderr, "[amp_disc profile] issuer CTAs=%d total=%.0f wait_full=%.0f wait_d1_empty=%.0f wait_d2_empty=%.0f | producer(all) wait_empty=%.0f wait_h1=%.0f (cycles, mean per CTA) | issuer wall %.1f us => SM clock %.0f MHz\n",
+                    cnt, acc[0] / cnt, acc[1] / cnt, acc[2] / cnt, acc[3] / cnt, acc[4] / n, acc[5] / n, acc[6] / cnt * 1e-3,
+                    acc[0] / acc[6] * 1e3);
     }
 #endif
     return AMP_OK;

@@ -334,6 +334,11 @@ __device__ __forceinline__ float table_ld(const float *p) {
     else return __ldg(p);
 }
 
+#ifdef AMP_COLLECT_PROFILE
+// developer builds only: 0 = normal, 1 = phase 1 only, 2 = phase 2 only (cheap metadata), 3 = phase 1 without the slerp
+__constant__ int c_collect_mode;
+#endif
+
 template <int NSLOT, bool SMEM_TABLE>
 __global__ void __launch_bounds__(SMEM_TABLE ? 1024 : kCollectWarps * 32, SMEM_TABLE ? 1 : 4)
 collect_reference_kernel(LibView v, const double *__restrict__ cur_times, const int64_t *__restrict__ ids, int64_t n,
@@ -388,6 +393,20 @@ collect_reference_kernel(LibView v, const double *__restrict__ cur_times, const 
             const int64_t sample = s0 + si;
             // g1_amp_env.py:454-457  t - dt*k, float64, never clamped (negative -> extrapolation)
             const double t = __dsub_rn(cur_times[sample], __dmul_rn(v.dt, (double)k));
+#ifdef AMP_COLLECT_PROFILE
+            if (c_collect_mode == 2) {
+                FrameMeta m;
+                m.off0 = (int32_t)(((sample * 7 + 1 - k) % (v.num_frames - 1)) * Rs);
+                m.off1 = m.off0 + Rs;
+                m.b = 0.25f; m.omb = 0.75f;
+                for (int i = 0; i < 6; ++i) m.tn[i] = 0.5f;
+                m.root[0] = m.root[1] = m.root[2] = 0.1f;
+                m.zero = 0.0f;
+                m.out = (start_row + sample) * row_stride + (int64_t)k * A;
+                meta[fl] = m;
+                continue;
+            }
+#endif
             const FrameBlend fb = lookup_frame(v, t, ids ? ids[sample] : 0);
             const float b = __double2float_rn(fb.blend), omb = __fsub_rn(1.0f, b);
             FrameMeta m;
@@ -400,6 +419,10 @@ collect_reference_kernel(LibView v, const double *__restrict__ cur_times, const 
                                           table_ld<SMEM_TABLE>(r0 + D2 + 3), table_ld<SMEM_TABLE>(r0 + D2 + 4));
             const float4 q1 = make_float4(table_ld<SMEM_TABLE>(r1 + D2 + 1), table_ld<SMEM_TABLE>(r1 + D2 + 2),
                                           table_ld<SMEM_TABLE>(r1 + D2 + 3), table_ld<SMEM_TABLE>(r1 + D2 + 4));
+#ifdef AMP_COLLECT_PROFILE
+            if (c_collect_mode == 3) tangent_normal(make_float4(q0.x * omb, q1.y * b, q0.z, q1.w), m.tn);
+            else
+#endif
             tangent_normal(slerp(q0, q1, b), m.tn);
             m.root[0] = lerp_w(omb, b, table_ld<SMEM_TABLE>(r0 + D2 + 5), table_ld<SMEM_TABLE>(r1 + D2 + 5));
             m.root[1] = lerp_w(omb, b, table_ld<SMEM_TABLE>(r0 + D2 + 6), table_ld<SMEM_TABLE>(r1 + D2 + 6));
@@ -416,6 +439,13 @@ collect_reference_kernel(LibView v, const double *__restrict__ cur_times, const 
             meta[fl] = m;
         }
         __syncwarp();
+#ifdef AMP_COLLECT_PROFILE
+        if (c_collect_mode == 1 || c_collect_mode == 3) {
+            if (lane < nf) out[meta[lane].out] = meta[lane].tn[0] + meta[lane].root[2];
+            __syncwarp();
+            continue;
+        }
+#endif
 
         // ---- phase 2: stream the rows out ----------------------------------------------------------------------
         // Lane l reads table[off + l + 32 s] unconditionally (the allocation is padded so the last row may be
@@ -1038,6 +1068,13 @@ int amp_collect_reference(amp_lib_t *lib, const double *cur_times, const int64_t
                                                                              tiles);                                    \
         }                                                                                                               \
     } while (0)
+#ifdef AMP_COLLECT_PROFILE
+    {
+        const char *e = getenv("AMP_COLLECT_MODE");
+        const int mode = e ? atoi(e) : 0;
+        AMP_CUDA_TRY(cudaMemcpyToSymbolAsync(c_collect_mode, &mode, sizeof(int), 0, cudaMemcpyHostToDevice, st));
+    }
+#endif
     switch (nslot) {
         case 1: AMP_LAUNCH_COLLECT(1); break;
         case 2: AMP_LAUNCH_COLLECT(2); break;
