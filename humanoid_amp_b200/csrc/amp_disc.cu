@@ -82,6 +82,11 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last() {
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
+__device__ __forceinline__ uint64_t l2_policy_evict_normal() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
@@ -275,6 +280,7 @@ __device__ __forceinline__ void walk_schedule(int T, int n1_tiles, int units, G1
 struct FusedParams {
     int M;          // rows of this launch (x_hat rows)
     int kb1;        // K blocks of layer 1 (Kp / 64)
+    int ksteps1_last;  // 16-wide K steps the LAST layer-1 block really needs: ceil((in_features - 64 (kb1 - 1)) / 16), 1..4
     int n1_tiles;   // h1 / 256
     int n2_tiles;   // h2 / 256
     const float *b1, *b2, *w3, *b3;
@@ -376,7 +382,10 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             int stage = 0;
             uint32_t phase = 0;
             [[maybe_unused]] long long w_empty = 0, w_h1 = 0;
-            const uint64_t keep = l2_policy_evict_last(), stream = l2_policy_evict_first();
+            // weights and h1 slots: evict_last.  x_hat: normal priority while its row tile is being re-read (a 48 KB tile comes
+            // back within a few microseconds), evict_first on its last pass -- marking it evict_last made 192 MB of x_hat
+            // per launch compete with the 77.6 MB of h1 slots for the protected part of L2.
+            const uint64_t keep = l2_policy_evict_last(), stream = l2_policy_evict_first(), normal = l2_policy_evict_normal();
             auto load_pair = [&](const CUtensorMap *ma, int a_col, int a_row, uint64_t a_policy, const CUtensorMap *mb, int b_col,
                                  int b_row) {
                 {
@@ -403,7 +412,7 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                     const int m = tile_of(ti);
                     // x_hat is read by the four N1 tiles of this row tile and never again: stream it on the last pass
                     for (int kb = 0; kb < p.kb1; ++kb)
-                        load_pair(&tmap_x, kb * BK, m * BM, nt == p.n1_tiles - 1 ? stream : keep, &tmap_w1, kb * BK, nt * BN);
+                        load_pair(&tmap_x, kb * BK, m * BM, nt == p.n1_tiles - 1 ? stream : normal, &tmap_w1, kb * BK, nt * BN);
                 },
                 [&](int ti, int u, int) {
                     const int n2 = u / kb2, kb = u - n2 * kb2;
@@ -437,7 +446,9 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             auto commit = [&](uint32_t bar) {
                 if constexpr (PAIR) umma_commit_pair(bar, (uint16_t)0x3); else umma_commit(bar);
             };
-            auto mma_block = [&](uint32_t d_tmem, bool first) {
+            // ksteps < 4 only for the last layer-1 block: x_hat is zero-padded to Kp, so the trailing all-zero K steps add
+            // exact zeros to the accumulator and can be skipped (166 inputs: 11 MMAs per layer-1 tile instead of 12)
+            auto mma_block = [&](uint32_t d_tmem, bool first, int ksteps) {
                 {
                     AMP_PROF_T0;
                     mbar_wait(full_bar + 8 * stage, phase);
@@ -448,6 +459,7 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                 const uint64_t b0 = make_kmajor_sw128_desc(smem_b + stage * B_BYTES);
 #pragma unroll
                 for (int k = 0; k < BK / UMMA_K; ++k) {
+                    if (k >= ksteps) break;
                     if constexpr (PAIR) umma_bf16_pair(d_tmem, a0 + 2 * k, b0 + 2 * k, kInstrDescPair, (uint32_t)(!first || k != 0));
                     else umma_bf16(d_tmem, a0 + 2 * k, b0 + 2 * k, kInstrDesc, (uint32_t)(!first || k != 0));
                 }
@@ -465,14 +477,15 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                 T, p.n1_tiles, units,
                 [&](int, int, int r) {
                     acquire_acc(r, w_d1);
-                    for (int kb = 0; kb < p.kb1; ++kb) mma_block(tmem_base + r * ACC_COLS, kb == 0);
+                    for (int kb = 0; kb < p.kb1; ++kb)
+                        mma_block(tmem_base + r * ACC_COLS, kb == 0, kb == p.kb1 - 1 ? p.ksteps1_last : BK / UMMA_K);
                     commit(acc_full + 8 * r);
                     uses ^= 1u << r;
                 },
                 [&](int, int u, int r) {
                     const int kb = u % kb2;
                     if (kb == 0) acquire_acc(r, w_d2);
-                    mma_block(tmem_base + r * ACC_COLS, kb == 0);
+                    mma_block(tmem_base + r * ACC_COLS, kb == 0, BK / UMMA_K);
                     if (kb == kb2 - 1) {
                         commit(acc_full + 8 * r);
                         uses ^= 1u << r;
@@ -1036,6 +1049,7 @@ int amp_disc_style_reward(amp_disc_t *d, const float *x, int64_t x_stride, int64
         FusedParams fp{};
         fp.M = (int)rows;
         fp.kb1 = d->Kp / BK;
+        fp.ksteps1_last = (d->in_features - BK * (fp.kb1 - 1) + UMMA_K - 1) / UMMA_K;
         fp.n1_tiles = d->h1 / BN;
         fp.n2_tiles = d->h2 / BN;
         fp.b1 = d->b1;
