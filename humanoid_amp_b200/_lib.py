@@ -81,7 +81,12 @@ SIGNATURES = {
     "amp_disc_chunk_rows": (C.c_int64, [_P]),
     "amp_disc_load": (C.c_int, [_P] * 9 + [_P]),
     "amp_disc_style_reward": (C.c_int, [_P, _P, _I64, _I64, _F32, _P, _P, _P]),
+    "amp_disc_style_reward_indexed": (C.c_int, [_P, _P, _I64, _I64, _P, _I64, _F32, _P, _P, _P, _P]),
     "amp_style_reward_from_logits": (C.c_int, [_P, _I64, _F32, _P, _P]),
+    "amp_gather_rows": (C.c_int, [_P, _I64, _I64, _P, _I64, _I32, _P, _I64, _P, _P]),
+    "amp_scaler_scratch_bytes": (C.c_int64, [_I32]),
+    "amp_scaler_update": (C.c_int, [_P, _I64, _I64, _I32, _P, _P, _P, _P, _I64, _P]),
+    "amp_scaler_apply": (C.c_int, [_P, _I64, _I64, _I32, _P, _P, _F32, _F32, _P, _I64, _P]),
 }
 
 _lib = None

@@ -28,6 +28,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hi
 # per-file extra flags: the motion/obs kernels must not contract a*b+c into FMA (reference rounds every op separately)
 SOURCES = {
     "amp_core.cu": [],
+    "amp_memory.cu": [],
     # AMP_COLLECT_PROFILE=1 (developer builds only) adds the phase-skipping modes of the reference-motion kernel
     "amp_motion.cu": ["-fmad=false"] + (["-DAMP_COLLECT_PROFILE"] if os.environ.get("AMP_COLLECT_PROFILE") == "1" else []),
     # AMP_DISC_PROFILE=1 (developer builds only) adds in-kernel cycle counters to the fused discriminator kernel

@@ -718,7 +718,9 @@ template <int NB, bool VEC>
 __global__ void __launch_bounds__(256) normalise_cast_kernel(const float *__restrict__ x, int64_t x_stride, int64_t M,
                                                               int in_features, const float *__restrict__ mean,
                                                               const float *__restrict__ denom,
-                                                              __nv_bfloat16 *__restrict__ out) {
+                                                              __nv_bfloat16 *__restrict__ out,
+                                                              const int64_t *__restrict__ row_index, int64_t capacity,
+                                                              uint32_t *__restrict__ flags) {
     constexpr int Kp = NB * 64;
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -733,8 +735,18 @@ __global__ void __launch_bounds__(256) normalise_cast_kernel(const float *__rest
         mu[j] = make_float2(c < in_features ? mean[c] : 0.0f, c + 1 < in_features ? mean[c + 1] : 0.0f);
         rc[j] = make_float2(c < in_features ? __frcp_rn(denom[c]) : 0.0f, c + 1 < in_features ? __frcp_rn(denom[c + 1]) : 0.0f);
     }
+    // row_index != NULL: destination row r reads source row row_index[r] (RandomMemory.sample_by_index fused into the
+    // preprocessor); an index outside [0, capacity) reads row 0 and raises bit 1 of *flags
     auto load_row = [&](int64_t r, float2(&v)[NB]) {
-        const float *xr = x + r * x_stride;
+        int64_t sr = r;
+        if (row_index) {
+            sr = __ldg(row_index + r);
+            if (sr < 0 || sr >= capacity) {
+                if (lane == 0 && flags) atomicOr(flags, 2u);
+                sr = 0;
+            }
+        }
+        const float *xr = x + sr * x_stride;
 #pragma unroll
         for (int j = 0; j < NB; ++j) {
             const int c = 2 * (lane + 32 * j);
@@ -775,10 +787,12 @@ __global__ void __launch_bounds__(256) normalise_cast_kernel(const float *__rest
 
 template <bool VEC>
 static int launch_normalise_cast(int nb, int grid, cudaStream_t st, const float *x, int64_t x_stride, int64_t rows, int in_features,
-                                 const float *mean, const float *denom, __nv_bfloat16 *out) {
+                                 const float *mean, const float *denom, __nv_bfloat16 *out, const int64_t *row_index,
+                                 int64_t capacity, uint32_t *flags) {
 #define AMP_CAST_CASE(NBV)                                                                                            \
     case NBV:                                                                                                         \
-        normalise_cast_kernel<NBV, VEC><<<grid, 256, 0, st>>>(x, x_stride, rows, in_features, mean, denom, out);      \
+        normalise_cast_kernel<NBV, VEC><<<grid, 256, 0, st>>>(x, x_stride, rows, in_features, mean, denom, out,       \
+                                                              row_index, capacity, flags);                            \
         break
     switch (nb) {
         AMP_CAST_CASE(1); AMP_CAST_CASE(2); AMP_CAST_CASE(3); AMP_CAST_CASE(4); AMP_CAST_CASE(5); AMP_CAST_CASE(6);
@@ -998,8 +1012,11 @@ int amp_disc_load(amp_disc_t *d, const float *W1, const float *b1, const float *
     return AMP_OK;
 }
 
-int amp_disc_style_reward(amp_disc_t *d, const float *x, int64_t x_stride, int64_t M, float reward_scale, float *reward,
-                          float *logits, void *stream) {
+}  // extern "C"
+
+// x rows are taken in order (row_index == NULL) or gathered: row r of the batch = x[row_index[r]] with x holding `capacity` rows
+static int style_reward_impl(amp_disc_t *d, const float *x, int64_t x_stride, const int64_t *row_index, int64_t capacity,
+                             uint32_t *flags, int64_t M, float reward_scale, float *reward, float *logits, void *stream) {
     AMP_REQUIRE(d && M >= 0, "amp_disc_style_reward: bad handle or negative size");
     AMP_REQUIRE(d->loaded, "amp_disc_style_reward: amp_disc_load has not been called");
     if (M == 0) return AMP_OK;
@@ -1020,11 +1037,14 @@ int amp_disc_style_reward(amp_disc_t *d, const float *x, int64_t x_stride, int64
         const int64_t r0 = c * d->chunk_rows, rows = std::min<int64_t>(d->chunk_rows, M - r0);
         cudaStream_t cs = overlap ? d->side : st;
         if (overlap && c >= 2) AMP_CUDA_TRY(cudaStreamWaitEvent(cs, d->ev_free[b], 0));  // fused(c-2) is done with xhat[b]
-        const float *xc = x + r0 * x_stride;
+        const float *xc = row_index ? x : x + r0 * x_stride;
+        const int64_t *ic = row_index ? row_index + r0 : nullptr;
         const bool vec = (x_stride % 2 == 0) && ((reinterpret_cast<uintptr_t>(xc) & 7u) == 0);
         const int cast_grid = (int)std::min<int64_t>((rows + 7) / 8, (int64_t)sms * 8);
-        int rc = vec ? launch_normalise_cast<true>(d->Kp / BK, cast_grid, cs, xc, x_stride, rows, d->in_features, d->mean, d->denom, d->xhat[b])
-                     : launch_normalise_cast<false>(d->Kp / BK, cast_grid, cs, xc, x_stride, rows, d->in_features, d->mean, d->denom, d->xhat[b]);
+        int rc = vec ? launch_normalise_cast<true>(d->Kp / BK, cast_grid, cs, xc, x_stride, rows, d->in_features, d->mean, d->denom,
+                                                   d->xhat[b], ic, capacity, flags)
+                     : launch_normalise_cast<false>(d->Kp / BK, cast_grid, cs, xc, x_stride, rows, d->in_features, d->mean, d->denom,
+                                                    d->xhat[b], ic, capacity, flags);
         if (rc != AMP_OK) return rc;
         AMP_CUDA_TRY(cudaGetLastError());
         if (overlap) AMP_CUDA_TRY(cudaEventRecord(d->ev_ready[b], cs));
@@ -1117,6 +1137,20 @@ int amp_disc_style_reward(amp_disc_t *d, const float *x, int64_t x_stride, int64
     }
 #endif
     return AMP_OK;
+}
+
+extern "C" {
+
+int amp_disc_style_reward(amp_disc_t *d, const float *x, int64_t x_stride, int64_t M, float reward_scale, float *reward,
+                          float *logits, void *stream) {
+    return style_reward_impl(d, x, x_stride, nullptr, 0, nullptr, M, reward_scale, reward, logits, stream);
+}
+
+int amp_disc_style_reward_indexed(amp_disc_t *d, const float *memory, int64_t memory_stride, int64_t capacity,
+                                  const int64_t *row_index, int64_t M, float reward_scale, float *reward, float *logits,
+                                  uint32_t *flags, void *stream) {
+    AMP_REQUIRE(M == 0 || (row_index && capacity >= 1), "amp_disc_style_reward_indexed: NULL row_index or empty memory");
+    return style_reward_impl(d, memory, memory_stride, row_index, capacity, flags, M, reward_scale, reward, logits, stream);
 }
 
 int amp_style_reward_from_logits(const float *logits, int64_t M, float reward_scale, float *reward, void *stream) {

@@ -71,6 +71,27 @@ class AmpDiscriminator:
         reward = reward.view(*lead, 1)
         return (reward, logits.view(*lead, 1)) if return_logits else reward
 
+    def style_reward_sampled(self, memory_states: torch.Tensor, indexes: torch.Tensor, return_logits: bool = False,
+                             out: Optional[torch.Tensor] = None, flags: Optional[torch.Tensor] = None):
+        """Style reward of ``memory_states[indexes]`` without materialising the gathered batch: skrl
+        ``Memory.sample_by_index`` fused into the preprocessor + discriminator.  ``memory_states`` is the ``(capacity, K*A)``
+        fp32 tensor of a memory (``AmpStateMemory.states``), ``indexes`` int64 ``(M,)``; ``flags`` an optional int32
+        device word whose bit 1 is raised by an out-of-range index."""
+        mem = memory_states
+        if mem.device != self.device or mem.dtype != torch.float32 or mem.dim() != 2 or mem.stride(1) != 1:
+            raise RuntimeError("memory_states must be a float32 (capacity, K*A) tensor on the discriminator's device")
+        if mem.shape[1] != self.in_features:
+            raise RuntimeError(f"expected memory rows of width {self.in_features}, got {mem.shape[1]}")
+        idx = indexes.to(self.device, torch.int64).reshape(-1).contiguous()
+        M = idx.numel()
+        reward = out if out is not None else torch.empty(M, dtype=torch.float32, device=self.device)
+        logits = torch.empty(M, dtype=torch.float32, device=self.device) if return_logits else None
+        lib, stream = _lib.enter(self.device)
+        _lib.check(lib.amp_disc_style_reward_indexed(self._h, _lib.ptr(mem), mem.stride(0), mem.shape[0], _lib.ptr(idx), M,
+                                                     self.reward_scale, _lib.ptr(reward), _lib.ptr(logits), _lib.ptr(flags), stream))
+        reward = reward.view(M, 1)
+        return (reward, logits.view(M, 1)) if return_logits else reward
+
     def close(self):
         if getattr(self, "_h", None) is not None:
             try:

@@ -171,12 +171,28 @@ AMP_API int amp_task_reward(const float *scales, const uint8_t *reset_terminated
                             int32_t D, const float *body_lin_vel_w, const float *body_quat_w, int32_t Bsim, int32_t ref_body,
                             const float *command, int64_t N, float *total, float *terms, float *track_err, void *stream);
 
+/* ---- AMP memories and the state preprocessor (upstream skrl >= 1.4.3, not vendored) ------------------ */
+/* skrl memories/torch/base.py Memory.sample_by_index (RandomMemory.sample draws the indexes): out[r,:] = src[row_index[r],:].
+ *   src device f32 (capacity, W) with row stride src_stride floats; row_index device i64[M]; out device f32 (M, W).
+ *   An index outside [0, capacity) (an IndexError in skrl) yields a zero row and sets bit 1 of *flags (device word or NULL). */
+AMP_API int amp_gather_rows(const float *src, int64_t src_stride, int64_t capacity, const int64_t *row_index, int64_t M, int32_t W,
+                            float *out, int64_t out_stride, uint32_t *flags, void *stream);
+/* skrl RunningStandardScaler, train = True (_parallel_variance): merge the batch x (M, W) into the float64 running
+ * statistics in place.  running_mean / running_variance device f64[W], current_count device f64[1]; scratch is a device
+ * buffer of at least amp_scaler_scratch_bytes(W) bytes (no allocation inside the call). */
+AMP_API int64_t amp_scaler_scratch_bytes(int32_t W);
+AMP_API int amp_scaler_update(const float *x, int64_t x_stride, int64_t M, int32_t W, double *running_mean, double *running_variance,
+                              double *current_count, void *scratch, int64_t scratch_bytes, void *stream);
+/* skrl RunningStandardScaler, train = False: out = clamp((x - mean.float()) / (sqrt(var.float()) + epsilon), -clip, clip). */
+AMP_API int amp_scaler_apply(const float *x, int64_t x_stride, int64_t M, int32_t W, const double *running_mean,
+                             const double *running_variance, float epsilon, float clip, float *out, int64_t out_stride, void *stream);
+
 /* ---- discriminator style reward (skrl AMP._update; cfg agents/skrl_g1_dance_amp_cfg.yaml:31-39, 80, 94-95) ------ */
 /* Network Linear(in,h1)-ReLU-Linear(h1,h2)-ReLU-Linear(h2,1) on RunningStandardScaler-normalised input.
- * h1, h2 must be multiples of 128 (reference: 1024, 512); in_features any value >= 1 (padded to 64 internally). */
+ * h1, h2 must be multiples of 256 (reference: 1024, 512); in_features any value >= 1 (padded to 64 internally). */
 AMP_API int amp_disc_create(int32_t in_features, int32_t h1, int32_t h2, int64_t max_rows, void *stream, amp_disc_t **out);
 AMP_API int amp_disc_destroy(amp_disc_t *d);
-/* Rows processed per internal chunk (three kernel launches per chunk); 0 for a NULL handle. */
+/* Rows processed per internal chunk (two kernel launches per chunk: scaler + cast, fused MLP); 0 for a NULL handle. */
 AMP_API int64_t amp_disc_chunk_rows(const amp_disc_t *d);
 /* Refresh the staged bf16 weights / fp32 biases / scaler statistics from the fp32 masters the trainer owns
  * (device pointers; W row-major (out,in) as torch.nn.Linear stores them; mean/var are the scaler's float64 buffers). */
@@ -186,6 +202,13 @@ AMP_API int amp_disc_load(amp_disc_t *d, const float *W1, const float *b1, const
  * logits device f32[M] or NULL.  reward = -log(max(1 - 1/(1+exp(-logit)), 1e-4)) * reward_scale. */
 AMP_API int amp_disc_style_reward(amp_disc_t *d, const float *x, int64_t x_stride, int64_t M, float reward_scale,
                           float *reward, float *logits, void *stream);
+/* The same on rows gathered from a memory: batch row r = memory[row_index[r], :] (skrl Memory.sample_by_index fused into the
+ * preprocessor + discriminator, no (M, in_features) intermediate).  memory device f32 (capacity, in_features), row stride
+ * memory_stride floats; row_index device i64[M]; an index outside [0, capacity) reads row 0 and sets bit 1 of *flags
+ * (device word or NULL). */
+AMP_API int amp_disc_style_reward_indexed(amp_disc_t *d, const float *memory, int64_t memory_stride, int64_t capacity,
+                                          const int64_t *row_index, int64_t M, float reward_scale, float *reward, float *logits,
+                                          uint32_t *flags, void *stream);
 /* Standalone epilogue (logits -> reward) for callers that own the discriminator forward. */
 AMP_API int amp_style_reward_from_logits(const float *logits, int64_t M, float reward_scale, float *reward, void *stream);
 

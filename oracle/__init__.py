@@ -6,7 +6,8 @@ reference's per-step AMP path so the CUDA kernels in ``humanoid_amp_b200`` can b
 * ``motion_oracle``  -- ``MotionLoader`` (reference ``motions/motion_loader.py:98-390``)
 * ``env_oracle``     -- ``compute_obs`` / ``quaternion_to_tangent_and_normal`` / ``collect_reference_motions`` /
                         history shift / reset fill (reference ``g1_amp_env.py:175-193, 414-419, 445-497, 535-561``)
-* ``disc_oracle``    -- skrl ``RunningStandardScaler`` (eval) + MLP + AMP style reward (upstream skrl >= 1.4.3,
+* ``memory_oracle``  -- skrl ``RandomMemory`` ring write / ``sample_by_index`` (upstream skrl, PARITY UNPINNED)
+* ``disc_oracle``    -- skrl ``RunningStandardScaler`` (eval + train-mode statistics) + MLP + AMP style reward (upstream skrl >= 1.4.3,
                         ``agents/torch/amp/amp.py::_update``; configured by ``agents/skrl_g1_dance_amp_cfg.yaml:31-39, 80, 94-95``)
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import
@@ -43,3 +44,4 @@ from .env_oracle import (  # noqa: F401
     task_rewards,
 )
 from .disc_oracle import OracleDiscriminator, running_standard_scaler_eval, style_reward_from_logits  # noqa: F401
+from .memory_oracle import OracleRandomMemory  # noqa: F401

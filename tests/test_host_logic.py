@@ -86,3 +86,39 @@ def test_synthetic_clip_has_reference_format(name):
     assert set(arr["dof_names"].tolist()) == set(robot.joint_names)
     for key in robot.key_body_names + (robot.reference_body,):
         assert key in arr["body_names"].tolist()
+
+
+def test_oracle_random_memory_ring_and_split():
+    """The memory oracle itself: wrap-around writes, ``filled``, and ``np.array_split`` mini-batches (skrl semantics)."""
+    import torch
+
+    from oracle import OracleRandomMemory
+
+    mem = OracleRandomMemory(5, 2)
+    mem.add_samples(torch.arange(6, dtype=torch.float32).view(3, 2))
+    assert len(mem) == 3 and not mem.filled and mem.memory_index == 3
+    mem.add_samples(torch.arange(6, 14, dtype=torch.float32).view(4, 2))
+    assert len(mem) == 5 and mem.filled and mem.memory_index == 2
+    assert mem.states[:, 0].tolist() == [10.0, 12.0, 4.0, 6.0, 8.0]
+    parts = mem.sample_by_index([0, 1, 2, 3, 4, 0, 1], mini_batches=3)
+    assert [p.shape[0] for p in parts] == [3, 2, 2]
+    assert parts[0][:, 0].tolist() == [10.0, 12.0, 4.0]
+
+
+def test_memory_and_scaler_need_cuda():
+    import torch
+
+    import humanoid_amp_b200 as amp
+
+    if torch.cuda.is_available():
+        import pytest
+
+        pytest.skip("CPU-only check")
+    for make in (lambda: amp.AmpStateMemory(8, 4, "cpu"), lambda: amp.RunningStandardScaler(4, device="cpu"),
+                 lambda: amp.InputPrefetcher("cpu", 8)):
+        try:
+            make()
+        except amp.AmpB200Error as e:
+            assert "no CPU" in str(e)
+        else:
+            raise AssertionError("constructed without a CUDA device")

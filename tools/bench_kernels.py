@@ -136,6 +136,29 @@ def main():
         ms = timed(lambda: disc.style_reward(x, out=r))
         row("disc style reward (cast + fused tcgen05)", ms, flops=M * bench.flops_per_row(width), note=f"K*A={width} M={M}")
         del disc, x
+
+    # ---- AMP memories + state preprocessor ----------------------------------------------------------------
+    for width, cap, M in ((166, 2_000_000, 1_000_000), (830, 400_000, 262_144), (166, 200_000, 65_536)):
+        mem = amp.AmpStateMemory(cap, width, DEV)
+        mem.add_samples(torch.randn(cap, width, device=DEV))
+        idx = mem.sample_indexes(M, generator=torch.Generator(device="cuda").manual_seed(3))
+        out = torch.empty((M, width), device=DEV)
+        ms = timed(lambda: mem.sample_by_index(idx, out=out))
+        row("gather_rows_kernel", ms, M * (2 * width * 4 + 8), note=f"RandomMemory.sample_by_index W={width} capacity={cap} M={M}")
+        sc = amp.RunningStandardScaler(width, device=DEV)
+        ms = timed(lambda: sc.update(out))
+        row("scaler_partial+merge_kernel", ms, M * width * 4, note=f"RunningStandardScaler train update W={width} M={M}")
+        res = torch.empty_like(out)
+        ms = timed(lambda: sc(out, out=res))
+        row("scaler_apply_kernel", ms, 2 * M * width * 4, note=f"RunningStandardScaler eval W={width} M={M}")
+        W, b = skrl_style_discriminator_params(width, seed=42, logit_gain=5.0)
+        disc = amp.AmpDiscriminator(width, device=DEV, max_rows=M)
+        disc.load(W, b, sc.running_mean, sc.running_variance)
+        r = torch.empty(M, device=DEV)
+        ms = timed(lambda: disc.style_reward_sampled(mem.states, idx, out=r))
+        row("disc style reward on sampled rows (gather fused into the cast)", ms, flops=M * bench.flops_per_row(width),
+            note=f"K*A={width} M={M} from capacity {cap}")
+        del mem, out, res, disc, sc
     tmp.cleanup()
 
 
