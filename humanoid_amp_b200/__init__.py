@@ -8,6 +8,7 @@ Public surface (same names and argument meaning as the reference, see each modul
 * ``AmpDiscriminator.style_reward``                  <- skrl ``AMP._update`` style-reward block
 * ``reduce_parameters`` / ``shard_envs``             <- skrl ``Model.reduce_parameters`` + per-rank env sharding
 * ``AmpStateMemory``, ``RunningStandardScaler``        <- skrl ``RandomMemory`` (motion dataset / replay buffer), AMP state preprocessor
+* ``AmpDiscriminatorUpdate``                         <- skrl ``AMP._update`` discriminator loss block + its backward pass
 * ``InputPrefetcher`` / ``ResultReader``             host staging: the reference's host ``times`` / ``motion_ids`` in, rewards out
 
 Everything executes in ``libamp_b200.so`` (hand-written CUDA behind the C ABI of ``include/amp_b200.h``); importing
@@ -23,5 +24,6 @@ from .distributed import reduce_parameters, shard_envs  # noqa: F401
 from .graphs import capture_step  # noqa: F401
 from .pipeline import InputPrefetcher, ResultReader  # noqa: F401
 from .memory import AmpStateMemory, RunningStandardScaler  # noqa: F401
+from .disc_update import AmpDiscriminatorUpdate  # noqa: F401
 
 __version__ = "0.1.0"

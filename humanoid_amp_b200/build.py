@@ -33,6 +33,7 @@ SOURCES = {
     "amp_motion.cu": ["-fmad=false"] + (["-DAMP_COLLECT_PROFILE"] if os.environ.get("AMP_COLLECT_PROFILE") == "1" else []),
     # AMP_DISC_PROFILE=1 (developer builds only) adds in-kernel cycle counters to the fused discriminator kernel
     "amp_disc.cu": ["-DAMP_DISC_PROFILE"] if os.environ.get("AMP_DISC_PROFILE") == "1" else [],
+    "amp_disc_train.cu": [],
 }
 HEADERS = ["amp_internal.h", "amp_math.cuh", os.path.join(ROOT, "include", "amp_b200.h")]
 

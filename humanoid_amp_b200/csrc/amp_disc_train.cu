@@ -1,0 +1,738 @@
+// Discriminator LOSS + GRADIENTS of the AMP update on the 5th-generation tensor cores.
+//
+//   amp_disc_train_*  <- skrl AMP._update, "compute discriminator loss" block + the backward pass of that loss (upstream
+//                        skrl >= 1.4.3, not vendored; configured by the reference at agents/skrl_g1_dance_amp_cfg.yaml:31-39
+//                        (MLP 1024-512-1, ReLU), :89 (loss scale 5), :94 (discriminator_batch_size 4096), :96-98 (logit
+//                        regularisation 0.05, gradient penalty 5, weight decay 1e-4))
+//
+// The three batches (agent rollout, replay buffer, motion dataset; B rows each) sit in ONE row space of four blocks of
+// Bp = B rounded up to 128 rows:   [agent | replay | motion | gradient-penalty rows of the motion block].
+// Every matrix below has 4*Bp rows, so the two weight-gradient products absorb the gradient-penalty terms as extra K:
+//
+//   X   (4Bp, Kp)  bf16   rows <3Bp: normalised states x_hat          rows >=3Bp: G  = dL/dg (g = input gradient of d)
+//   A1  (4Bp, h1)  bf16   rows <3Bp: a1 = relu(x_hat W1^T + b1)       rows >=3Bp: q1 = (G W1^T) * m1
+//   A2  (3Bp, h2)  bf16   a2 = relu(a1 W2^T + b2)
+//   E2  (4Bp, h2)  bf16   rows <3Bp: dz2 = dd * w3 * m2               rows >=3Bp: u2 = w3 * m2
+//   E1  (4Bp, h1)  bf16   rows <3Bp: dz1 = (dz2 W2) * m1              rows >=3Bp: v1 = (u2 W2) * m1
+//
+//   dL/dW2 = E2^T A1          dL/dW1 = E1^T X          (both contract over all 4Bp rows; derivation: oracle/disc_train_oracle.py)
+//
+// Launch sequence of one step (9 GEMM launches of ONE templated tcgen05 kernel + 6 small kernels):
+//   cast_transpose x2   W1, W2 -> bf16 (row-major and transposed) + sum of squares
+//   GEMM  F1   A1[:3Bp] = relu(X[:3Bp] W1^T + b1)                     NT, bias+ReLU epilogue
+//   GEMM  F2   A2       = relu(A1[:3Bp] W2^T + b2)                    NT, bias+ReLU
+//   head       d = a2.w3 + b3, BCE terms, dd, E2 (dz2 and u2), dL/db2, dL/dw3 (BCE part), dL/db3
+//   GEMM  B1   E1 = (E2 W2) * m1            (all 4Bp rows: dz1 and v1 in one launch)    NT on W2^T, mask epilogue
+//   GEMM  GP2  G = c * (v1 W1), sum g^2     -> X[3Bp:]                                 NT on W1^T, scale+sumsq epilogue
+//   GEMM  GP3  q1 = (G W1^T) * m1           -> A1[3Bp:]                                NT, mask epilogue
+//   GEMM  GP6  S = (q1 W2^T) * m2                                                      NT, mask epilogue
+//   GEMM  dW2  slices of E2^T A1            both operands MN-major (the batch dimension is K), split-K into slices
+//   GEMM  dW1  slices of E1^T X
+//   colsum x2  dL/db1 = colsum(E1[:3Bp]),  dL/dw3 += colsum(S)
+//   finalize   sum the split-K slices, add weight decay / logit regularisation, write the fp32 gradients and loss terms
+//
+// Rows >= B inside a block are padding: the head kernel writes zero rows there, and zero rows of E2 stay zero through every
+// later product, so no GEMM needs a row bound.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "amp_internal.h"
+#include "amp_tc.cuh"
+
+namespace amp {
+namespace train {
+
+using namespace amp::tc;
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = kBlockK;
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
+constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KiB
+constexpr int MN_BOX_BYTES = BK * 64 * 2;   // one MN-major TMA box: 64 K-rows x 64 columns (128-byte swizzled rows) = 8 KiB
+constexpr int GEMM_THREADS = 320;
+constexpr int TMEM_COLS = 512;
+constexpr int GEMM_SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 + 1024;
+
+enum Epilogue { EPI_BIAS_RELU = 0, EPI_MASK = 1, EPI_SCALE_SUMSQ = 2, EPI_SLICE = 3 };
+
+// MN-major operand in the canonical 128B-swizzle layout: a [64 K-rows x 64 MN-elements] TMA box puts K-row k at byte k*128
+// with the 16-byte chunks XOR-swizzled by (k % 8).  Canonical form (CUTLASS make_umma_desc<Major::MN>, SW128, units of
+// 16 bytes): ((8,n),(8,k)) : ((1,LBO),(8,SBO)) -- 64 MN-elements contiguous, 8 K-rows 128 B apart form one swizzle atom,
+// SBO = distance between 8-row K groups (1024 B), LBO = distance between 64-element MN blocks (one box = 8192 B).
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)(MN_BOX_BYTES >> 4) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+struct GemmParams {
+    int m_tiles, n_tiles, splits, kblocks;  // work items = splits x m_tiles x n_tiles; kblocks = K / 64 over all splits
+    int n_valid;                            // output columns >= n_valid do not exist (multiple of 32)
+    const float *bias;                      // EPI_BIAS_RELU
+    __nv_bfloat16 *out;                     // bf16 output (all but EPI_SLICE)
+    long long out_ld;
+    const __nv_bfloat16 *mask;              // EPI_MASK: out = mask[mrow, col] != 0 ? alpha * acc : 0
+    long long mask_ld;
+    int mask_split, mask_shift;             // mrow = row < mask_split ? row : row - mask_shift
+    float alpha;                            // EPI_MASK / EPI_SCALE_SUMSQ
+    float *sumsq;                           // EPI_SCALE_SUMSQ: atomicAdd(sumsq, sum acc^2)
+    float *slices;                          // EPI_SLICE: fp32 (splits, m_tiles*128, slice_ld)
+    long long slice_ld, slice_stride;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&v);
+}
+
+// One persistent launch: D[128 x 256] tiles of  A (M x K)  times  B (N x K)^T, bf16 operands, fp32 accumulation in TMEM.
+//   A_MN / B_MN = false: operand stored K-major (row = M/N index, K contiguous)   -> TMA box [128|256 rows x 64 K]
+//               = true : operand stored MN-major (row = K index, M/N contiguous)  -> TMA boxes [64 K-rows x 64 columns]
+// Warp roles (320 threads): 0 TMA producer, 1 TMEM alloc + single-thread MMA issuer, 2..9 epilogue (warps w and w+4 share a
+// TMEM lane quarter and split the 256 accumulator columns).  Accumulators ping-pong between the two halves of TMEM so the
+// drain of item i overlaps the MMAs of item i+1.
+template <bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+train_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t smem_a = base;
+    const uint32_t smem_b = base + STAGES * A_STAGE_BYTES;
+    const uint32_t bars = smem_b + STAGES * B_STAGE_BYTES;
+    const uint32_t full_bar = bars, empty_bar = bars + 8 * STAGES;
+    const uint32_t acc_full = bars + 16 * STAGES, acc_empty = acc_full + 16;
+    const uint32_t tmem_slot = acc_full + 32;
+    uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles = p.m_tiles * p.n_tiles;
+    const int items = tiles * p.splits;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(full_bar + 8 * i, 1);
+            mbar_init(empty_bar + 8 * i, 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(acc_full + 8 * i, 1);
+            mbar_init(acc_empty + 8 * i, 8);  // one arrival per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint64_t keep = l2_policy_evict_last();  // every operand of the step is re-read by other CTAs / later launches
+            for (int item = blockIdx.x; item < items; item += gridDim.x) {
+                const int s = item / tiles, t = item - s * tiles;
+                const int m = t / p.n_tiles, n = t - m * p.n_tiles;
+                const int kb0 = (int)((long long)s * p.kblocks / p.splits), kb1 = (int)((long long)(s + 1) * p.kblocks / p.splits);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+                    const uint32_t fb = full_bar + 8 * stage;
+                    mbar_arrive_expect_tx(fb, A_STAGE_BYTES + B_STAGE_BYTES);
+                    const uint32_t sa = smem_a + stage * A_STAGE_BYTES, sb = smem_b + stage * B_STAGE_BYTES;
+                    if constexpr (A_MN) {
+#pragma unroll
+                        for (int j = 0; j < BM / 64; ++j) tma_load_2d_hint(sa + j * MN_BOX_BYTES, &tmap_a, m * BM + j * 64, kb * BK, fb, keep);
+                    } else {
+                        tma_load_2d_hint(sa, &tmap_a, kb * BK, m * BM, fb, keep);
+                    }
+                    if constexpr (B_MN) {
+#pragma unroll
+                        for (int j = 0; j < BN / 64; ++j) tma_load_2d_hint(sb + j * MN_BOX_BYTES, &tmap_b, n * BN + j * 64, kb * BK, fb, keep);
+                    } else {
+                        tma_load_2d_hint(sb, &tmap_b, kb * BK, n * BN, fb, keep);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            // kind::f16 instruction descriptor: D fp32 (bit 4), A/B bf16 (bits 7, 10), A/B major (bits 15, 16; 1 = MN-major),
+            // N >> 3 at bits [17,23), M >> 4 at bits [24,29)
+            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)A_MN << 15) | ((uint32_t)B_MN << 16) |
+                                       ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            // descriptor start-address step (units of 16 B) per UMMA_K = 16: K-major 32 B inside the swizzled row;
+            // MN-major 16 K-rows x 128 B = 2048 B
+            constexpr uint32_t a_step = A_MN ? (16 * 128) >> 4 : 2;
+            constexpr uint32_t b_step = B_MN ? (16 * 128) >> 4 : 2;
+            int stage = 0;
+            uint32_t phase = 0, it = 0;
+            for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+                const int s = item / tiles;
+                const int kb0 = (int)((long long)s * p.kblocks / p.splits), kb1 = (int)((long long)(s + 1) * p.kblocks / p.splits);
+                const uint32_t r = it & 1, use = it >> 1;
+                mbar_wait(acc_empty + 8 * r, (use & 1) ^ 1);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + r * BN;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(full_bar + 8 * stage, phase);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_a + stage * A_STAGE_BYTES, sb = smem_b + stage * B_STAGE_BYTES;
+                    const uint64_t a0 = A_MN ? make_mnmajor_sw128_desc(sa) : make_kmajor_sw128_desc(sa);
+                    const uint64_t b0 = B_MN ? make_mnmajor_sw128_desc(sb) : make_kmajor_sw128_desc(sb);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        umma_bf16(d_tmem, a0 + a_step * k, b0 + b_step * k, idesc, (uint32_t)(kb != kb0 || k != 0));
+                    umma_commit(empty_bar + 8 * stage);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(acc_full + 8 * r);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================= epilogue warps 2..9 =================
+        const int quarter = warp & 3;
+        const int colhalf = (warp - 2) >> 2;
+        const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+        uint32_t it = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+            const int s = item / tiles, t = item - s * tiles;
+            const int m = t / p.n_tiles, n = t - m * p.n_tiles;
+            const uint32_t r = it & 1, use = it >> 1;
+            const long long row = (long long)m * BM + quarter * 32 + lane;
+            const int col0 = n * BN + colhalf * (BN / 2);
+            const uint32_t acc = tmem_base + lane_base + r * BN + (uint32_t)(colhalf * (BN / 2));
+            mbar_wait(acc_full + 8 * r, use & 1);
+            tcgen05_fence_after();
+            [[maybe_unused]] float ss = 0.0f;
+            [[maybe_unused]] long long mrow = 0;
+            if constexpr (EPI == EPI_MASK) mrow = row < p.mask_split ? row : row - p.mask_shift;
+            const int chunks = min(4, max(0, (p.n_valid - col0 + 31) / 32));  // warp-uniform
+            uint32_t v[2][32];
+            if (chunks > 0) tmem_ld_32x32(acc, v[0]);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (c >= chunks) break;
+                const int col = col0 + c * 32;
+                [[maybe_unused]] uint4 mk[4];
+                if constexpr (EPI == EPI_MASK) {
+                    const uint4 *mp = reinterpret_cast<const uint4 *>(p.mask + mrow * p.mask_ld + col);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) mk[j] = __ldg(mp + j);
+                }
+                tmem_ld_wait();
+                if (c + 1 < chunks) tmem_ld_32x32(acc + (uint32_t)((c + 1) * 32), v[(c + 1) & 1]);
+                const uint32_t(&cur)[32] = v[c & 1];
+                if constexpr (EPI == EPI_SLICE) {
+                    float4 *dst = reinterpret_cast<float4 *>(p.slices + (long long)s * p.slice_stride + row * p.slice_ld + col);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        dst[j] = make_float4(__uint_as_float(cur[4 * j]), __uint_as_float(cur[4 * j + 1]), __uint_as_float(cur[4 * j + 2]),
+                                             __uint_as_float(cur[4 * j + 3]));
+                } else {
+                    uint32_t o[16];
+                    if constexpr (EPI == EPI_BIAS_RELU) {
+                        const float4 *bias4 = reinterpret_cast<const float4 *>(p.bias + col);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 b = __ldg(bias4 + j);
+                            o[2 * j] = pack_bf16(fmaxf(__uint_as_float(cur[4 * j]) + b.x, 0.0f), fmaxf(__uint_as_float(cur[4 * j + 1]) + b.y, 0.0f));
+                            o[2 * j + 1] = pack_bf16(fmaxf(__uint_as_float(cur[4 * j + 2]) + b.z, 0.0f), fmaxf(__uint_as_float(cur[4 * j + 3]) + b.w, 0.0f));
+                        }
+                    } else if constexpr (EPI == EPI_MASK) {
+                        const uint32_t *mw = reinterpret_cast<const uint32_t *>(mk);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float a = (mw[j] & 0xffffu) ? __uint_as_float(cur[2 * j]) * p.alpha : 0.0f;
+                            const float b = (mw[j] >> 16) ? __uint_as_float(cur[2 * j + 1]) * p.alpha : 0.0f;
+                            o[j] = pack_bf16(a, b);
+                        }
+                    } else {  // EPI_SCALE_SUMSQ
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float a = __uint_as_float(cur[2 * j]), b = __uint_as_float(cur[2 * j + 1]);
+                            ss = fmaf(a, a, ss);
+                            ss = fmaf(b, b, ss);
+                            o[j] = pack_bf16(a * p.alpha, b * p.alpha);
+                        }
+                    }
+                    uint4 *dst = reinterpret_cast<uint4 *>(p.out + row * p.out_ld + col);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dst[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                }
+            }
+            // all TMEM reads of this accumulator by this warp have completed (tcgen05.wait::ld above): release the region
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + 8 * r);
+            if constexpr (EPI == EPI_SCALE_SUMSQ) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                if (lane == 0 && chunks > 0) atomicAdd(p.sumsq, ss);
+            }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// fp32 master (R, C) -> bf16 (R, Cp) zero padded, its transpose bf16 (Cp, R), and sum of squares (atomicAdd into *sumsq).
+// 32 x 32 tiles through shared memory: both stores are coalesced.  R % 32 == 0, Cp % 32 == 0.
+__global__ void __launch_bounds__(256) cast_transpose_kernel(const float *__restrict__ w, int R, int C, int Cp,
+                                                              __nv_bfloat16 *__restrict__ out, __nv_bfloat16 *__restrict__ out_t,
+                                                              float *__restrict__ sumsq) {
+    __shared__ float tile[32][33];
+    __shared__ float part[8];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    float ss = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = r0 + ty + 8 * i, c = c0 + tx;
+        const float x = c < C ? w[(long long)r * C + c] : 0.0f;
+        ss = fmaf(x, x, ss);
+        tile[ty + 8 * i][tx] = x;
+        out[(long long)r * Cp + c] = __float2bfloat16_rn(x);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = c0 + ty + 8 * i, r = r0 + tx;
+        out_t[(long long)c * R + r] = __float2bfloat16_rn(tile[tx][ty + 8 * i]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (tx == 0) part[ty] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.0f;
+        for (int i = 0; i < 8; ++i) t += part[i];
+        atomicAdd(sumsq, t);
+    }
+}
+
+// scalar accumulators at the head of the fp32 workspace (zeroed at the start of every step)
+enum Acc { ACC_BCE_CAT = 0, ACC_BCE_MOTION, ACC_W3_SQ, ACC_GP_SQ, ACC_W_SQ, ACC_GB3, ACC_COUNT = 8 };
+
+__device__ __forceinline__ float softplus_f(float x) { return fmaxf(x, 0.0f) + log1pf(__expf(-fabsf(x))); }
+
+// After the second layer: logits, BCE terms, dL/dd, and everything that hangs off it row by row.
+//   rows_per_block = 32; phase A: one warp per row -> d = a2 . w3 + b3 and dd; phase B: one thread per column pair walks the
+//   32 rows: E2[row] = dd * w3 * m2 (and, for motion rows, E2[row + Bp] = w3 * m2), column sums dL/db2 and sum dd * a2.
+__global__ void __launch_bounds__(256) head_kernel(const __nv_bfloat16 *__restrict__ a2, int h2, int Bp, int B,
+                                                   const float *__restrict__ w3, const float *__restrict__ b3, float loss_scale,
+                                                   __nv_bfloat16 *__restrict__ e2, float *__restrict__ acc, float *__restrict__ gw3,
+                                                   float *__restrict__ gb2, float *__restrict__ logits) {
+    __shared__ float s_dd[32];
+    __shared__ float s_loss[32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long row0 = (long long)blockIdx.x * 32;
+    const int block_src = (int)(row0 / Bp);  // 32 | Bp: a block never straddles two sources
+    for (int rl = warp; rl < 32; rl += 8) {
+        const long long row = row0 + rl;
+        const __nv_bfloat16 *ar = a2 + row * h2;
+        float dot = 0.0f;
+        for (int c = lane * 8; c < h2; c += 256) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4 *>(ar + c));
+            const float4 wa = __ldg(reinterpret_cast<const float4 *>(w3 + c)), wb = __ldg(reinterpret_cast<const float4 *>(w3 + c + 4));
+            const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&q);
+            const float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]), f2 = __bfloat1622float2(h[2]), f3 = __bfloat1622float2(h[3]);
+            dot = fmaf(f0.x, wa.x, dot); dot = fmaf(f0.y, wa.y, dot); dot = fmaf(f1.x, wa.z, dot); dot = fmaf(f1.y, wa.w, dot);
+            dot = fmaf(f2.x, wb.x, dot); dot = fmaf(f2.y, wb.y, dot); dot = fmaf(f3.x, wb.z, dot); dot = fmaf(f3.y, wb.w, dot);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        if (lane == 0) {
+            const bool valid = (int)(row - (long long)block_src * Bp) < B;
+            const float d = dot + __ldg(b3);
+            if (logits) logits[row] = d;
+            const float sig = 1.0f / (1.0f + __expf(-d));
+            float dd, loss;
+            if (block_src < 2) {  // agent / replay: target 0, mean over 2B rows
+                dd = 0.5f * loss_scale * sig / (2.0f * (float)B);
+                loss = softplus_f(d);
+            } else {              // motion: target 1, mean over B rows
+                dd = 0.5f * loss_scale * (sig - 1.0f) / (float)B;
+                loss = softplus_f(-d);
+            }
+            s_dd[rl] = valid ? dd : 0.0f;
+            s_loss[rl] = valid ? loss : 0.0f;
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        float l = s_loss[lane], g = s_dd[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            l += __shfl_xor_sync(0xffffffffu, l, o);
+            g += __shfl_xor_sync(0xffffffffu, g, o);
+        }
+        if (lane == 0) {
+            atomicAdd(acc + (block_src < 2 ? ACC_BCE_CAT : ACC_BCE_MOTION), l);
+            atomicAdd(acc + ACC_GB3, g);
+        }
+    }
+    const bool motion = block_src == 2;
+    for (int c = threadIdx.x * 2; c < h2; c += 512) {
+        const float2 w = __ldg(reinterpret_cast<const float2 *>(w3 + c));
+        float sb0 = 0.0f, sb1 = 0.0f, sw0 = 0.0f, sw1 = 0.0f;
+#pragma unroll 4
+        for (int rl = 0; rl < 32; ++rl) {
+            const long long row = row0 + rl;
+            const float dd = s_dd[rl];
+            const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(a2 + row * h2 + c));
+            const float m0 = a.x > 0.0f ? 1.0f : 0.0f, m1 = a.y > 0.0f ? 1.0f : 0.0f;
+            const float z0 = dd * w.x * m0, z1 = dd * w.y * m1;
+            sb0 += z0; sb1 += z1;
+            sw0 = fmaf(dd, a.x, sw0); sw1 = fmaf(dd, a.y, sw1);
+            *reinterpret_cast<uint32_t *>(e2 + row * h2 + c) = pack_bf16(z0, z1);
+            if (motion) {
+                const bool valid = (int)(row - 2LL * Bp) < B;
+                *reinterpret_cast<uint32_t *>(e2 + (row + Bp) * h2 + c) = valid ? pack_bf16(w.x * m0, w.y * m1) : 0u;
+            }
+        }
+        atomicAdd(gb2 + c, sb0); atomicAdd(gb2 + c + 1, sb1);
+        atomicAdd(gw3 + c, sw0); atomicAdd(gw3 + c + 1, sw1);
+    }
+}
+
+// out[c] += sum over rows of src[r, c] (bf16 -> fp32): a block takes 64 rows x 512 columns, one thread per column pair
+__global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16 *__restrict__ src, long long ld, int rows, int cols,
+                                                     float *__restrict__ out) {
+    const int c = blockIdx.x * 512 + threadIdx.x * 2;
+    if (c >= cols) return;
+    const int r0 = blockIdx.y * 64, r1 = min(rows, r0 + 64);
+    float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll 8
+    for (int r = r0; r < r1; ++r) {
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(src + (long long)r * ld + c));
+        s0 += a.x; s1 += a.y;
+    }
+    atomicAdd(out + c, s0);
+    atomicAdd(out + c + 1, s1);
+}
+
+struct FinalizeParams {
+    const float *W1, *W2, *w3;     // fp32 masters
+    const float *slices1, *slices2;
+    int splits1, splits2, in_features, Kp, h1, h2, B;
+    const float *acc;              // scalar accumulators
+    const float *ws_gw3, *ws_gb2, *ws_gb1;
+    float loss_scale, c_reg, c_gp, c_wd;
+    float *gW1, *gb1, *gW2, *gb2, *gW3, *gb3, *terms;
+};
+
+// Deterministic split-K reduction + the closed-form regularisation gradients; writes the six fp32 gradient tensors (torch
+// layout) and terms[6] = {bce_agent_replay, bce_motion, logit_regularization, gradient_penalty, weight_decay, loss}.
+__global__ void __launch_bounds__(256) finalize_kernel(FinalizeParams p) {
+    const long long n1 = (long long)p.h1 * p.in_features, n2 = (long long)p.h2 * p.h1;
+    const float cw = 2.0f * p.loss_scale * p.c_wd;
+    const long long stride = (long long)gridDim.x * blockDim.x, tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long s1 = (long long)p.h1 * p.Kp, s2 = n2;
+    for (long long e = tid; e < n1; e += stride) {
+        const int r = (int)(e / p.in_features), c = (int)(e - (long long)r * p.in_features);
+        float g = 0.0f;
+        for (int s = 0; s < p.splits1; ++s) g += p.slices1[s * s1 + (long long)r * p.Kp + c];
+        p.gW1[e] = fmaf(cw, p.W1[e], g);
+    }
+    for (long long e = tid; e < n2; e += stride) {
+        float g = 0.0f;
+        for (int s = 0; s < p.splits2; ++s) g += p.slices2[s * s2 + e];
+        p.gW2[e] = fmaf(cw, p.W2[e], g);
+    }
+    for (long long e = tid; e < p.h2; e += stride) {
+        p.gW3[e] = fmaf(cw + 2.0f * p.loss_scale * p.c_reg, p.w3[e], p.ws_gw3[e]);
+        p.gb2[e] = p.ws_gb2[e];
+    }
+    for (long long e = tid; e < p.h1; e += stride) p.gb1[e] = p.ws_gb1[e];
+    if (tid == 0) {
+        p.gb3[0] = p.acc[ACC_GB3];
+        const float bce_cat = p.acc[ACC_BCE_CAT] / (2.0f * (float)p.B), bce_motion = p.acc[ACC_BCE_MOTION] / (float)p.B;
+        const float reg = p.acc[ACC_W3_SQ], gp = p.acc[ACC_GP_SQ] / (float)p.B, wd = p.acc[ACC_W_SQ] + p.acc[ACC_W3_SQ];
+        if (p.terms) {
+            p.terms[0] = bce_cat; p.terms[1] = bce_motion; p.terms[2] = reg; p.terms[3] = gp; p.terms[4] = wd;
+            p.terms[5] = p.loss_scale * (0.5f * (bce_cat + bce_motion) + p.c_reg * reg + p.c_gp * gp + p.c_wd * wd);
+        }
+    }
+}
+
+__global__ void sumsq_kernel(const float *__restrict__ x, int n, float *__restrict__ out) {
+    float s = 0.0f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s = fmaf(x[i], x[i], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
+}
+
+template <bool A_MN, bool B_MN, int EPI>
+static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const GemmParams &p, cudaStream_t st) {
+    static bool configured = false;
+    auto kern = train_gemm_kernel<A_MN, B_MN, EPI>;
+    if (!configured) {
+        AMP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+        configured = true;
+    }
+    const int items = p.m_tiles * p.n_tiles * p.splits;
+    if (items <= 0) return AMP_OK;
+    const int grid = std::min(items, sm_count());
+    kern<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(ta, tb, p);
+    AMP_CUDA_TRY(cudaGetLastError());
+    return AMP_OK;
+}
+
+}  // namespace train
+}  // namespace amp
+
+struct amp_disc_train {
+    int in_features, Kp, h1, h2, device;
+    int64_t max_batch, Bp_max;
+    __nv_bfloat16 *X, *A1, *A2, *E1, *E2, *S;   // activations (row counts: 4Bp, 4Bp, 3Bp, 4Bp, 4Bp, Bp)
+    __nv_bfloat16 *W1b, *W1t, *W2b, *W2t;       // bf16 weights: (h1,Kp), (Kp,h1), (h2,h1), (h1,h2)
+    float *ws;                                  // fp32: [ACC_COUNT scalars | gw3 h2 | gb2 h2 | gb1 h1]
+    float *slices1, *slices2;                   // split-K slices of dW1 (splits1, h1, Kp) and dW2 (splits2, h2, h1)
+    float *mean_f, *denom_f, *ident_mean, *ident_denom;
+    int splits1, splits2;
+    int64_t staged_rows[3];                     // rows staged per source since the last step (-1: none)
+};
+
+using namespace amp;
+using namespace amp::train;
+
+extern "C" {
+
+int amp_disc_train_destroy(amp_disc_train_t *t) {
+    if (!t) return AMP_OK;
+    void *ptrs[] = {t->X, t->A1, t->A2, t->E1, t->E2, t->S, t->W1b, t->W1t, t->W2b, t->W2t, t->ws, t->slices1, t->slices2,
+                    t->mean_f, t->denom_f, t->ident_mean, t->ident_denom};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    delete t;
+    return AMP_OK;
+}
+
+int amp_disc_train_create(int32_t in_features, int32_t h1, int32_t h2, int64_t max_batch_rows, void *stream, amp_disc_train_t **out) {
+    AMP_REQUIRE(out, "amp_disc_train_create: NULL out");
+    *out = nullptr;
+    AMP_REQUIRE(in_features >= 1 && in_features <= 1024 && h1 >= BN && h2 >= BN && h1 % BN == 0 && h2 % BN == 0,
+                "amp_disc_train_create: hidden sizes must be multiples of %d (got %d, %d), 1 <= in_features <= 1024 (got %d)", BN, h1, h2,
+                in_features);
+    AMP_REQUIRE(max_batch_rows >= 1 && max_batch_rows <= (1 << 22), "amp_disc_train_create: max_batch_rows must be in [1, 4194304]");
+    int dev = 0, major = 0;
+    AMP_CUDA_TRY(cudaGetDevice(&dev));
+    AMP_CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major != 10) return fail(AMP_ENODEV, "amp_disc_train_create: tcgen05 kernels need an sm_100 device (found compute capability %d.x)", major);
+    amp_disc_train *t = new (std::nothrow) amp_disc_train();
+    if (!t) return fail(AMP_ENOMEM, "amp_disc_train_create: host allocation failed");
+    std::memset(t, 0, sizeof(*t));
+    t->device = dev;
+    t->in_features = in_features;
+    t->Kp = (in_features + BK - 1) / BK * BK;
+    t->h1 = h1;
+    t->h2 = h2;
+    t->max_batch = max_batch_rows;
+    t->Bp_max = (max_batch_rows + BM - 1) / BM * BM;
+    for (int i = 0; i < 3; ++i) t->staged_rows[i] = -1;
+    const int sms = sm_count();
+    // split-K so that the weight-gradient products fill the machine: items = splits x (M/128) x ceil(N/256) ~ one wave
+    const int tiles1 = (h1 / BM) * ((t->Kp + BN - 1) / BN), tiles2 = (h2 / BM) * (h1 / BN);
+    t->splits1 = std::max(1, std::min(16, sms / tiles1));
+    t->splits2 = std::max(1, std::min(16, sms / tiles2));
+    const size_t Bp = (size_t)t->Bp_max;
+    struct { void **p; size_t bytes; } allocs[] = {
+        {(void **)&t->X, 4 * Bp * t->Kp * 2},   {(void **)&t->A1, 4 * Bp * h1 * 2},     {(void **)&t->A2, 3 * Bp * h2 * 2},
+        {(void **)&t->E1, 4 * Bp * h1 * 2},     {(void **)&t->E2, 4 * Bp * h2 * 2},     {(void **)&t->S, Bp * h2 * 2},
+        {(void **)&t->W1b, (size_t)h1 * t->Kp * 2}, {(void **)&t->W1t, (size_t)t->Kp * h1 * 2},
+        {(void **)&t->W2b, (size_t)h2 * h1 * 2},    {(void **)&t->W2t, (size_t)h1 * h2 * 2},
+        {(void **)&t->ws, (size_t)(ACC_COUNT + 2 * h2 + h1) * 4},
+        {(void **)&t->slices1, (size_t)t->splits1 * h1 * t->Kp * 4}, {(void **)&t->slices2, (size_t)t->splits2 * h2 * h1 * 4},
+        {(void **)&t->mean_f, (size_t)in_features * 4}, {(void **)&t->denom_f, (size_t)in_features * 4},
+        {(void **)&t->ident_mean, (size_t)in_features * 4}, {(void **)&t->ident_denom, (size_t)in_features * 4},
+    };
+    cudaStream_t st = as_stream(stream);
+    for (auto &a : allocs) {
+        cudaError_t e = cudaMalloc(a.p, a.bytes);
+        if (e == cudaSuccess) e = cudaMemsetAsync(*a.p, 0, a.bytes, st);  // padding rows must hold finite values from the start
+        if (e != cudaSuccess) {
+            amp_disc_train_destroy(t);
+            return cuda_fail(e, "cudaMalloc(amp_disc_train_create)");
+        }
+    }
+    {  // identity scaler for already-normalised inputs: mean 0, denominator 1
+        std::vector<float> ones((size_t)in_features, 1.0f);
+        cudaError_t e = cudaMemcpyAsync(t->ident_denom, ones.data(), ones.size() * 4, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            amp_disc_train_destroy(t);
+            return cuda_fail(e, "amp_disc_train_create: identity scaler upload");
+        }
+    }
+    *out = t;
+    return AMP_OK;
+}
+
+int amp_disc_train_stage(amp_disc_train_t *t, int32_t source, const float *x, int64_t x_stride, int64_t rows, int64_t batch_rows,
+                         const double *running_mean, const double *running_variance, void *stream) {
+    AMP_REQUIRE(t && source >= 0 && source < 3, "amp_disc_train_stage: bad handle or source %d (0 agent, 1 replay, 2 motion)", source);
+    AMP_REQUIRE(batch_rows >= 1 && batch_rows <= t->max_batch, "amp_disc_train_stage: batch_rows %lld outside [1, %lld]",
+                (long long)batch_rows, (long long)t->max_batch);
+    AMP_REQUIRE(rows == batch_rows, "amp_disc_train_stage: rows (%lld) must equal batch_rows (%lld)", (long long)rows, (long long)batch_rows);
+    AMP_REQUIRE(x && x_stride >= t->in_features, "amp_disc_train_stage: NULL x or x_stride < in_features");
+    AMP_REQUIRE((running_mean == nullptr) == (running_variance == nullptr), "amp_disc_train_stage: give both scaler buffers or neither");
+    cudaStream_t st = as_stream(stream);
+    const int64_t Bp = (batch_rows + BM - 1) / BM * BM;
+    const float *mean = t->ident_mean, *denom = t->ident_denom;
+    if (running_mean) {
+        int rc = scaler_stats_to_f32(running_mean, running_variance, t->in_features, t->mean_f, t->denom_f, st);
+        if (rc != AMP_OK) return rc;
+        mean = t->mean_f;
+        denom = t->denom_f;
+    }
+    int rc = normalise_cast_rows(x, x_stride, rows, t->in_features, t->Kp, mean, denom, t->X + (size_t)source * Bp * t->Kp, st);
+    if (rc != AMP_OK) return rc;
+    t->staged_rows[source] = rows;
+    return AMP_OK;
+}
+
+int amp_disc_train_step(amp_disc_train_t *t, const float *W1, const float *b1, const float *W2, const float *b2, const float *W3,
+                        const float *b3, int64_t batch_rows, float loss_scale, float logit_regularization_scale,
+                        float gradient_penalty_scale, float weight_decay_scale, float *gW1, float *gb1, float *gW2, float *gb2,
+                        float *gW3, float *gb3, float *terms, float *logits, void *stream) {
+    AMP_REQUIRE(t && W1 && b1 && W2 && b2 && W3 && b3 && gW1 && gb1 && gW2 && gb2 && gW3 && gb3, "amp_disc_train_step: NULL argument");
+    AMP_REQUIRE(batch_rows >= 1 && batch_rows <= t->max_batch, "amp_disc_train_step: batch_rows %lld outside [1, %lld]",
+                (long long)batch_rows, (long long)t->max_batch);
+    for (int i = 0; i < 3; ++i)
+        AMP_REQUIRE(t->staged_rows[i] == batch_rows, "amp_disc_train_step: source %d has %lld staged rows, the step needs %lld", i,
+                    (long long)t->staged_rows[i], (long long)batch_rows);
+    cudaStream_t st = as_stream(stream);
+    const int B = (int)batch_rows;
+    const int Bp = (B + BM - 1) / BM * BM;
+    const int Kp = t->Kp, h1 = t->h1, h2 = t->h2;
+    float *acc = t->ws, *ws_gw3 = t->ws + ACC_COUNT, *ws_gb2 = ws_gw3 + h2, *ws_gb1 = ws_gb2 + h2;
+    AMP_CUDA_TRY(cudaMemsetAsync(t->ws, 0, (size_t)(ACC_COUNT + 2 * h2 + h1) * 4, st));
+
+    // ---- weights: bf16 copies (both orientations) + sums of squares ----
+    cast_transpose_kernel<<<dim3(Kp / 32, h1 / 32), 256, 0, st>>>(W1, h1, t->in_features, Kp, t->W1b, t->W1t, acc + ACC_W_SQ);
+    cast_transpose_kernel<<<dim3(h1 / 32, h2 / 32), 256, 0, st>>>(W2, h2, h1, h1, t->W2b, t->W2t, acc + ACC_W_SQ);
+    sumsq_kernel<<<1, 256, 0, st>>>(W3, h2, acc + ACC_W3_SQ);
+    AMP_CUDA_TRY(cudaGetLastError());
+
+    // ---- tensor maps (buffers are fixed; row counts depend on this step's batch) ----
+    CUtensorMap tX_k, tX_mn, tA1_k, tA1_mn, tE2_k, tE2_mn, tE1_k, tE1_mn, tW1b, tW1t, tW2b, tW2t;
+    int rc = AMP_OK;
+    auto mk = [&](CUtensorMap *m, const void *ptr, int64_t rows, int64_t cols, int box_rows, int box_cols) {
+        if (rc == AMP_OK) rc = make_tmap(m, ptr, rows, cols, cols, box_rows, box_cols);
+    };
+    mk(&tX_k, t->X, 4LL * Bp, Kp, BM, BK);
+    mk(&tX_mn, t->X, 4LL * Bp, Kp, BK, 64);
+    mk(&tA1_k, t->A1, 4LL * Bp, h1, BM, BK);
+    mk(&tA1_mn, t->A1, 4LL * Bp, h1, BK, 64);
+    mk(&tE2_k, t->E2, 4LL * Bp, h2, BM, BK);
+    mk(&tE2_mn, t->E2, 4LL * Bp, h2, BK, 64);
+    mk(&tE1_k, t->E1, 4LL * Bp, h1, BM, BK);
+    mk(&tE1_mn, t->E1, 4LL * Bp, h1, BK, 64);
+    mk(&tW1b, t->W1b, h1, Kp, BN, BK);
+    mk(&tW1t, t->W1t, Kp, h1, BN, BK);
+    mk(&tW2b, t->W2b, h2, h1, BN, BK);
+    mk(&tW2t, t->W2t, h1, h2, BN, BK);
+    if (rc != AMP_OK) return rc;
+    // row-block views: a TMA coordinate is relative to the map's base, so sub-ranges get their own maps
+    CUtensorMap tXgp_k, tA1gp_k, tE1gp_k;
+    mk(&tXgp_k, t->X + (size_t)3 * Bp * Kp, Bp, Kp, BM, BK);
+    mk(&tA1gp_k, t->A1 + (size_t)3 * Bp * h1, Bp, h1, BM, BK);
+    mk(&tE1gp_k, t->E1 + (size_t)3 * Bp * h1, Bp, h1, BM, BK);
+    if (rc != AMP_OK) return rc;
+
+    GemmParams g{};
+    // F1: A1[:3Bp] = relu(X[:3Bp] W1^T + b1)
+    g = GemmParams{};
+    g.m_tiles = 3 * Bp / BM; g.n_tiles = h1 / BN; g.splits = 1; g.kblocks = Kp / BK; g.n_valid = h1;
+    g.bias = b1; g.out = t->A1; g.out_ld = h1;
+    if ((rc = launch_gemm<false, false, EPI_BIAS_RELU>(tX_k, tW1b, g, st)) != AMP_OK) return rc;
+    // F2: A2 = relu(A1[:3Bp] W2^T + b2)
+    g = GemmParams{};
+    g.m_tiles = 3 * Bp / BM; g.n_tiles = h2 / BN; g.splits = 1; g.kblocks = h1 / BK; g.n_valid = h2;
+    g.bias = b2; g.out = t->A2; g.out_ld = h2;
+    if ((rc = launch_gemm<false, false, EPI_BIAS_RELU>(tA1_k, tW2b, g, st)) != AMP_OK) return rc;
+    // head: logits, BCE, dd, E2 (dz2 | u2), dL/db2, dL/dw3 (first part), dL/db3
+    head_kernel<<<3 * Bp / 32, 256, 0, st>>>(t->A2, h2, Bp, B, W3, b3, loss_scale, t->E2, acc, ws_gw3, ws_gb2, logits);
+    AMP_CUDA_TRY(cudaGetLastError());
+    // B1: E1 = (E2 W2) * m1 -- rows < 3Bp use a1 of the same row, rows >= 3Bp (u2 -> v1) the a1 of the motion block
+    g = GemmParams{};
+    g.m_tiles = 4 * Bp / BM; g.n_tiles = h1 / BN; g.splits = 1; g.kblocks = h2 / BK; g.n_valid = h1;
+    g.out = t->E1; g.out_ld = h1; g.mask = t->A1; g.mask_ld = h1; g.mask_split = 3 * Bp; g.mask_shift = Bp; g.alpha = 1.0f;
+    if ((rc = launch_gemm<false, false, EPI_MASK>(tE2_k, tW2t, g, st)) != AMP_OK) return rc;
+    // GP2: g = v1 W1 (motion rows); X[3Bp:] = G = (2 s c_gp / B) g; sum g^2
+    g = GemmParams{};
+    g.m_tiles = Bp / BM; g.n_tiles = (Kp + BN - 1) / BN; g.splits = 1; g.kblocks = h1 / BK; g.n_valid = Kp;
+    g.out = t->X + (size_t)3 * Bp * Kp; g.out_ld = Kp; g.alpha = 2.0f * loss_scale * gradient_penalty_scale / (float)B;
+    g.sumsq = acc + ACC_GP_SQ;
+    if ((rc = launch_gemm<false, false, EPI_SCALE_SUMSQ>(tE1gp_k, tW1t, g, st)) != AMP_OK) return rc;
+    // GP3: A1[3Bp:] = q1 = (G W1^T) * m1(motion)
+    g = GemmParams{};
+    g.m_tiles = Bp / BM; g.n_tiles = h1 / BN; g.splits = 1; g.kblocks = Kp / BK; g.n_valid = h1;
+    g.out = t->A1 + (size_t)3 * Bp * h1; g.out_ld = h1; g.mask = t->A1 + (size_t)2 * Bp * h1; g.mask_ld = h1;
+    g.mask_split = 1 << 30; g.mask_shift = 0; g.alpha = 1.0f;
+    if ((rc = launch_gemm<false, false, EPI_MASK>(tXgp_k, tW1b, g, st)) != AMP_OK) return rc;
+    // GP6: S = (q1 W2^T) * m2(motion)
+    g = GemmParams{};
+    g.m_tiles = Bp / BM; g.n_tiles = h2 / BN; g.splits = 1; g.kblocks = h1 / BK; g.n_valid = h2;
+    g.out = t->S; g.out_ld = h2; g.mask = t->A2 + (size_t)2 * Bp * h2; g.mask_ld = h2; g.mask_split = 1 << 30; g.mask_shift = 0;
+    g.alpha = 1.0f;
+    if ((rc = launch_gemm<false, false, EPI_MASK>(tA1gp_k, tW2b, g, st)) != AMP_OK) return rc;
+    // dW2 slices = E2^T A1 over all 4Bp rows (K = rows: both operands MN-major)
+    g = GemmParams{};
+    g.m_tiles = h2 / BM; g.n_tiles = h1 / BN; g.splits = std::min(t->splits2, 4 * Bp / BK); g.kblocks = 4 * Bp / BK; g.n_valid = h1;
+    g.slices = t->slices2; g.slice_ld = h1; g.slice_stride = (long long)h2 * h1;
+    const int used2 = g.splits;
+    if ((rc = launch_gemm<true, true, EPI_SLICE>(tE2_mn, tA1_mn, g, st)) != AMP_OK) return rc;
+    // dW1 slices = E1^T X
+    g = GemmParams{};
+    g.m_tiles = h1 / BM; g.n_tiles = (Kp + BN - 1) / BN; g.splits = std::min(t->splits1, 4 * Bp / BK); g.kblocks = 4 * Bp / BK; g.n_valid = Kp;
+    g.slices = t->slices1; g.slice_ld = Kp; g.slice_stride = (long long)h1 * Kp;
+    const int used1 = g.splits;
+    if ((rc = launch_gemm<true, true, EPI_SLICE>(tE1_mn, tX_mn, g, st)) != AMP_OK) return rc;
+    // bias gradient of layer 1 and the gradient-penalty part of dL/dw3
+    colsum_kernel<<<dim3((h1 + 511) / 512, (3 * Bp + 63) / 64), 256, 0, st>>>(t->E1, h1, 3 * Bp, h1, ws_gb1);
+    colsum_kernel<<<dim3((h2 + 511) / 512, (Bp + 63) / 64), 256, 0, st>>>(t->S, h2, Bp, h2, ws_gw3);
+    AMP_CUDA_TRY(cudaGetLastError());
+
+    FinalizeParams f{};
+    f.W1 = W1; f.W2 = W2; f.w3 = W3; f.slices1 = t->slices1; f.slices2 = t->slices2; f.splits1 = used1; f.splits2 = used2;
+    f.in_features = t->in_features; f.Kp = Kp; f.h1 = h1; f.h2 = h2; f.B = B; f.acc = acc; f.ws_gw3 = ws_gw3; f.ws_gb2 = ws_gb2;
+    f.ws_gb1 = ws_gb1; f.loss_scale = loss_scale; f.c_reg = logit_regularization_scale; f.c_gp = gradient_penalty_scale;
+    f.c_wd = weight_decay_scale; f.gW1 = gW1; f.gb1 = gb1; f.gW2 = gW2; f.gb2 = gb2; f.gW3 = gW3; f.gb3 = gb3; f.terms = terms;
+    finalize_kernel<<<sm_count() * 4, 256, 0, st>>>(f);
+    AMP_CUDA_TRY(cudaGetLastError());
+    for (int i = 0; i < 3; ++i) t->staged_rows[i] = -1;
+    return AMP_OK;
+}
+
+}  // extern "C"

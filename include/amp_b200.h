@@ -44,6 +44,7 @@ enum {
 
 typedef struct amp_lib amp_lib_t;   /* a motion library staged on one device */
 typedef struct amp_disc amp_disc_t; /* discriminator weights staged for the tensor-core kernel */
+typedef struct amp_disc_train amp_disc_train_t; /* workspaces of the discriminator loss + gradient step */
 
 /* Description of a loaded motion library: what the reference MotionLoader.__init__ leaves behind
  * (motions/motion_loader.py:98-164) plus the env's index lists (g1_amp_env.py:40-60). */
@@ -211,6 +212,33 @@ AMP_API int amp_disc_style_reward_indexed(amp_disc_t *d, const float *memory, in
                                           uint32_t *flags, void *stream);
 /* Standalone epilogue (logits -> reward) for callers that own the discriminator forward. */
 AMP_API int amp_style_reward_from_logits(const float *logits, int64_t M, float reward_scale, float *reward, void *stream);
+
+/* ---- discriminator loss + gradients (skrl AMP._update "compute discriminator loss" block and its backward
+ *      pass; cfg agents/skrl_g1_dance_amp_cfg.yaml:89, 94, 96-98) ------------------------------------------------------- */
+/* Workspaces for batches of up to max_batch_rows rows PER SOURCE (skrl: discriminator_batch_size, or the mini-batch length
+ * when that is 0).  Same network shape constraints as amp_disc_create; in_features <= 1024. */
+AMP_API int amp_disc_train_create(int32_t in_features, int32_t h1, int32_t h2, int64_t max_batch_rows, void *stream,
+                                  amp_disc_train_t **out);
+AMP_API int amp_disc_train_destroy(amp_disc_train_t *t);
+/* Stage one of the three batches of the step: source 0 = agent AMP states (rollout memory), 1 = replay buffer, 2 = motion
+ * dataset.  x device f32 (rows, in_features), row stride x_stride floats; rows must equal batch_rows.
+ * running_mean / running_variance: the amp_state_preprocessor's float64 buffers AFTER its train-mode update for this batch
+ * (skrl calls the preprocessor with train=True on each batch in turn; use amp_scaler_update for that) -- the rows are
+ * normalised, clipped to +-5 and rounded to bf16; both NULL = x is already normalised. */
+AMP_API int amp_disc_train_stage(amp_disc_train_t *t, int32_t source, const float *x, int64_t x_stride, int64_t rows,
+                                 int64_t batch_rows, const double *running_mean, const double *running_variance, void *stream);
+/* Loss and gradients of  loss_scale * (0.5 (BCE(cat(agent, replay), 0) + BCE(motion, 1)) + logit_reg * |W3|^2
+ *                                      + grad_penalty * mean_rows |d logit / d motion_state|^2 + weight_decay * sum |W|^2)
+ * for the three staged batches.  W1 (h1,in) b1 W2 (h2,h1) b2 W3 (1,h2) b3: fp32 masters, device, torch.nn.Linear layout.
+ * gW1 .. gb3: device f32, same shapes, OVERWRITTEN with d loss / d parameter (they may point into the trainer's flat
+ * all-reduce bucket).  terms: device f32[6] or NULL = {bce_agent_replay, bce_motion, logit_regularization (sum W3^2),
+ * gradient_penalty, weight_decay (sum of all W^2), loss}.  logits: device f32[3 * Bp] or NULL, Bp = batch_rows rounded up to
+ * 128; the logit of row r of source s is logits[s * Bp + r].  bf16 tensor-core operands, fp32 accumulation. */
+AMP_API int amp_disc_train_step(amp_disc_train_t *t, const float *W1, const float *b1, const float *W2, const float *b2,
+                                const float *W3, const float *b3, int64_t batch_rows, float loss_scale,
+                                float logit_regularization_scale, float gradient_penalty_scale, float weight_decay_scale,
+                                float *gW1, float *gb1, float *gW2, float *gb2, float *gW3, float *gb3, float *terms,
+                                float *logits, void *stream);
 
 #ifdef __cplusplus
 }
