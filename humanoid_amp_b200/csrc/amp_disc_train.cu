@@ -41,7 +41,6 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
-#include <vector>
 
 #include "amp_internal.h"
 #include "amp_tc.cuh"
@@ -61,7 +60,8 @@ constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KiB
 constexpr int MN_BOX_BYTES = BK * 64 * 2;   // one MN-major TMA box: 64 K-rows x 64 columns (128-byte swizzled rows) = 8 KiB
 constexpr int GEMM_THREADS = 320;
 constexpr int TMEM_COLS = 512;
-constexpr int GEMM_SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 + 1024;
+constexpr int SLAB_BYTES = 32 * 64 * 2;     // per epilogue warp: 32 rows x 64 bf16 columns, staged for coalesced stores
+constexpr int GEMM_SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 8 * SLAB_BYTES + 256 + 1024;
 
 enum Epilogue { EPI_BIAS_RELU = 0, EPI_MASK = 1, EPI_SCALE_SUMSQ = 2, EPI_SLICE = 3 };
 
@@ -81,8 +81,10 @@ __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr) 
 
 struct GemmParams {
     int m_tiles, n_tiles, splits, kblocks;  // work items = splits x m_tiles x n_tiles; kblocks = K / 64 over all splits
-    int n_valid;                            // output columns >= n_valid do not exist (multiple of 32)
+    int n_valid;                            // output columns >= n_valid do not exist (multiple of 64)
     const float *bias;                      // EPI_BIAS_RELU
+    const float *dot_w;                     // EPI_BIAS_RELU, optional: dot_out[row] += sum_col relu(acc + bias)[col] * dot_w[col]
+    float *dot_out;                         //   (fp32 atomics, one per epilogue warp-row and tile; the last layer of the MLP)
     __nv_bfloat16 *out;                     // bf16 output (all but EPI_SLICE)
     long long out_ld;
     const __nv_bfloat16 *mask;              // EPI_MASK: out = mask[mrow, col] != 0 ? alpha * acc : 0
@@ -112,7 +114,8 @@ train_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t smem_a = base;
     const uint32_t smem_b = base + STAGES * A_STAGE_BYTES;
-    const uint32_t bars = smem_b + STAGES * B_STAGE_BYTES;
+    const uint32_t slabs = smem_b + STAGES * B_STAGE_BYTES;
+    const uint32_t bars = slabs + 8 * SLAB_BYTES;
     const uint32_t full_bar = bars, empty_bar = bars + 8 * STAGES;
     const uint32_t acc_full = bars + 16 * STAGES, acc_empty = acc_full + 16;
     const uint32_t tmem_slot = acc_full + 32;
@@ -217,32 +220,47 @@ train_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const int quarter = warp & 3;
         const int colhalf = (warp - 2) >> 2;
         const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+        [[maybe_unused]] const uint32_t slab = slabs + (uint32_t)((warp - 2) * SLAB_BYTES);
         uint32_t it = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
             const int s = item / tiles, t = item - s * tiles;
             const int m = t / p.n_tiles, n = t - m * p.n_tiles;
             const uint32_t r = it & 1, use = it >> 1;
-            const long long row = (long long)m * BM + quarter * 32 + lane;
+            [[maybe_unused]] const long long row = (long long)m * BM + quarter * 32 + lane;
             const int col0 = n * BN + colhalf * (BN / 2);
             const uint32_t acc = tmem_base + lane_base + r * BN + (uint32_t)(colhalf * (BN / 2));
+            const int chunks = min(4, max(0, (p.n_valid - col0 + 31) / 32));  // warp-uniform; n_valid % 64 == 0: 0, 2 or 4
+            // bf16 epilogues go through a per-warp shared-memory slab (32 rows x 64 columns, 16-byte pieces XOR-swizzled by
+            // row): the TMEM read-out gives a thread one ROW, but global memory wants 8 lanes on the 128 contiguous bytes of a
+            // row.  In the second pass lane l handles 16-byte piece (l & 7) of rows (l >> 3) + 4 i: every row segment is
+            // one full 128-byte line (4 lines per instruction instead of 32).  (Direct stores from the row-per-thread layout:
+            // the B1 launch spent 8 us per tile in this epilogue against 2 us of MMAs.)
+            // EPI_MASK: the mask (activations of an earlier launch) does not depend on this accumulator -- fetch it in the
+            // second-pass layout before waiting for the MMAs, so the global-memory latency hides under them.
+            const long long row_base = (long long)m * BM + quarter * 32;
+            const int sub_row = lane >> 3, piece = lane & 7;
+            [[maybe_unused]] uint4 mk[2][8];
+            if constexpr (EPI == EPI_MASK) {
+                const long long mbase = row_base < p.mask_split ? row_base : row_base - p.mask_shift;  // tile-uniform side
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    if (2 * g >= chunks) break;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        mk[g][i] = __ldg(reinterpret_cast<const uint4 *>(p.mask + (mbase + sub_row + 4 * i) * p.mask_ld + col0 + g * 64) + piece);
+                }
+            }
             mbar_wait(acc_full + 8 * r, use & 1);
             tcgen05_fence_after();
             [[maybe_unused]] float ss = 0.0f;
-            [[maybe_unused]] long long mrow = 0;
-            if constexpr (EPI == EPI_MASK) mrow = row < p.mask_split ? row : row - p.mask_shift;
-            const int chunks = min(4, max(0, (p.n_valid - col0 + 31) / 32));  // warp-uniform
+            [[maybe_unused]] float dot = 0.0f;
+            [[maybe_unused]] const bool with_dot = EPI == EPI_BIAS_RELU && p.dot_w != nullptr;  // launch-uniform
             uint32_t v[2][32];
             if (chunks > 0) tmem_ld_32x32(acc, v[0]);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 if (c >= chunks) break;
                 const int col = col0 + c * 32;
-                [[maybe_unused]] uint4 mk[4];
-                if constexpr (EPI == EPI_MASK) {
-                    const uint4 *mp = reinterpret_cast<const uint4 *>(p.mask + mrow * p.mask_ld + col);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) mk[j] = __ldg(mp + j);
-                }
                 tmem_ld_wait();
                 if (c + 1 < chunks) tmem_ld_32x32(acc + (uint32_t)((c + 1) * 32), v[(c + 1) & 1]);
                 const uint32_t(&cur)[32] = v[c & 1];
@@ -259,29 +277,53 @@ train_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const float4 b = __ldg(bias4 + j);
-                            o[2 * j] = pack_bf16(fmaxf(__uint_as_float(cur[4 * j]) + b.x, 0.0f), fmaxf(__uint_as_float(cur[4 * j + 1]) + b.y, 0.0f));
-                            o[2 * j + 1] = pack_bf16(fmaxf(__uint_as_float(cur[4 * j + 2]) + b.z, 0.0f), fmaxf(__uint_as_float(cur[4 * j + 3]) + b.w, 0.0f));
+                            const float h0 = fmaxf(__uint_as_float(cur[4 * j]) + b.x, 0.0f), h1 = fmaxf(__uint_as_float(cur[4 * j + 1]) + b.y, 0.0f);
+                            const float h2 = fmaxf(__uint_as_float(cur[4 * j + 2]) + b.z, 0.0f), h3 = fmaxf(__uint_as_float(cur[4 * j + 3]) + b.w, 0.0f);
+                            o[2 * j] = pack_bf16(h0, h1);
+                            o[2 * j + 1] = pack_bf16(h2, h3);
+                            if (with_dot) {
+                                const float4 w = __ldg(reinterpret_cast<const float4 *>(p.dot_w + col) + j);
+                                dot = fmaf(h0, w.x, dot); dot = fmaf(h1, w.y, dot); dot = fmaf(h2, w.z, dot); dot = fmaf(h3, w.w, dot);
+                            }
                         }
-                    } else if constexpr (EPI == EPI_MASK) {
-                        const uint32_t *mw = reinterpret_cast<const uint32_t *>(mk);
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const float a = (mw[j] & 0xffffu) ? __uint_as_float(cur[2 * j]) * p.alpha : 0.0f;
-                            const float b = (mw[j] >> 16) ? __uint_as_float(cur[2 * j + 1]) * p.alpha : 0.0f;
-                            o[j] = pack_bf16(a, b);
-                        }
-                    } else {  // EPI_SCALE_SUMSQ
+                    } else {  // EPI_MASK (mask applied in the second pass), EPI_SCALE_SUMSQ
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             const float a = __uint_as_float(cur[2 * j]), b = __uint_as_float(cur[2 * j + 1]);
-                            ss = fmaf(a, a, ss);
-                            ss = fmaf(b, b, ss);
+                            if constexpr (EPI == EPI_SCALE_SUMSQ) {
+                                ss = fmaf(a, a, ss);
+                                ss = fmaf(b, b, ss);
+                            }
                             o[j] = pack_bf16(a * p.alpha, b * p.alpha);
                         }
                     }
-                    uint4 *dst = reinterpret_cast<uint4 *>(p.out + row * p.out_ld + col);
+                    // first pass: this thread's 32 columns = pieces (c & 1) * 4 + j of its row in the slab
+                    const uint32_t my_row = slab + (uint32_t)(lane * 128);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) dst[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                    for (int j = 0; j < 4; ++j)
+                        st_shared_v4(my_row + (uint32_t)((((c & 1) * 4 + j) ^ (lane & 7)) * 16), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                    if (c & 1) {  // the 64-column group is complete: second pass
+                        __syncwarp();
+                        const int g = c >> 1;
+                        __nv_bfloat16 *dst = p.out + (row_base + sub_row) * p.out_ld + col0 + g * 64 + piece * 8;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int rr = sub_row + 4 * i;
+                            uint4 q;
+                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                         : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w)
+                                         : "r"(slab + (uint32_t)(rr * 128 + ((piece ^ (rr & 7)) * 16))));
+                            if constexpr (EPI == EPI_MASK) {
+                                const uint4 mm = mk[g][i];
+                                q.x &= ((mm.x & 0xffffu) ? 0xffffu : 0u) | ((mm.x >> 16) ? 0xffff0000u : 0u);
+                                q.y &= ((mm.y & 0xffffu) ? 0xffffu : 0u) | ((mm.y >> 16) ? 0xffff0000u : 0u);
+                                q.z &= ((mm.z & 0xffffu) ? 0xffffu : 0u) | ((mm.z >> 16) ? 0xffff0000u : 0u);
+                                q.w &= ((mm.w & 0xffffu) ? 0xffffu : 0u) | ((mm.w >> 16) ? 0xffff0000u : 0u);
+                            }
+                            *reinterpret_cast<uint4 *>(dst + (long long)(4 * i) * p.out_ld) = q;
+                        }
+                        __syncwarp();  // the slab is rewritten by the next group
+                    }
                 }
             }
             // all TMEM reads of this accumulator by this warp have completed (tcgen05.wait::ld above): release the region
@@ -292,6 +334,9 @@ train_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
                 if (lane == 0 && chunks > 0) atomicAdd(p.sumsq, ss);
+            }
+            if constexpr (EPI == EPI_BIAS_RELU) {
+                if (with_dot && chunks > 0) atomicAdd(p.dot_out + row, dot);
             }
         }
     }
@@ -339,53 +384,59 @@ __global__ void __launch_bounds__(256) cast_transpose_kernel(const float *__rest
     }
 }
 
+// Column sums arrive by fp32 atomics from a few hundred CTAs at once; same-address atomics serialise in L2, so each sum has
+// REPL copies (CTA b adds into copy b % REPL) that finalize_kernel folds.
+constexpr int REPL = 8;
+
 // scalar accumulators at the head of the fp32 workspace (zeroed at the start of every step)
 enum Acc { ACC_BCE_CAT = 0, ACC_BCE_MOTION, ACC_W3_SQ, ACC_GP_SQ, ACC_W_SQ, ACC_GB3, ACC_COUNT = 8 };
 
 __device__ __forceinline__ float softplus_f(float x) { return fmaxf(x, 0.0f) + log1pf(__expf(-fabsf(x))); }
 
 // After the second layer: logits, BCE terms, dL/dd, and everything that hangs off it row by row.
-//   rows_per_block = 32; phase A: one warp per row -> d = a2 . w3 + b3 and dd; phase B: one thread per column pair walks the
-//   32 rows: E2[row] = dd * w3 * m2 (and, for motion rows, E2[row + Bp] = w3 * m2), column sums dL/db2 and sum dd * a2.
-__global__ void __launch_bounds__(256) head_kernel(const __nv_bfloat16 *__restrict__ a2, int h2, int Bp, int B,
-                                                   const float *__restrict__ w3, const float *__restrict__ b3, float loss_scale,
+//   A block takes 32 rows: the a2 tile (32 x h2 bf16) is read ONCE into shared memory; phase A: one lane per row ->
+//   d = dotsum + b3 (dotsum = a2 . w3 from the layer-2 epilogue) and dd; phase B: one thread per column pair walks the 32 rows: E2[row] = dd * w3 * m2 (and, for motion
+//   rows, E2[row + Bp] = w3 * m2), column sums dL/db2 and sum dd * a2.  Dynamic shared memory: 32 * h2 * 2 bytes.
+__global__ void __launch_bounds__(256) head_kernel(const __nv_bfloat16 *__restrict__ a2, const float *__restrict__ dotsum, int h2,
+                                                   int Bp, int B, const float *__restrict__ w3, const float *__restrict__ b3, float loss_scale,
                                                    __nv_bfloat16 *__restrict__ e2, float *__restrict__ acc, float *__restrict__ gw3,
                                                    float *__restrict__ gb2, float *__restrict__ logits) {
+    extern __shared__ __align__(16) unsigned char head_smem[];
+    __nv_bfloat16 *tile = reinterpret_cast<__nv_bfloat16 *>(head_smem);
     __shared__ float s_dd[32];
     __shared__ float s_loss[32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long row0 = (long long)blockIdx.x * 32;
     const int block_src = (int)(row0 / Bp);  // 32 | Bp: a block never straddles two sources
-    for (int rl = warp; rl < 32; rl += 8) {
-        const long long row = row0 + rl;
-        const __nv_bfloat16 *ar = a2 + row * h2;
-        float dot = 0.0f;
-        for (int c = lane * 8; c < h2; c += 256) {
-            const uint4 q = __ldg(reinterpret_cast<const uint4 *>(ar + c));
-            const float4 wa = __ldg(reinterpret_cast<const float4 *>(w3 + c)), wb = __ldg(reinterpret_cast<const float4 *>(w3 + c + 4));
-            const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&q);
-            const float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]), f2 = __bfloat1622float2(h[2]), f3 = __bfloat1622float2(h[3]);
-            dot = fmaf(f0.x, wa.x, dot); dot = fmaf(f0.y, wa.y, dot); dot = fmaf(f1.x, wa.z, dot); dot = fmaf(f1.y, wa.w, dot);
-            dot = fmaf(f2.x, wb.x, dot); dot = fmaf(f2.y, wb.y, dot); dot = fmaf(f3.x, wb.z, dot); dot = fmaf(f3.y, wb.w, dot);
-        }
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(a2 + row0 * h2);
+        uint4 *dst = reinterpret_cast<uint4 *>(tile);
+        const int quads = 32 * h2 / 8;  // h2 % 256 == 0: a multiple of 4 * 256
+        for (int i = threadIdx.x; i < quads; i += 4 * 256) {  // four loads in flight per thread
+            uint4 q[4];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-        if (lane == 0) {
-            const bool valid = (int)(row - (long long)block_src * Bp) < B;
-            const float d = dot + __ldg(b3);
-            if (logits) logits[row] = d;
-            const float sig = 1.0f / (1.0f + __expf(-d));
-            float dd, loss;
-            if (block_src < 2) {  // agent / replay: target 0, mean over 2B rows
-                dd = 0.5f * loss_scale * sig / (2.0f * (float)B);
-                loss = softplus_f(d);
-            } else {              // motion: target 1, mean over B rows
-                dd = 0.5f * loss_scale * (sig - 1.0f) / (float)B;
-                loss = softplus_f(-d);
-            }
-            s_dd[rl] = valid ? dd : 0.0f;
-            s_loss[rl] = valid ? loss : 0.0f;
+            for (int u = 0; u < 4; ++u) q[u] = __ldg(src + i + u * 256);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) dst[i + u * 256] = q[u];
         }
+    }
+    __syncthreads();
+    if (warp == 0) {  // the logits were accumulated (fp32, before the bf16 rounding of a2) by the epilogue of the layer-2 GEMM
+        const long long row = row0 + lane;
+        const bool valid = (int)(row - (long long)block_src * Bp) < B;
+        const float d = dotsum[row] + __ldg(b3);
+        if (logits) logits[row] = d;
+        const float sig = 1.0f / (1.0f + __expf(-d));
+        float dd, loss;
+        if (block_src < 2) {  // agent / replay: target 0, mean over 2B rows
+            dd = 0.5f * loss_scale * sig / (2.0f * (float)B);
+            loss = softplus_f(d);
+        } else {              // motion: target 1, mean over B rows
+            dd = 0.5f * loss_scale * (sig - 1.0f) / (float)B;
+            loss = softplus_f(-d);
+        }
+        s_dd[lane] = valid ? dd : 0.0f;
+        s_loss[lane] = valid ? loss : 0.0f;
     }
     __syncthreads();
     if (warp == 0) {
@@ -401,14 +452,16 @@ __global__ void __launch_bounds__(256) head_kernel(const __nv_bfloat16 *__restri
         }
     }
     const bool motion = block_src == 2;
+    gb2 += (blockIdx.x % REPL) * h2;
+    gw3 += (blockIdx.x % REPL) * h2;
     for (int c = threadIdx.x * 2; c < h2; c += 512) {
         const float2 w = __ldg(reinterpret_cast<const float2 *>(w3 + c));
         float sb0 = 0.0f, sb1 = 0.0f, sw0 = 0.0f, sw1 = 0.0f;
-#pragma unroll 4
+#pragma unroll 8
         for (int rl = 0; rl < 32; ++rl) {
             const long long row = row0 + rl;
             const float dd = s_dd[rl];
-            const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(a2 + row * h2 + c));
+            const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(tile + rl * h2 + c));
             const float m0 = a.x > 0.0f ? 1.0f : 0.0f, m1 = a.y > 0.0f ? 1.0f : 0.0f;
             const float z0 = dd * w.x * m0, z1 = dd * w.y * m1;
             sb0 += z0; sb1 += z1;
@@ -424,18 +477,65 @@ __global__ void __launch_bounds__(256) head_kernel(const __nv_bfloat16 *__restri
     }
 }
 
-// out[c] += sum over rows of src[r, c] (bf16 -> fp32): a block takes 64 rows x 512 columns, one thread per column pair
+// Staging of one source: RunningStandardScaler (eval form, skrl) + bf16 cast, one thread per output column pair -- the
+// batches of a discriminator update are a few thousand rows, so the row-per-warp kernel of the style-reward path (built for
+// 1 M rows, statistics cached in registers) would be one long latency chain here.  Same arithmetic as that kernel:
+// clamp((x - (float)mean) * rcp(sqrt((float)var) + 1e-8), -5, 5).  mean == NULL: x is already normalised.
+// Column `in_features` (when Kp > in_features) is set to 1: with that "ones" column the product E1^T X delivers the bias
+// gradient dL/db1 = colsum(E1) as column in_features of dL/dW1 (W1's own padding columns are zero, so nothing else sees it).
+constexpr int STAGE_ROWS = 32;  // rows per CTA of stage_cast_kernel
+__global__ void __launch_bounds__(256) stage_cast_kernel(const float *__restrict__ x, long long x_stride, int rows, int in_features,
+                                                         int Kp, const double *__restrict__ mean, const double *__restrict__ var,
+                                                         __nv_bfloat16 *__restrict__ out) {
+    // blockIdx.x: strip of 512 columns (one column pair per thread); blockIdx.y: strip of STAGE_ROWS rows.  The float64
+    // statistics of the thread's two columns are narrowed ONCE (fp64 conversions run at a small fraction of the fp32 rate:
+    // converting per element made this kernel 4x slower than its memory traffic).
+    const int c = blockIdx.x * 512 + threadIdx.x * 2;
+    if (c >= Kp) return;
+    float mu[2], rc[2];
+    bool live[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int cc = c + j;
+        live[j] = cc < in_features;
+        mu[j] = live[j] && mean ? __double2float_rn(__ldg(mean + cc)) : 0.0f;
+        rc[j] = live[j] ? __frcp_rn(var ? __fadd_rn(__fsqrt_rn(__double2float_rn(__ldg(var + cc))), 1e-8f) : 1.0f) : 0.0f;
+    }
+    const float pad0 = c == in_features ? 1.0f : 0.0f, pad1 = c + 1 == in_features ? 1.0f : 0.0f;
+    const int r0 = blockIdx.y * STAGE_ROWS, r1 = min(rows, r0 + STAGE_ROWS);
+    // eight rows of loads are issued before the first is consumed (the ld.global.cs intrinsics keep program order)
+    for (int rb = r0; rb < r1; rb += 8) {
+        float x0[8], x1[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float *xr = x + (long long)min(rb + u, r1 - 1) * x_stride + c;
+            x0[u] = live[0] ? __ldcs(xr) : 0.0f;
+            x1[u] = live[1] ? __ldcs(xr + 1) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (rb + u >= r1) break;
+            const float v0 = live[0] ? fminf(fmaxf(__fmul_rn(__fsub_rn(x0[u], mu[0]), rc[0]), -5.0f), 5.0f) : pad0;
+            const float v1 = live[1] ? fminf(fmaxf(__fmul_rn(__fsub_rn(x1[u], mu[1]), rc[1]), -5.0f), 5.0f) : pad1;
+            *reinterpret_cast<uint32_t *>(out + (long long)(rb + u) * Kp + c) = pack_bf16(v0, v1);
+        }
+    }
+}
+
+// out[b % REPL][c] += sum over rows of src[r, c] (bf16 -> fp32): block b takes 16 rows x 512 columns, one thread per column pair
+constexpr int COLSUM_ROWS = 16;
 __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16 *__restrict__ src, long long ld, int rows, int cols,
                                                      float *__restrict__ out) {
     const int c = blockIdx.x * 512 + threadIdx.x * 2;
     if (c >= cols) return;
-    const int r0 = blockIdx.y * 64, r1 = min(rows, r0 + 64);
+    const int r0 = blockIdx.y * COLSUM_ROWS, r1 = min(rows, r0 + COLSUM_ROWS);
     float s0 = 0.0f, s1 = 0.0f;
-#pragma unroll 8
+#pragma unroll 16
     for (int r = r0; r < r1; ++r) {
         const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(src + (long long)r * ld + c));
         s0 += a.x; s1 += a.y;
     }
+    out += (blockIdx.y % REPL) * (long long)cols;
     atomicAdd(out + c, s0);
     atomicAdd(out + c + 1, s1);
 }
@@ -457,22 +557,57 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinalizeParams p) {
     const float cw = 2.0f * p.loss_scale * p.c_wd;
     const long long stride = (long long)gridDim.x * blockDim.x, tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long s1 = (long long)p.h1 * p.Kp, s2 = n2;
-    for (long long e = tid; e < n1; e += stride) {
-        const int r = (int)(e / p.in_features), c = (int)(e - (long long)r * p.in_features);
-        float g = 0.0f;
-        for (int s = 0; s < p.splits1; ++s) g += p.slices1[s * s1 + (long long)r * p.Kp + c];
-        p.gW1[e] = fmaf(cw, p.W1[e], g);
+    if ((p.in_features & 1) == 0) {  // rows of gW1 / W1 are 8-byte aligned: two columns per thread
+        const int half = p.in_features / 2;
+        for (long long e = tid; e < n1 / 2; e += stride) {
+            const int r = (int)(e / half), c = 2 * (int)(e - (long long)r * half);
+            float2 g = make_float2(0.0f, 0.0f);
+            for (int s = 0; s < p.splits1; ++s) {
+                const float2 v = *reinterpret_cast<const float2 *>(p.slices1 + s * s1 + (long long)r * p.Kp + c);
+                g.x += v.x; g.y += v.y;
+            }
+            const float2 w = *reinterpret_cast<const float2 *>(p.W1 + 2 * e);
+            *reinterpret_cast<float2 *>(p.gW1 + 2 * e) = make_float2(fmaf(cw, w.x, g.x), fmaf(cw, w.y, g.y));
+        }
+    } else {
+        for (long long e = tid; e < n1; e += stride) {
+            const int r = (int)(e / p.in_features), c = (int)(e - (long long)r * p.in_features);
+            float g = 0.0f;
+            for (int s = 0; s < p.splits1; ++s) g += p.slices1[s * s1 + (long long)r * p.Kp + c];
+            p.gW1[e] = fmaf(cw, p.W1[e], g);
+        }
     }
-    for (long long e = tid; e < n2; e += stride) {
-        float g = 0.0f;
-        for (int s = 0; s < p.splits2; ++s) g += p.slices2[s * s2 + e];
-        p.gW2[e] = fmaf(cw, p.W2[e], g);
+    for (long long e = tid; e < n2 / 4; e += stride) {  // h1 % 256 == 0: every row of W2 is 16-byte aligned
+        float4 g = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        for (int s = 0; s < p.splits2; ++s) {
+            const float4 v = *reinterpret_cast<const float4 *>(p.slices2 + s * s2 + 4 * e);
+            g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+        }
+        const float4 w = *reinterpret_cast<const float4 *>(p.W2 + 4 * e);
+        *reinterpret_cast<float4 *>(p.gW2 + 4 * e) = make_float4(fmaf(cw, w.x, g.x), fmaf(cw, w.y, g.y), fmaf(cw, w.z, g.z), fmaf(cw, w.w, g.w));
     }
     for (long long e = tid; e < p.h2; e += stride) {
-        p.gW3[e] = fmaf(cw + 2.0f * p.loss_scale * p.c_reg, p.w3[e], p.ws_gw3[e]);
-        p.gb2[e] = p.ws_gb2[e];
+        float gw = 0.0f, gb = 0.0f;
+#pragma unroll
+        for (int k = 0; k < REPL; ++k) {
+            gw += p.ws_gw3[k * p.h2 + e];
+            gb += p.ws_gb2[k * p.h2 + e];
+        }
+        p.gW3[e] = fmaf(cw + 2.0f * p.loss_scale * p.c_reg, p.w3[e], gw);
+        p.gb2[e] = gb;
     }
-    for (long long e = tid; e < p.h1; e += stride) p.gb1[e] = p.ws_gb1[e];
+    for (long long e = tid; e < p.h1; e += stride) {
+        if (p.Kp > p.in_features) {  // the "ones" column of X (stage_cast_kernel): column in_features of E1^T X is colsum(E1)
+            float g = 0.0f;
+            for (int s = 0; s < p.splits1; ++s) g += p.slices1[s * s1 + e * p.Kp + p.in_features];
+            p.gb1[e] = g;
+        } else {
+            float g = 0.0f;
+#pragma unroll
+            for (int k = 0; k < REPL; ++k) g += p.ws_gb1[k * p.h1 + e];
+            p.gb1[e] = g;
+        }
+    }
     if (tid == 0) {
         p.gb3[0] = p.acc[ACC_GB3];
         const float bce_cat = p.acc[ACC_BCE_CAT] / (2.0f * (float)p.B), bce_motion = p.acc[ACC_BCE_MOTION] / (float)p.B;
@@ -518,7 +653,6 @@ struct amp_disc_train {
     __nv_bfloat16 *W1b, *W1t, *W2b, *W2t;       // bf16 weights: (h1,Kp), (Kp,h1), (h2,h1), (h1,h2)
     float *ws;                                  // fp32: [ACC_COUNT scalars | gw3 h2 | gb2 h2 | gb1 h1]
     float *slices1, *slices2;                   // split-K slices of dW1 (splits1, h1, Kp) and dW2 (splits2, h2, h1)
-    float *mean_f, *denom_f, *ident_mean, *ident_denom;
     int splits1, splits2;
     int64_t staged_rows[3];                     // rows staged per source since the last step (-1: none)
 };
@@ -530,8 +664,7 @@ extern "C" {
 
 int amp_disc_train_destroy(amp_disc_train_t *t) {
     if (!t) return AMP_OK;
-    void *ptrs[] = {t->X, t->A1, t->A2, t->E1, t->E2, t->S, t->W1b, t->W1t, t->W2b, t->W2t, t->ws, t->slices1, t->slices2,
-                    t->mean_f, t->denom_f, t->ident_mean, t->ident_denom};
+    void *ptrs[] = {t->X, t->A1, t->A2, t->E1, t->E2, t->S, t->W1b, t->W1t, t->W2b, t->W2t, t->ws, t->slices1, t->slices2};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     delete t;
@@ -541,9 +674,9 @@ int amp_disc_train_destroy(amp_disc_train_t *t) {
 int amp_disc_train_create(int32_t in_features, int32_t h1, int32_t h2, int64_t max_batch_rows, void *stream, amp_disc_train_t **out) {
     AMP_REQUIRE(out, "amp_disc_train_create: NULL out");
     *out = nullptr;
-    AMP_REQUIRE(in_features >= 1 && in_features <= 1024 && h1 >= BN && h2 >= BN && h1 % BN == 0 && h2 % BN == 0,
-                "amp_disc_train_create: hidden sizes must be multiples of %d (got %d, %d), 1 <= in_features <= 1024 (got %d)", BN, h1, h2,
-                in_features);
+    AMP_REQUIRE(in_features >= 1 && in_features <= 1024 && h1 >= BN && h2 >= BN && h1 % BN == 0 && h2 % BN == 0 && h2 <= 2048,
+                "amp_disc_train_create: hidden sizes must be multiples of %d, h2 <= 2048 (got %d, %d), 1 <= in_features <= 1024 (got %d)", BN,
+                h1, h2, in_features);
     AMP_REQUIRE(max_batch_rows >= 1 && max_batch_rows <= (1 << 22), "amp_disc_train_create: max_batch_rows must be in [1, 4194304]");
     int dev = 0, major = 0;
     AMP_CUDA_TRY(cudaGetDevice(&dev));
@@ -571,10 +704,8 @@ int amp_disc_train_create(int32_t in_features, int32_t h1, int32_t h2, int64_t m
         {(void **)&t->E1, 4 * Bp * h1 * 2},     {(void **)&t->E2, 4 * Bp * h2 * 2},     {(void **)&t->S, Bp * h2 * 2},
         {(void **)&t->W1b, (size_t)h1 * t->Kp * 2}, {(void **)&t->W1t, (size_t)t->Kp * h1 * 2},
         {(void **)&t->W2b, (size_t)h2 * h1 * 2},    {(void **)&t->W2t, (size_t)h1 * h2 * 2},
-        {(void **)&t->ws, (size_t)(ACC_COUNT + 2 * h2 + h1) * 4},
+        {(void **)&t->ws, ((size_t)ACC_COUNT + (size_t)REPL * (2 * h2 + h1) + 3 * Bp) * 4},
         {(void **)&t->slices1, (size_t)t->splits1 * h1 * t->Kp * 4}, {(void **)&t->slices2, (size_t)t->splits2 * h2 * h1 * 4},
-        {(void **)&t->mean_f, (size_t)in_features * 4}, {(void **)&t->denom_f, (size_t)in_features * 4},
-        {(void **)&t->ident_mean, (size_t)in_features * 4}, {(void **)&t->ident_denom, (size_t)in_features * 4},
     };
     cudaStream_t st = as_stream(stream);
     for (auto &a : allocs) {
@@ -585,13 +716,11 @@ int amp_disc_train_create(int32_t in_features, int32_t h1, int32_t h2, int64_t m
             return cuda_fail(e, "cudaMalloc(amp_disc_train_create)");
         }
     }
-    {  // identity scaler for already-normalised inputs: mean 0, denominator 1
-        std::vector<float> ones((size_t)in_features, 1.0f);
-        cudaError_t e = cudaMemcpyAsync(t->ident_denom, ones.data(), ones.size() * 4, cudaMemcpyHostToDevice, st);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if ((size_t)32 * h2 * 2 > 48 * 1024) {  // head_kernel keeps a 32-row tile of a2 in shared memory
+        cudaError_t e = cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * h2 * 2);
         if (e != cudaSuccess) {
             amp_disc_train_destroy(t);
-            return cuda_fail(e, "amp_disc_train_create: identity scaler upload");
+            return cuda_fail(e, "cudaFuncSetAttribute(head_kernel)");
         }
     }
     *out = t;
@@ -608,15 +737,9 @@ int amp_disc_train_stage(amp_disc_train_t *t, int32_t source, const float *x, in
     AMP_REQUIRE((running_mean == nullptr) == (running_variance == nullptr), "amp_disc_train_stage: give both scaler buffers or neither");
     cudaStream_t st = as_stream(stream);
     const int64_t Bp = (batch_rows + BM - 1) / BM * BM;
-    const float *mean = t->ident_mean, *denom = t->ident_denom;
-    if (running_mean) {
-        int rc = scaler_stats_to_f32(running_mean, running_variance, t->in_features, t->mean_f, t->denom_f, st);
-        if (rc != AMP_OK) return rc;
-        mean = t->mean_f;
-        denom = t->denom_f;
-    }
-    int rc = normalise_cast_rows(x, x_stride, rows, t->in_features, t->Kp, mean, denom, t->X + (size_t)source * Bp * t->Kp, st);
-    if (rc != AMP_OK) return rc;
+    stage_cast_kernel<<<dim3((t->Kp + 511) / 512, (unsigned)((rows + STAGE_ROWS - 1) / STAGE_ROWS)), 256, 0, st>>>(
+        x, x_stride, (int)rows, t->in_features, t->Kp, running_mean, running_variance, t->X + (size_t)source * Bp * t->Kp);
+    AMP_CUDA_TRY(cudaGetLastError());
     t->staged_rows[source] = rows;
     return AMP_OK;
 }
@@ -635,8 +758,9 @@ int amp_disc_train_step(amp_disc_train_t *t, const float *W1, const float *b1, c
     const int B = (int)batch_rows;
     const int Bp = (B + BM - 1) / BM * BM;
     const int Kp = t->Kp, h1 = t->h1, h2 = t->h2;
-    float *acc = t->ws, *ws_gw3 = t->ws + ACC_COUNT, *ws_gb2 = ws_gw3 + h2, *ws_gb1 = ws_gb2 + h2;
-    AMP_CUDA_TRY(cudaMemsetAsync(t->ws, 0, (size_t)(ACC_COUNT + 2 * h2 + h1) * 4, st));
+    float *acc = t->ws, *ws_gw3 = t->ws + ACC_COUNT, *ws_gb2 = ws_gw3 + REPL * h2, *ws_gb1 = ws_gb2 + REPL * h2;
+    float *ws_dot = ws_gb1 + REPL * h1;  // [3Bp] a2 . w3, accumulated by the layer-2 epilogue
+    AMP_CUDA_TRY(cudaMemsetAsync(t->ws, 0, ((size_t)ACC_COUNT + (size_t)REPL * (2 * h2 + h1) + 3 * (size_t)Bp) * 4, st));
 
     // ---- weights: bf16 copies (both orientations) + sums of squares ----
     cast_transpose_kernel<<<dim3(Kp / 32, h1 / 32), 256, 0, st>>>(W1, h1, t->in_features, Kp, t->W1b, t->W1t, acc + ACC_W_SQ);
@@ -679,10 +803,10 @@ int amp_disc_train_step(amp_disc_train_t *t, const float *W1, const float *b1, c
     // F2: A2 = relu(A1[:3Bp] W2^T + b2)
     g = GemmParams{};
     g.m_tiles = 3 * Bp / BM; g.n_tiles = h2 / BN; g.splits = 1; g.kblocks = h1 / BK; g.n_valid = h2;
-    g.bias = b2; g.out = t->A2; g.out_ld = h2;
+    g.bias = b2; g.out = t->A2; g.out_ld = h2; g.dot_w = W3; g.dot_out = ws_dot;
     if ((rc = launch_gemm<false, false, EPI_BIAS_RELU>(tA1_k, tW2b, g, st)) != AMP_OK) return rc;
     // head: logits, BCE, dd, E2 (dz2 | u2), dL/db2, dL/dw3 (first part), dL/db3
-    head_kernel<<<3 * Bp / 32, 256, 0, st>>>(t->A2, h2, Bp, B, W3, b3, loss_scale, t->E2, acc, ws_gw3, ws_gb2, logits);
+    head_kernel<<<3 * Bp / 32, 256, (size_t)32 * h2 * 2, st>>>(t->A2, ws_dot, h2, Bp, B, W3, b3, loss_scale, t->E2, acc, ws_gw3, ws_gb2, logits);
     AMP_CUDA_TRY(cudaGetLastError());
     // B1: E1 = (E2 W2) * m1 -- rows < 3Bp use a1 of the same row, rows >= 3Bp (u2 -> v1) the a1 of the motion block
     g = GemmParams{};
@@ -720,8 +844,9 @@ int amp_disc_train_step(amp_disc_train_t *t, const float *W1, const float *b1, c
     const int used1 = g.splits;
     if ((rc = launch_gemm<true, true, EPI_SLICE>(tE1_mn, tX_mn, g, st)) != AMP_OK) return rc;
     // bias gradient of layer 1 and the gradient-penalty part of dL/dw3
-    colsum_kernel<<<dim3((h1 + 511) / 512, (3 * Bp + 63) / 64), 256, 0, st>>>(t->E1, h1, 3 * Bp, h1, ws_gb1);
-    colsum_kernel<<<dim3((h2 + 511) / 512, (Bp + 63) / 64), 256, 0, st>>>(t->S, h2, Bp, h2, ws_gw3);
+    if (Kp == t->in_features)  // no spare column for the "ones" trick: explicit column sum
+        colsum_kernel<<<dim3((h1 + 511) / 512, (3 * Bp + COLSUM_ROWS - 1) / COLSUM_ROWS), 256, 0, st>>>(t->E1, h1, 3 * Bp, h1, ws_gb1);
+    colsum_kernel<<<dim3((h2 + 511) / 512, (Bp + COLSUM_ROWS - 1) / COLSUM_ROWS), 256, 0, st>>>(t->S, h2, Bp, h2, ws_gw3);
     AMP_CUDA_TRY(cudaGetLastError());
 
     FinalizeParams f{};

@@ -104,16 +104,31 @@ __global__ void __launch_bounds__(kStatThreads) scaler_partial_kernel(const floa
     }
 }
 
-__global__ void __launch_bounds__(kStatThreads) scaler_merge_kernel(const double *__restrict__ scratch, int parts, int64_t M, int W,
-                                                                     double *__restrict__ running_mean,
-                                                                     double *__restrict__ running_var,
-                                                                     const double *__restrict__ count_in) {
-    const int c = blockIdx.x * kStatThreads + threadIdx.x;
-    if (c >= W) return;
+// 32 columns per block; the 8 warps split the partial sums (warp w takes parts w, w+8, ...) and meet in shared memory in a
+// fixed order, so the result does not depend on scheduling.
+__global__ void __launch_bounds__(256) scaler_merge_kernel(const double *__restrict__ scratch, int parts, int64_t M, int W,
+                                                           double *__restrict__ running_mean, double *__restrict__ running_var,
+                                                           const double *__restrict__ count_in) {
+    __shared__ double sh[2][8][32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
     double s = 0.0, ss = 0.0;
-    for (int p = 0; p < parts; ++p) {
-        s += scratch[(size_t)p * 2 * W + c];
-        ss += scratch[(size_t)p * 2 * W + W + c];
+    if (c < W) {
+#pragma unroll 4
+        for (int p = ty; p < parts; p += 8) {
+            s += scratch[(size_t)p * 2 * W + c];
+            ss += scratch[(size_t)p * 2 * W + W + c];
+        }
+    }
+    sh[0][ty][tx] = s;
+    sh[1][ty][tx] = ss;
+    __syncthreads();
+    if (ty != 0 || c >= W) return;
+    s = ss = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        s += sh[0][w][tx];
+        ss += sh[1][w][tx];
     }
     const double n = (double)M;
     // torch.mean / torch.var(unbiased) of an fp32 batch are fp32 values; M == 1 gives NaN like torch.var
@@ -201,7 +216,7 @@ int amp_gather_rows(const float *src, int64_t src_stride, int64_t capacity, cons
     return AMP_OK;
 }
 
-static int stat_parts(int64_t M) { return (int)std::max<int64_t>(1, std::min<int64_t>((M + 63) / 64, (int64_t)sm_count() * 4)); }
+static int stat_parts(int64_t M) { return (int)std::max<int64_t>(1, std::min<int64_t>((M + 15) / 16, (int64_t)sm_count() * 4)); }
 
 int64_t amp_scaler_scratch_bytes(int32_t W) { return W < 1 ? 0 : (int64_t)sm_count() * 4 * 2 * W * (int64_t)sizeof(double); }
 
@@ -217,7 +232,7 @@ int amp_scaler_update(const float *x, int64_t x_stride, int64_t M, int32_t W, do
     cudaStream_t st = as_stream(stream);
     const int col_blocks = (W + kStatThreads - 1) / kStatThreads;
     scaler_partial_kernel<<<dim3(parts, col_blocks), kStatThreads, 0, st>>>(x, x_stride, M, W, static_cast<double *>(scratch));
-    scaler_merge_kernel<<<col_blocks, kStatThreads, 0, st>>>(static_cast<const double *>(scratch), parts, M, W, running_mean,
+    scaler_merge_kernel<<<(W + 31) / 32, 256, 0, st>>>(static_cast<const double *>(scratch), parts, M, W, running_mean,
                                                              running_variance, current_count);
     scaler_count_kernel<<<1, 1, 0, st>>>(current_count, M);
     AMP_CUDA_TRY(cudaGetLastError());

@@ -135,9 +135,10 @@ def discriminator_loss_manual(weights: Sequence[torch.Tensor], biases: Sequence[
     W1r, W2r = _r(W1, e), _r(W2, e)
 
     a1 = _r(torch.relu(x @ W1r.t() + b1), e)
-    a2 = _r(torch.relu(a1 @ W2r.t() + b2), e)
+    a2_full = torch.relu(a1 @ W2r.t() + b2)
+    a2 = _r(a2_full, e)
     m1, m2 = (a1 > 0).to(dtype), (a2 > 0).to(dtype)
-    d = a2 @ w3 + b3
+    d = a2_full @ w3 + b3  # the CUDA path folds the last layer into the layer-2 read-out, before a2 is rounded
     sig = torch.sigmoid(d)
     softplus = torch.nn.functional.softplus
     bce_cat = softplus(d[:n_cat]).mean()
