@@ -184,8 +184,8 @@ train_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         if (lane == 0) {
             // kind::f16 instruction descriptor: D fp32 (bit 4), A/B bf16 (bits 7, 10), A/B major (bits 15, 16; 1 = MN-major),
             // N >> 3 at bits [17,23), M >> 4 at bits [24,29)
-            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)A_MN << 15) | ((uint32_t)B_MN << 16) |
-                                       ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            constexpr uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)A_MN << 15) | ((uint32_t)B_MN << 16) |
+                                            ((uint32_t)(BM >> 4) << 24);
             // descriptor start-address step (units of 16 B) per UMMA_K = 16: K-major 32 B inside the swizzled row;
             // MN-major 16 K-rows x 128 B = 2048 B
             constexpr uint32_t a_step = A_MN ? (16 * 128) >> 4 : 2;
@@ -193,8 +193,11 @@ train_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             int stage = 0;
             uint32_t phase = 0, it = 0;
             for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
-                const int s = item / tiles;
+                const int s = item / tiles, n = (item - s * tiles) % p.n_tiles;
                 const int kb0 = (int)((long long)s * p.kblocks / p.splits), kb1 = (int)((long long)(s + 1) * p.kblocks / p.splits);
+                // the last N tile may be narrower than 256 columns (n_valid = 832: 256, 256, 256, 64): issue only the columns
+                // that exist (UMMA N is any multiple of 16); the TMA boxes past n_valid are zero-filled and simply not read
+                const uint32_t idesc = idesc_base | ((uint32_t)(min(BN, p.n_valid - n * BN) >> 3) << 17);
                 const uint32_t r = it & 1, use = it >> 1;
                 mbar_wait(acc_empty + 8 * r, (use & 1) ^ 1);
                 tcgen05_fence_after();

@@ -24,15 +24,8 @@ import torch
 import yaml
 
 from . import _lib
-
-_TENSOR_KEYS = (
-    "dof_positions",
-    "dof_velocities",
-    "body_positions",
-    "body_rotations",
-    "body_linear_velocities",
-    "body_angular_velocities",
-)
+from .clip_cache import TENSOR_KEYS as _TENSOR_KEYS
+from .clip_cache import load_clips
 
 
 def _resolve_motion_files(motion_file: str) -> list[str]:
@@ -133,39 +126,30 @@ class MotionLoader:
     Reference: ``motions/motion_loader.py:87-430``.  ``device`` must be a CUDA device.
     """
 
-    def __init__(self, motion_file: str, device) -> None:
+    def __init__(self, motion_file: str, device, cache_dir: Optional[str] = None) -> None:
+        """``motion_file``: anything the reference accepts (``motion_loader.py:14-84``) or one packed ``.ampclip`` file.
+        ``cache_dir`` (or the environment variable ``AMP_B200_CLIP_CACHE``): keep / reuse a packed cache of the resolved
+        clip set there (``clip_cache.py``)."""
         files = _resolve_motion_files(motion_file)
         print(f"Loading {len(files)} motion file(s) from: {motion_file}")
         self.device = _lib.require_cuda(device)
 
-        parts = {k: [] for k in _TENSOR_KEYS}
-        starts, ends, durs = [], [], []
-        cursor = 0
-        self.dt = None
-        for path in files:
-            with np.load(path) as data:
-                if self.dt is None:  # names and fps come from the first file only (reference :119-122)
-                    self._dof_names = data["dof_names"].tolist()
-                    self._body_names = data["body_names"].tolist()
-                    self.dt = 1.0 / data["fps"]
-                for k in _TENSOR_KEYS:
-                    parts[k].append(data[k])
-                n_frames = data["dof_positions"].shape[0]
-            starts.append(cursor)
-            cursor += n_frames
-            ends.append(cursor - 1)
-            durs.append(self.dt * (n_frames - 1))
-        self.traj_starts = np.array(starts)
-        self.traj_ends = np.array(ends)
-        self.durations = np.array(durs)
-        self.num_trajectories = len(files)
-        self.num_frames = cursor
+        def pinned(nbytes: int) -> np.ndarray:
+            self._staging = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+            return self._staging.numpy()
+
+        clip, self.load_path = load_clips(files, cache_dir or os.environ.get("AMP_B200_CLIP_CACHE") or None, pinned)
+        self._dof_names, self._body_names = clip.dof_names, clip.body_names
+        self.dt = clip.dt
+        self.traj_starts, self.traj_ends, self.durations = clip.traj_starts, clip.traj_ends, clip.durations
+        self.num_trajectories = clip.num_trajectories
+        self.num_frames = clip.num_frames
         self.duration = float(np.sum(self.durations))
-        for k in _TENSOR_KEYS:  # float64 clip arrays are narrowed to fp32 exactly as torch.tensor(..., float32) does
-            host = np.ascontiguousarray(np.concatenate(parts[k]).astype(np.float32))
-            setattr(self, k, torch.from_numpy(host).to(self.device).contiguous())
-        if self.body_positions.shape[1] != len(self._body_names) or self.dof_positions.shape[1] != len(self._dof_names):
-            raise ValueError("clip tensors do not match dof_names / body_names of the first file")
+        # ONE host-to-device copy of the whole arena; the six tensors the reference keeps (:141-158) are views into it
+        self._arena = self._staging.to(self.device, non_blocking=True)
+        for k, off, shape in zip(_TENSOR_KEYS, clip.offsets, clip.shapes):
+            nbytes = 4 * int(np.prod(shape))
+            setattr(self, k, self._arena[off : off + nbytes].view(torch.float32).view(shape))
         print(
             f"Motion loaded: {self.num_trajectories} files, total duration: {self.duration} sec, total frames: {self.num_frames}"
         )
