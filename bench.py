@@ -255,11 +255,25 @@ def run_ours(args, spec, rank, world, local_rank):
     rows_for_reward = obs if spec["reward_mult"] == 1 else torch.empty((reward_rows, width), dtype=torch.float32, device=dev).normal_()
     reward = torch.empty(reward_rows, dtype=torch.float32, device=dev)
     state = synthetic_sim_state(n, robot, dev, seed=7) if spec["env_step"] else None
-    grads = None
+    grads = bucket = None
     if spec["allreduce"]:
-        # policy + value + discriminator of the humanoid config: one flat fp32 gradient buffer (SURVEY 8d cfg 5)
+        # policy + value + discriminator of the humanoid config: one flat fp32 gradient bucket (SURVEY 8d cfg 5), averaged
+        # over the ranks by the peer-memory kernel (csrc/amp_bucket.cu); AMP_B200_BENCH_NCCL=1 times NCCL instead
         n_disc = width * 1024 + 1024 + 1024 * 512 + 512 + 512 + 1
-        grads = torch.randn(3 * n_disc, dtype=torch.float32, device=dev)
+        if distributed and os.environ.get("AMP_B200_BENCH_NCCL") != "1":
+            bucket = amp.GradientBucket(3 * n_disc, dev)
+            grads = bucket.flat[: 3 * n_disc].normal_()
+        else:
+            grads = torch.randn(3 * n_disc, dtype=torch.float32, device=dev)
+
+    def exchange_gradients():
+        if grads is None or not distributed:
+            return
+        if bucket is not None:
+            bucket.all_reduce_mean()
+        else:
+            dist.all_reduce(grads)
+            grads.div_(world)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if spec["flush"] else None
 
     def step_resident():
@@ -267,11 +281,10 @@ def run_ours(args, spec, rank, world, local_rank):
         if state is not None:
             env.update_amp_observations(*state)
         disc.style_reward(rows_for_reward, out=reward)
-        if grads is not None and distributed:
-            dist.all_reduce(grads)
-            grads.div_(world)
+        exchange_gradients()
 
     launches_per_step = 1 + (1 if state is not None else 0) + 2 * ((reward_rows + disc.chunk_rows - 1) // disc.chunk_rows)
+    launches_per_step += 1 if bucket is not None else 0  # the peer-memory all-reduce kernel
 
     def sync_all():
         if distributed:
@@ -309,9 +322,7 @@ def run_ours(args, spec, rank, world, local_rank):
             g_obs.replay() if use_graph else stage_obs()
             s1.record()
             g_disc.replay() if use_graph else stage_disc()
-            if grads is not None and distributed:
-                dist.all_reduce(grads)
-                grads.div_(world)
+            exchange_gradients()
             s2.record()
         whole1.record()
         sync_all()

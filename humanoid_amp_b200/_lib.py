@@ -91,6 +91,14 @@ SIGNATURES = {
     "amp_disc_train_destroy": (C.c_int, [_P]),
     "amp_disc_train_stage": (C.c_int, [_P, _I32, _P, _I64, _I64, _I64, _P, _P, _P]),
     "amp_disc_train_step": (C.c_int, [_P] * 7 + [_I64, _F32, _F32, _F32, _F32] + [_P] * 9),
+    "amp_bucket_create": (C.c_int, [_I64, _I32, _I32, C.POINTER(_P)]),
+    "amp_bucket_destroy": (C.c_int, [_P]),
+    "amp_bucket_floats": (C.c_int64, [_P]),
+    "amp_bucket_data": (C.c_void_p, [_P]),
+    "amp_bucket_export": (C.c_int, [_P, _P]),
+    "amp_bucket_connect": (C.c_int, [_P, _P]),
+    "amp_bucket_allreduce_mean": (C.c_int, [_P, _I64, _I64, _P]),
+    "amp_bucket_poll_status": (C.c_int, [_P, _P, C.POINTER(C.c_uint32)]),
 }
 
 _lib = None

@@ -34,6 +34,7 @@ SOURCES = {
     # AMP_DISC_PROFILE=1 (developer builds only) adds in-kernel cycle counters to the fused discriminator kernel
     "amp_disc.cu": ["-DAMP_DISC_PROFILE"] if os.environ.get("AMP_DISC_PROFILE") == "1" else [],
     "amp_disc_train.cu": [],
+    "amp_bucket.cu": [],
 }
 HEADERS = ["amp_internal.h", "amp_math.cuh", os.path.join(ROOT, "include", "amp_b200.h")]
 

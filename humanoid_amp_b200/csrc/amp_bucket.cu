@@ -1,0 +1,253 @@
+// The one exchange step of the AMP path: the gradient all-reduce.
+//
+//   amp_bucket_*  <- skrl Model.reduce_parameters (upstream skrl >= 1.4.3; enabled by the reference at train.py:53-58,
+//                    184-196): all-reduce(SUM) of the flattened gradients, divided by the world size, per mini-batch.
+//
+// One process per GPU.  Each rank owns a "bucket": ONE flat fp32 device buffer that the gradient producers write into
+// directly (amp_disc_train_step's outputs are views of it), exported to the other ranks of the node with CUDA IPC.  The
+// all-reduce is ONE kernel per rank working on peer memory over NVLink / NVSwitch, two-shot and in place:
+//
+//   barrier A   every rank tells every peer "my bucket holds this step's gradients" (a flag written into the peer's memory)
+//   reduce      rank r owns slice r of the bucket: it loads slice r of EVERY rank (peer loads, fixed rank order, so the sum
+//               is deterministic and identical everywhere), scales by 1/world, and stores the result into slice r of
+//               EVERY rank (peer stores)
+//   barrier B   "my stores are out" -- when a rank has seen that flag from all peers its whole bucket is final
+//
+// so each rank moves 2 (W-1)/W of the bucket over NVLink, all links busy in both directions at once, with no staging
+// copy and no second launch.  Flags are monotonically increasing epochs (two per call); spins are bounded (about two
+// seconds) and report AMP_ECUDA-style failure through a device word instead of hanging the GPU if a peer never arrives.
+#include <algorithm>
+#include <cstring>
+#include <new>
+
+#include "amp_internal.h"
+
+namespace amp {
+namespace bucket {
+
+constexpr int kMaxWorld = 16;
+constexpr int kThreads = 256;
+constexpr long long kSpinLimitCycles = 4000000000LL;  // ~2 s at 2 GHz
+
+struct Peers {
+    float *data[kMaxWorld];
+    uint32_t *flags[kMaxWorld];  // flags[p] = rank p's flag array (kMaxWorld words: word q is written by rank q)
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 ld_peer(const float4 *p) {  // L2-coherent load: peer memory is never served from a stale L1 line
+    float4 v;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_peer(float4 *p, float4 v) {
+    asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// wait until every rank's word in the LOCAL flag array has reached `epoch`; returns false on timeout
+__device__ __forceinline__ bool wait_all(const uint32_t *local_flags, int world, uint32_t epoch) {
+    const long long t0 = clock64();
+    for (int p = 0; p < world; ++p) {
+        while ((int32_t)(ld_acquire_sys(local_flags + p) - epoch) < 0) {
+            if (clock64() - t0 > kSpinLimitCycles) return false;
+            __nanosleep(64);
+        }
+    }
+    return true;
+}
+
+// count % 4 == 0, base pointers 16-byte aligned.  Slice r = quads [r * per, min((r + 1) * per, quads)).
+__global__ void __launch_bounds__(kThreads) allreduce_mean_kernel(Peers peers, int rank, int world, long long offset, long long count,
+                                                                  uint32_t epoch, unsigned int *arrivals, uint32_t *status) {
+    __shared__ bool ok;
+    uint32_t *local_flags = peers.flags[rank];
+    // ---- barrier A: announce (block 0) and wait (every block, on the local flag array) ----
+    if (blockIdx.x == 0 && threadIdx.x < world) {
+        __threadfence_system();
+        st_release_sys(peers.flags[threadIdx.x] + rank, epoch);
+    }
+    if (threadIdx.x == 0) ok = wait_all(local_flags, world, epoch);
+    __syncthreads();
+    if (!ok) {
+        if (threadIdx.x == 0) atomicOr(status, 1u);
+        return;
+    }
+    // ---- reduce slice `rank` and publish it to everyone ----
+    const long long quads = count / 4;
+    const long long per = (quads + world - 1) / world;
+    const long long q0 = (long long)rank * per, q1 = min(quads, q0 + per);
+    const float inv = 1.0f / (float)world;
+    // four quads per thread per trip, all peer loads of a trip issued before the first add: NVLink round trips (~2 us) are
+    // the cost here, not bandwidth, so what matters is bytes in flight
+    constexpr int U = 4;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long q = q0 + blockIdx.x * (long long)blockDim.x + threadIdx.x; q < q1; q += U * stride) {
+        float4 acc[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int p = 0; p < world; ++p) {
+            const float4 *src = reinterpret_cast<const float4 *>(peers.data[p] + offset);
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (q + u * stride < q1) v[u] = ld_peer(src + q + u * stride);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (q + u * stride < q1) { acc[u].x += v[u].x; acc[u].y += v[u].y; acc[u].z += v[u].z; acc[u].w += v[u].w; }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) { acc[u].x *= inv; acc[u].y *= inv; acc[u].z *= inv; acc[u].w *= inv; }
+        for (int p = 0; p < world; ++p) {
+            float4 *dst = reinterpret_cast<float4 *>(peers.data[p] + offset);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (q + u * stride < q1) st_peer(dst + q + u * stride, acc[u]);
+        }
+    }
+    // ---- barrier B: the last block of this rank to finish announces; it also waits, so the kernel (and with it the stream)
+    // completes only when every peer's stores into the local bucket have been announced ----
+    __threadfence_system();
+    __syncthreads();
+    __shared__ bool last;
+    if (threadIdx.x == 0) last = atomicAdd(arrivals, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    if (threadIdx.x == 0) *arrivals = 0;  // ready for the next call (stream-ordered)
+    if (threadIdx.x < world) {
+        __threadfence_system();
+        st_release_sys(peers.flags[threadIdx.x] + rank, epoch + 1);
+    }
+    if (threadIdx.x == 0 && !wait_all(local_flags, world, epoch + 1)) atomicOr(status, 2u);
+}
+
+}  // namespace bucket
+}  // namespace amp
+
+struct amp_bucket {
+    int world, rank, device;
+    int64_t floats;
+    float *data;          // local bucket (cudaMalloc, IPC-exported)
+    uint32_t *flags;      // local flag array [kMaxWorld] (IPC-exported) ... + arrivals + status words behind it
+    amp::bucket::Peers peers;
+    void *opened[2 * amp::bucket::kMaxWorld];
+    int n_opened;
+    uint32_t epoch;       // last epoch used
+    bool connected;
+};
+
+using namespace amp;
+using namespace amp::bucket;
+
+extern "C" {
+
+int amp_bucket_destroy(amp_bucket_t *b) {
+    if (!b) return AMP_OK;
+    for (int i = 0; i < b->n_opened; ++i)
+        if (b->opened[i]) cudaIpcCloseMemHandle(b->opened[i]);
+    if (b->data) cudaFree(b->data);
+    if (b->flags) cudaFree(b->flags);
+    delete b;
+    return AMP_OK;
+}
+
+int amp_bucket_create(int64_t floats, int32_t world, int32_t rank, amp_bucket_t **out) {
+    AMP_REQUIRE(out, "amp_bucket_create: NULL out");
+    *out = nullptr;
+    AMP_REQUIRE(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, "amp_bucket_create: bad world %d / rank %d (max %d ranks)",
+                world, rank, kMaxWorld);
+    AMP_REQUIRE(floats >= 1, "amp_bucket_create: empty bucket");
+    amp_bucket *b = new (std::nothrow) amp_bucket();
+    if (!b) return fail(AMP_ENOMEM, "amp_bucket_create: host allocation failed");
+    std::memset(b, 0, sizeof(*b));
+    b->world = world;
+    b->rank = rank;
+    b->floats = (floats + 3) / 4 * 4;
+    AMP_CUDA_TRY(cudaGetDevice(&b->device));
+    cudaError_t e = cudaMalloc((void **)&b->data, (size_t)b->floats * 4);
+    if (e == cudaSuccess) e = cudaMemset(b->data, 0, (size_t)b->floats * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&b->flags, (kMaxWorld + 2) * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemset(b->flags, 0, (kMaxWorld + 2) * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        amp_bucket_destroy(b);
+        return cuda_fail(e, "cudaMalloc(amp_bucket_create)");
+    }
+    if (world == 1) {  // nothing to exchange: the "all-reduce" is the identity
+        b->peers.data[0] = b->data;
+        b->peers.flags[0] = b->flags;
+        b->connected = true;
+    }
+    *out = b;
+    return AMP_OK;
+}
+
+int64_t amp_bucket_floats(const amp_bucket_t *b) { return b ? b->floats : 0; }
+
+float *amp_bucket_data(amp_bucket_t *b) { return b ? b->data : nullptr; }
+
+int amp_bucket_export(amp_bucket_t *b, void *handles128) {
+    AMP_REQUIRE(b && handles128, "amp_bucket_export: NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h[2];
+    AMP_CUDA_TRY(cudaIpcGetMemHandle(&h[0], b->data));
+    AMP_CUDA_TRY(cudaIpcGetMemHandle(&h[1], b->flags));
+    std::memcpy(handles128, h, 128);
+    return AMP_OK;
+}
+
+int amp_bucket_connect(amp_bucket_t *b, const void *all_handles) {
+    AMP_REQUIRE(b && all_handles, "amp_bucket_connect: NULL argument");
+    AMP_REQUIRE(!b->connected, "amp_bucket_connect: already connected");
+    const cudaIpcMemHandle_t *h = static_cast<const cudaIpcMemHandle_t *>(all_handles);
+    for (int p = 0; p < b->world; ++p) {
+        if (p == b->rank) {
+            b->peers.data[p] = b->data;
+            b->peers.flags[p] = b->flags;
+            continue;
+        }
+        void *d = nullptr, *f = nullptr;
+        AMP_CUDA_TRY(cudaIpcOpenMemHandle(&d, h[2 * p], cudaIpcMemLazyEnablePeerAccess));
+        b->opened[b->n_opened++] = d;
+        AMP_CUDA_TRY(cudaIpcOpenMemHandle(&f, h[2 * p + 1], cudaIpcMemLazyEnablePeerAccess));
+        b->opened[b->n_opened++] = f;
+        b->peers.data[p] = static_cast<float *>(d);
+        b->peers.flags[p] = static_cast<uint32_t *>(f);
+    }
+    b->connected = true;
+    return AMP_OK;
+}
+
+int amp_bucket_allreduce_mean(amp_bucket_t *b, int64_t offset_floats, int64_t count, void *stream) {
+    AMP_REQUIRE(b, "amp_bucket_allreduce_mean: NULL handle");
+    AMP_REQUIRE(b->connected, "amp_bucket_allreduce_mean: amp_bucket_connect has not been called");
+    AMP_REQUIRE(offset_floats >= 0 && count >= 0 && offset_floats % 4 == 0 && offset_floats + count <= b->floats,
+                "amp_bucket_allreduce_mean: range [%lld, +%lld) outside the bucket of %lld floats or not 16-byte aligned",
+                (long long)offset_floats, (long long)count, (long long)b->floats);
+    if (count == 0 || b->world == 1) return AMP_OK;
+    const long long padded = (count + 3) / 4 * 4;  // the bucket is padded to whole quads; the tail floats are zero everywhere
+    AMP_REQUIRE(offset_floats + padded <= b->floats, "amp_bucket_allreduce_mean: range end is not quad-aligned inside the bucket");
+    const long long per = (padded / 4 + b->world - 1) / b->world;
+    const int grid = (int)std::max<long long>(1, std::min<long long>((per + 4 * kThreads - 1) / (4 * kThreads), 4LL * sm_count()));
+    b->epoch += 2;
+    allreduce_mean_kernel<<<grid, kThreads, 0, as_stream(stream)>>>(b->peers, b->rank, b->world, offset_floats, padded, b->epoch - 1,
+                                                                     reinterpret_cast<unsigned int *>(b->flags + kMaxWorld),
+                                                                     b->flags + kMaxWorld + 1);
+    AMP_CUDA_TRY(cudaGetLastError());
+    return AMP_OK;
+}
+
+int amp_bucket_poll_status(amp_bucket_t *b, void *stream, uint32_t *status) {
+    AMP_REQUIRE(b && status, "amp_bucket_poll_status: NULL argument");
+    AMP_CUDA_TRY(cudaMemcpyAsync(status, b->flags + kMaxWorld + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, as_stream(stream)));
+    AMP_CUDA_TRY(cudaStreamSynchronize(as_stream(stream)));
+    return AMP_OK;
+}
+
+}  // extern "C"

@@ -45,6 +45,7 @@ enum {
 typedef struct amp_lib amp_lib_t;   /* a motion library staged on one device */
 typedef struct amp_disc amp_disc_t; /* discriminator weights staged for the tensor-core kernel */
 typedef struct amp_disc_train amp_disc_train_t; /* workspaces of the discriminator loss + gradient step */
+typedef struct amp_bucket amp_bucket_t; /* one rank's flat gradient bucket, shared with the node's other ranks over NVLink */
 
 /* Description of a loaded motion library: what the reference MotionLoader.__init__ leaves behind
  * (motions/motion_loader.py:98-164) plus the env's index lists (g1_amp_env.py:40-60). */
@@ -239,6 +240,26 @@ AMP_API int amp_disc_train_step(amp_disc_train_t *t, const float *W1, const floa
                                 float logit_regularization_scale, float gradient_penalty_scale, float weight_decay_scale,
                                 float *gW1, float *gb1, float *gW2, float *gb2, float *gW3, float *gb3, float *terms,
                                 float *logits, void *stream);
+
+/* ---- gradient all-reduce over peer memory (skrl Model.reduce_parameters, enabled by the
+ *      reference at train.py:53-58, 184-196) ------------------------------------------------------------------------ */
+/* One process per GPU, all ranks on one node.  A bucket is ONE flat fp32 device buffer (rounded up to 4 floats, zero
+ * initialised) that gradient producers write into directly; amp_bucket_allreduce_mean averages it over the ranks in place
+ * with one kernel per rank that loads / stores peer memory over NVLink (two-shot: rank r reduces slice r of every rank
+ * and writes the result back to every rank).  world == 1 needs no export / connect and the all-reduce is a no-op.
+ *   create  -> export (128 bytes: two CUDA IPC handles) -> [exchange the blobs of all ranks, rank order] -> connect.
+ * Every rank must call amp_bucket_allreduce_mean the same number of times with the same range (like any collective). */
+AMP_API int amp_bucket_create(int64_t floats, int32_t world, int32_t rank, amp_bucket_t **out);
+AMP_API int amp_bucket_destroy(amp_bucket_t *b);
+AMP_API int64_t amp_bucket_floats(const amp_bucket_t *b);
+AMP_API float *amp_bucket_data(amp_bucket_t *b);
+AMP_API int amp_bucket_export(amp_bucket_t *b, void *handles128);
+AMP_API int amp_bucket_connect(amp_bucket_t *b, const void *all_handles);
+/* In place: bucket[offset, offset+count) = mean over ranks.  offset % 4 == 0.  Enqueued on `stream`; spins on peers are
+ * bounded (~2 s) and a timeout is reported by amp_bucket_poll_status (bit 0: a peer never announced its data, bit 1: a
+ * peer never announced its stores), not by hanging the device. */
+AMP_API int amp_bucket_allreduce_mean(amp_bucket_t *b, int64_t offset_floats, int64_t count, void *stream);
+AMP_API int amp_bucket_poll_status(amp_bucket_t *b, void *stream, uint32_t *status);
 
 #ifdef __cplusplus
 }

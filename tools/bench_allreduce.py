@@ -1,0 +1,131 @@
+"""Gradient all-reduce over peer memory (csrc/amp_bucket.cu) against NCCL, under torchrun on ONE node:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tools/bench_allreduce.py [--numel 2650000] [--iters 50]
+
+Checks (every rank): the bucket result equals NCCL all_reduce(SUM) / world within fp32 summation-order noise, is bitwise
+IDENTICAL on all ranks, stays correct over many back-to-back calls (epoch logic) and when the gradients are produced
+in place by AmpDiscriminatorUpdate.  Times both with CUDA events (barrier + synchronize on both sides, max over ranks).
+Rank 0 prints one JSON line ("ok": true/false).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def timed(fn, iters, dev):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+    torch.cuda.synchronize(dev)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize(dev)
+    t = torch.tensor([a.elapsed_time(b) / iters], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--numel", type=int, default=2_650_000)  # policy + value + discriminator of the G1 dance config
+    ap.add_argument("--iters", type=int, default=50)
+    a = ap.parse_args()
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", device_id=dev)
+    import humanoid_amp_b200 as amp
+
+    ok, notes = True, []
+    bucket = amp.GradientBucket(a.numel, dev)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+
+    # 1. correctness against NCCL, many calls back to back, odd sub-ranges
+    for it, (off, cnt) in enumerate([(0, a.numel), (0, a.numel), (4, a.numel - 7), (1024, 1001), (0, 4), (0, a.numel)]):
+        src = torch.randn(a.numel, device=dev, generator=g) * (1.0 + rank)
+        bucket.flat[: a.numel].copy_(src)
+        want = src.clone()
+        dist.all_reduce(want, op=dist.ReduceOp.SUM)
+        want /= world
+        bucket.all_reduce_mean(off, cnt)
+        got = bucket.flat[: a.numel]
+        end = off + (cnt + 3) // 4 * 4  # the kernel works on whole quads
+        err = float((got[off:end] - want[off:end]).abs().max())
+        scale = float(want.abs().max())
+        if not err <= 1e-5 * max(scale, 1.0):
+            ok = False
+            notes.append(f"call {it}: max err {err:.3e}")
+        if not torch.equal(got[:off], src[:off]) or not torch.equal(got[end:], src[end:]):
+            ok = False
+            notes.append(f"call {it}: elements outside the range changed")
+        mine = got[off:end].clone()
+        ref0 = mine.clone()
+        dist.broadcast(ref0, 0)
+        if not torch.equal(mine, ref0):
+            ok = False
+            notes.append(f"call {it}: ranks disagree bitwise")
+    if bucket.poll_status() != 0:
+        ok = False
+        notes.append("device status word set")
+
+    # 2. gradients produced in place by the discriminator update
+    in_features, hidden, B = 166, (1024, 512), 512
+    from humanoid_amp_b200.synthetic import skrl_style_discriminator_params
+
+    W, b = skrl_style_discriminator_params(in_features, seed=42)
+    W, b = [w.to(dev) for w in W], [x.to(dev) for x in b]
+    shapes = [tuple(w.shape) for w in W] + [tuple(x.shape) for x in b]
+    disc_bucket = amp.GradientBucket(sum(w.numel() for w in W) + sum(x.numel() for x in b), dev)
+    views = disc_bucket.carve(shapes)
+    upd = amp.AmpDiscriminatorUpdate(in_features, hidden, max_batch_rows=B, device=dev)
+    batches = [torch.randn(B, in_features, device=dev, generator=g).clamp_(-5, 5) for _ in range(3)]
+    upd(W, b, *batches, grad_weights=views[:3], grad_biases=views[3:])
+    local_grads = disc_bucket.flat[: disc_bucket.numel].clone()
+    want = local_grads.clone()
+    dist.all_reduce(want, op=dist.ReduceOp.SUM)
+    want /= world
+    disc_bucket.all_reduce_mean()
+    err = float((disc_bucket.flat[: disc_bucket.numel] - want).abs().max())
+    if not err <= 1e-5 * max(1.0, float(want.abs().max())):
+        ok = False
+        notes.append(f"in-place discriminator gradients: max err {err:.3e}")
+
+    # 3. timing
+    scratch = torch.randn(a.numel, device=dev, generator=g)
+
+    def nccl():
+        dist.all_reduce(scratch, op=dist.ReduceOp.SUM)
+        scratch.div_(world)
+
+    ms_nccl = timed(nccl, a.iters, dev)
+    ms_bucket = timed(lambda: bucket.all_reduce_mean(0, a.numel), a.iters, dev)
+    if bucket.poll_status() != 0:
+        ok = False
+        notes.append("device status word set after timing")
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        bytes_moved = 2.0 * (world - 1) / world * a.numel * 4
+        print(json.dumps({"what": "gradient all-reduce (mean) of one flat fp32 bucket", "world": world, "numel": a.numel,
+                          "ok": bool(flag.item()), "notes": notes, "ms_nccl_allreduce_plus_div": ms_nccl, "ms_peer_memory_kernel": ms_bucket,
+                          "speedup": ms_nccl / ms_bucket, "nvlink_gbs_per_rank_each_way": bytes_moved / ms_bucket / 1e6}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
