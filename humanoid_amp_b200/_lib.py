@@ -99,6 +99,7 @@ SIGNATURES = {
     "amp_bucket_connect": (C.c_int, [_P, _P]),
     "amp_bucket_allreduce_mean": (C.c_int, [_P, _I64, _I64, _P]),
     "amp_bucket_poll_status": (C.c_int, [_P, _P, C.POINTER(C.c_uint32)]),
+    "amp_bucket_last_timing": (C.c_int, [_P, _P, C.POINTER(C.c_uint64)]),
 }
 
 _lib = None

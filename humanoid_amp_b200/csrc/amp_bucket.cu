@@ -42,13 +42,16 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ float4 ld_peer(const float4 *p) {  // L2-coherent load: peer memory is never served from a stale L1 line
+// Data moves with ordinary (weak) accesses that bypass L1 -- .cg loads are served by the owning GPU's L2, so a line of peer
+// memory is never read from a stale local L1 -- and is ordered against the flags by __threadfence_system() + the
+// release / acquire pair of the barriers.  (sys-scoped relaxed accesses for the payload ran at 210 GB/s per direction.)
+__device__ __forceinline__ float4 ld_peer(const float4 *p) {
     float4 v;
-    asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_peer(float4 *p, float4 v) {
-    asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    asm volatile("st.global.cg.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
 // wait until every rank's word in the LOCAL flag array has reached `epoch`; returns false on timeout
@@ -64,9 +67,13 @@ __device__ __forceinline__ bool wait_all(const uint32_t *local_flags, int world,
 }
 
 // count % 4 == 0, base pointers 16-byte aligned.  Slice r = quads [r * per, min((r + 1) * per, quads)).
+template <int MAXW, int U>
 __global__ void __launch_bounds__(kThreads) allreduce_mean_kernel(Peers peers, int rank, int world, long long offset, long long count,
-                                                                  uint32_t epoch, unsigned int *arrivals, uint32_t *status) {
+                                                                  uint32_t epoch, unsigned int *arrivals, uint32_t *status,
+                                                                  unsigned long long *timing) {
     __shared__ bool ok;
+    unsigned long long t_start = 0, t_a = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
     uint32_t *local_flags = peers.flags[rank];
     // ---- barrier A: announce (block 0) and wait (every block, on the local flag array) ----
     if (blockIdx.x == 0 && threadIdx.x < world) {
@@ -79,36 +86,51 @@ __global__ void __launch_bounds__(kThreads) allreduce_mean_kernel(Peers peers, i
         if (threadIdx.x == 0) atomicOr(status, 1u);
         return;
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_a));
+        timing[0] = t_start;
+        timing[1] = t_a;
+    }
     // ---- reduce slice `rank` and publish it to everyone ----
     const long long quads = count / 4;
     const long long per = (quads + world - 1) / world;
     const long long q0 = (long long)rank * per, q1 = min(quads, q0 + per);
     const float inv = 1.0f / (float)world;
-    // four quads per thread per trip, all peer loads of a trip issued before the first add: NVLink round trips (~2 us) are
-    // the cost here, not bandwidth, so what matters is bytes in flight
-    constexpr int U = 4;
+    // NVLink round trips (~2 us) are the cost here, not bandwidth, so what matters is bytes in flight: every thread issues
+    // the loads of U quads from ALL peers (fully unrolled over up to MAXW ranks) before the first add.
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long q = q0 + blockIdx.x * (long long)blockDim.x + threadIdx.x; q < q1; q += U * stride) {
+        float4 v[MAXW][U];
+#pragma unroll
+        for (int p = 0; p < MAXW; ++p) {
+            if (p < world) {
+                const float4 *src = reinterpret_cast<const float4 *>(peers.data[p] + offset);
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (q + u * stride < q1) v[p][u] = ld_peer(src + q + u * stride);
+            }
+        }
         float4 acc[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int p = 0; p < world; ++p) {
-            const float4 *src = reinterpret_cast<const float4 *>(peers.data[p] + offset);
-            float4 v[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u)
-                if (q + u * stride < q1) v[u] = ld_peer(src + q + u * stride);
+        for (int p = 0; p < MAXW; ++p) {  // fixed rank order: the sum is the same on every rank
+            if (p < world) {
 #pragma unroll
-            for (int u = 0; u < U; ++u)
-                if (q + u * stride < q1) { acc[u].x += v[u].x; acc[u].y += v[u].y; acc[u].z += v[u].z; acc[u].w += v[u].w; }
+                for (int u = 0; u < U; ++u)
+                    if (q + u * stride < q1) { acc[u].x += v[p][u].x; acc[u].y += v[p][u].y; acc[u].z += v[p][u].z; acc[u].w += v[p][u].w; }
+            }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) { acc[u].x *= inv; acc[u].y *= inv; acc[u].z *= inv; acc[u].w *= inv; }
-        for (int p = 0; p < world; ++p) {
-            float4 *dst = reinterpret_cast<float4 *>(peers.data[p] + offset);
 #pragma unroll
-            for (int u = 0; u < U; ++u)
-                if (q + u * stride < q1) st_peer(dst + q + u * stride, acc[u]);
+        for (int p = 0; p < MAXW; ++p) {
+            if (p < world) {
+                float4 *dst = reinterpret_cast<float4 *>(peers.data[p] + offset);
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (q + u * stride < q1) st_peer(dst + q + u * stride, acc[u]);
+            }
         }
     }
     // ---- barrier B: the last block of this rank to finish announces; it also waits, so the kernel (and with it the stream)
@@ -124,7 +146,14 @@ __global__ void __launch_bounds__(kThreads) allreduce_mean_kernel(Peers peers, i
         __threadfence_system();
         st_release_sys(peers.flags[threadIdx.x] + rank, epoch + 1);
     }
-    if (threadIdx.x == 0 && !wait_all(local_flags, world, epoch + 1)) atomicOr(status, 2u);
+    if (threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        timing[2] = t;  // this rank's reduce + publish is complete
+        if (!wait_all(local_flags, world, epoch + 1)) atomicOr(status, 2u);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        timing[3] = t;
+    }
 }
 
 }  // namespace bucket
@@ -135,6 +164,7 @@ struct amp_bucket {
     int64_t floats;
     float *data;          // local bucket (cudaMalloc, IPC-exported)
     uint32_t *flags;      // local flag array [kMaxWorld] (IPC-exported) ... + arrivals + status words behind it
+    unsigned long long *timing;  // globaltimer stamps of the last call: start, barrier A passed, slice published, barrier B passed
     amp::bucket::Peers peers;
     void *opened[2 * amp::bucket::kMaxWorld];
     int n_opened;
@@ -153,6 +183,7 @@ int amp_bucket_destroy(amp_bucket_t *b) {
         if (b->opened[i]) cudaIpcCloseMemHandle(b->opened[i]);
     if (b->data) cudaFree(b->data);
     if (b->flags) cudaFree(b->flags);
+    if (b->timing) cudaFree(b->timing);
     delete b;
     return AMP_OK;
 }
@@ -174,6 +205,8 @@ int amp_bucket_create(int64_t floats, int32_t world, int32_t rank, amp_bucket_t 
     if (e == cudaSuccess) e = cudaMemset(b->data, 0, (size_t)b->floats * 4);
     if (e == cudaSuccess) e = cudaMalloc((void **)&b->flags, (kMaxWorld + 2) * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMemset(b->flags, 0, (kMaxWorld + 2) * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&b->timing, 4 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(b->timing, 0, 4 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         amp_bucket_destroy(b);
@@ -234,12 +267,25 @@ int amp_bucket_allreduce_mean(amp_bucket_t *b, int64_t offset_floats, int64_t co
     const long long padded = (count + 3) / 4 * 4;  // the bucket is padded to whole quads; the tail floats are zero everywhere
     AMP_REQUIRE(offset_floats + padded <= b->floats, "amp_bucket_allreduce_mean: range end is not quad-aligned inside the bucket");
     const long long per = (padded / 4 + b->world - 1) / b->world;
-    const int grid = (int)std::max<long long>(1, std::min<long long>((per + 4 * kThreads - 1) / (4 * kThreads), 4LL * sm_count()));
     b->epoch += 2;
-    allreduce_mean_kernel<<<grid, kThreads, 0, as_stream(stream)>>>(b->peers, b->rank, b->world, offset_floats, padded, b->epoch - 1,
-                                                                     reinterpret_cast<unsigned int *>(b->flags + kMaxWorld),
-                                                                     b->flags + kMaxWorld + 1);
+    unsigned int *arrivals = reinterpret_cast<unsigned int *>(b->flags + kMaxWorld);
+    uint32_t *status = b->flags + kMaxWorld + 1;
+    auto launch = [&](auto kern, int u) {
+        const int grid = (int)std::max<long long>(1, std::min<long long>((per + (long long)u * kThreads - 1) / ((long long)u * kThreads), 8LL * sm_count()));
+        kern<<<grid, kThreads, 0, as_stream(stream)>>>(b->peers, b->rank, b->world, offset_floats, padded, b->epoch - 1, arrivals, status, b->timing);
+    };
+    if (b->world <= 2) launch(allreduce_mean_kernel<2, 4>, 4);
+    else if (b->world <= 4) launch(allreduce_mean_kernel<4, 4>, 4);
+    else if (b->world <= 8) launch(allreduce_mean_kernel<8, 2>, 2);
+    else launch(allreduce_mean_kernel<kMaxWorld, 1>, 1);
     AMP_CUDA_TRY(cudaGetLastError());
+    return AMP_OK;
+}
+
+int amp_bucket_last_timing(amp_bucket_t *b, void *stream, uint64_t *stamps4) {
+    AMP_REQUIRE(b && stamps4, "amp_bucket_last_timing: NULL argument");
+    AMP_CUDA_TRY(cudaMemcpyAsync(stamps4, b->timing, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, as_stream(stream)));
+    AMP_CUDA_TRY(cudaStreamSynchronize(as_stream(stream)));
     return AMP_OK;
 }
 

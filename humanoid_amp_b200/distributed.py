@@ -94,6 +94,14 @@ class GradientBucket:
         _lib.check(lib.amp_bucket_poll_status(self._h, stream, C.byref(status)))
         return int(status.value)
 
+    def last_timing_us(self) -> dict:
+        """Phases of the last all-reduce on this rank (device ``%globaltimer``): waiting for the peers' data, reducing and
+        publishing the own slice, waiting for the peers' stores.  Synchronises."""
+        lib, stream = _lib.enter(self.device)
+        t = (C.c_uint64 * 4)()
+        _lib.check(lib.amp_bucket_last_timing(self._h, stream, t))
+        return {"barrier_a": (t[1] - t[0]) / 1e3, "reduce_publish": (t[2] - t[1]) / 1e3, "barrier_b": (t[3] - t[2]) / 1e3}
+
     def close(self):
         if getattr(self, "_h", None) is not None:
             self.flat = None

@@ -260,6 +260,9 @@ AMP_API int amp_bucket_connect(amp_bucket_t *b, const void *all_handles);
  * peer never announced its stores), not by hanging the device. */
 AMP_API int amp_bucket_allreduce_mean(amp_bucket_t *b, int64_t offset_floats, int64_t count, void *stream);
 AMP_API int amp_bucket_poll_status(amp_bucket_t *b, void *stream, uint32_t *status);
+/* %globaltimer stamps (ns) of the last all-reduce on this rank: kernel start, barrier A passed, own slice published,
+ * barrier B passed.  Synchronises the stream.  For tools/bench_allreduce.py. */
+AMP_API int amp_bucket_last_timing(amp_bucket_t *b, void *stream, uint64_t *stamps4);
 
 #ifdef __cplusplus
 }

@@ -113,6 +113,7 @@ def main():
 
     ms_nccl = timed(nccl, a.iters, dev)
     ms_bucket = timed(lambda: bucket.all_reduce_mean(0, a.numel), a.iters, dev)
+    phases = bucket.last_timing_us()
     if bucket.poll_status() != 0:
         ok = False
         notes.append("device status word set after timing")
@@ -122,7 +123,7 @@ def main():
         bytes_moved = 2.0 * (world - 1) / world * a.numel * 4
         print(json.dumps({"what": "gradient all-reduce (mean) of one flat fp32 bucket", "world": world, "numel": a.numel,
                           "ok": bool(flag.item()), "notes": notes, "ms_nccl_allreduce_plus_div": ms_nccl, "ms_peer_memory_kernel": ms_bucket,
-                          "speedup": ms_nccl / ms_bucket, "nvlink_gbs_per_rank_each_way": bytes_moved / ms_bucket / 1e6}))
+                          "speedup": ms_nccl / ms_bucket, "phases_us_rank0_last_call": phases, "nvlink_gbs_per_rank_each_way": bytes_moved / ms_bucket / 1e6}))
     dist.barrier()
     dist.destroy_process_group()
 
