@@ -112,7 +112,8 @@ __device__ __forceinline__ void walk_schedule(int T, int n1_tiles, int units, G1
 struct FusedParams {
     int M;          // rows of this launch (x_hat rows)
     int kb1;        // K blocks of layer 1 (Kp / 64)
-    int ksteps1_last;  // 16-wide K steps the LAST layer-1 block really needs: ceil((in_features - 64 (kb1 - 1)) / 16), 1..4
+    int ksteps1_last;  // 16-wide K steps the LAST layer-1 block really needs: ceil((in_features [+ 2] - 64 (kb1 - 1)) / 16), 1..4
+    int fold_bias1;    // b1 travels inside the layer-1 product (two padding columns of x_hat / W1): D1 is cvt + max only
     int n1_tiles;   // h1 / 256
     int n2_tiles;   // h2 / 256
     const float *b1, *b2, *w3, *b3;
@@ -376,15 +377,17 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                     const int col = nt * BN + (int)col_base + h * 32;  // h1 column of this step
                     const float4 *bias4 = reinterpret_cast<const float4 *>(p.b1 + col);
                     float4 bb[8];
+                    if (!p.fold_bias1) {  // launch-uniform
 #ifdef AMP_DISC_PROFILE
-                    if (p.prof_mode & 2) {
+                        if (p.prof_mode & 2) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) bb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    } else
+                            for (int j = 0; j < 8; ++j) bb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        } else
 #endif
-                    {
+                        {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) bb[j] = __ldg(bias4 + j);
+                            for (int j = 0; j < 8; ++j) bb[j] = __ldg(bias4 + j);
+                        }
                     }
                     const uint32_t slab = staging + (uint32_t)((ew * 2 + (store_it & 1)) * STORE_SLAB_BYTES);
                     {
@@ -410,15 +413,26 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 #endif
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {  // 16-byte chunk j of this thread's 64-byte slab row
-                        const float4 b0 = bb[2 * j], b1v = bb[2 * j + 1];
-                        const __nv_bfloat162 p0 = __floats2bfloat162_rn(fmaxf(__uint_as_float(cur[8 * j + 0]) + b0.x, 0.0f),
-                                                                        fmaxf(__uint_as_float(cur[8 * j + 1]) + b0.y, 0.0f));
-                        const __nv_bfloat162 p1 = __floats2bfloat162_rn(fmaxf(__uint_as_float(cur[8 * j + 2]) + b0.z, 0.0f),
-                                                                        fmaxf(__uint_as_float(cur[8 * j + 3]) + b0.w, 0.0f));
-                        const __nv_bfloat162 p2 = __floats2bfloat162_rn(fmaxf(__uint_as_float(cur[8 * j + 4]) + b1v.x, 0.0f),
-                                                                        fmaxf(__uint_as_float(cur[8 * j + 5]) + b1v.y, 0.0f));
-                        const __nv_bfloat162 p3 = __floats2bfloat162_rn(fmaxf(__uint_as_float(cur[8 * j + 6]) + b1v.z, 0.0f),
-                                                                        fmaxf(__uint_as_float(cur[8 * j + 7]) + b1v.w, 0.0f));
+                        __nv_bfloat162 p0, p1, p2, p3;
+                        if (p.fold_bias1) {
+                            // the accumulator already holds x W1^T + b1: round, then ReLU on the packed pair (rounding is
+                            // monotonic and keeps the sign, so max(round(x), 0) == round(max(x, 0))): 1 instruction per element
+                            const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.0f, 0.0f);
+                            p0 = __hmax2(__floats2bfloat162_rn(__uint_as_float(cur[8 * j + 0]), __uint_as_float(cur[8 * j + 1])), zero2);
+                            p1 = __hmax2(__floats2bfloat162_rn(__uint_as_float(cur[8 * j + 2]), __uint_as_float(cur[8 * j + 3])), zero2);
+                            p2 = __hmax2(__floats2bfloat162_rn(__uint_as_float(cur[8 * j + 4]), __uint_as_float(cur[8 * j + 5])), zero2);
+                            p3 = __hmax2(__floats2bfloat162_rn(__uint_as_float(cur[8 * j + 6]), __uint_as_float(cur[8 * j + 7])), zero2);
+                        } else {
+                            const float4 b0 = bb[2 * j], b1v = bb[2 * j + 1];
+                            p0 = __floats2bfloat162_rn(fmaxf(__uint_as_float(cur[8 * j + 0]) + b0.x, 0.0f),
+                                                       fmaxf(__uint_as_float(cur[8 * j + 1]) + b0.y, 0.0f));
+                            p1 = __floats2bfloat162_rn(fmaxf(__uint_as_float(cur[8 * j + 2]) + b0.z, 0.0f),
+                                                       fmaxf(__uint_as_float(cur[8 * j + 3]) + b0.w, 0.0f));
+                            p2 = __floats2bfloat162_rn(fmaxf(__uint_as_float(cur[8 * j + 4]) + b1v.x, 0.0f),
+                                                       fmaxf(__uint_as_float(cur[8 * j + 5]) + b1v.y, 0.0f));
+                            p3 = __floats2bfloat162_rn(fmaxf(__uint_as_float(cur[8 * j + 6]) + b1v.z, 0.0f),
+                                                       fmaxf(__uint_as_float(cur[8 * j + 7]) + b1v.w, 0.0f));
+                        }
                         // SWIZZLE_64B: 16-byte chunk index XOR address bits [7,9) = (row >> 1) & 3 (rows are 64 bytes)
                         const int chunk = j ^ ((lane >> 1) & 3);
                         st_shared_v4(slab + (uint32_t)(lane * 64 + chunk * 16), *reinterpret_cast<const uint32_t *>(&p0),
@@ -552,7 +566,7 @@ __global__ void __launch_bounds__(256) normalise_cast_kernel(const float *__rest
                                                               const float *__restrict__ denom,
                                                               __nv_bfloat16 *__restrict__ out,
                                                               const int64_t *__restrict__ row_index, int64_t capacity,
-                                                              uint32_t *__restrict__ flags) {
+                                                              uint32_t *__restrict__ flags, int ones_cols) {
     constexpr int Kp = NB * 64;
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -566,6 +580,10 @@ __global__ void __launch_bounds__(256) normalise_cast_kernel(const float *__rest
         const int c = 2 * (lane + 32 * j);
         mu[j] = make_float2(c < in_features ? mean[c] : 0.0f, c + 1 < in_features ? mean[c + 1] : 0.0f);
         rc[j] = make_float2(c < in_features ? __frcp_rn(denom[c]) : 0.0f, c + 1 < in_features ? __frcp_rn(denom[c + 1]) : 0.0f);
+        // the first `ones_cols` padding columns hold 1.0 (the layer-1 bias rides in the matching columns of W1, see
+        // cast_weight_kernel): x is read as 0 there, so (0 - (-1)) * 1 = 1
+        if (c >= in_features && c < in_features + ones_cols) { mu[j].x = -1.0f; rc[j].x = 1.0f; }
+        if (c + 1 >= in_features && c + 1 < in_features + ones_cols) { mu[j].y = -1.0f; rc[j].y = 1.0f; }
     }
     // row_index != NULL: destination row r reads source row row_index[r] (RandomMemory.sample_by_index fused into the
     // preprocessor); an index outside [0, capacity) reads row 0 and raises bit 1 of *flags
@@ -620,11 +638,11 @@ __global__ void __launch_bounds__(256) normalise_cast_kernel(const float *__rest
 template <bool VEC>
 static int launch_normalise_cast(int nb, int grid, cudaStream_t st, const float *x, int64_t x_stride, int64_t rows, int in_features,
                                  const float *mean, const float *denom, __nv_bfloat16 *out, const int64_t *row_index,
-                                 int64_t capacity, uint32_t *flags) {
+                                 int64_t capacity, uint32_t *flags, int ones_cols = 0) {
 #define AMP_CAST_CASE(NBV)                                                                                            \
     case NBV:                                                                                                         \
         normalise_cast_kernel<NBV, VEC><<<grid, 256, 0, st>>>(x, x_stride, rows, in_features, mean, denom, out,       \
-                                                              row_index, capacity, flags);                            \
+                                                              row_index, capacity, flags, ones_cols);                 \
         break
     switch (nb) {
         AMP_CAST_CASE(1); AMP_CAST_CASE(2); AMP_CAST_CASE(3); AMP_CAST_CASE(4); AMP_CAST_CASE(5); AMP_CAST_CASE(6);
@@ -636,13 +654,21 @@ static int launch_normalise_cast(int nb, int grid, cudaStream_t st, const float 
     return AMP_OK;
 }
 
-// fp32 master (rows, cols) -> bf16 (rows, cols_padded), zero padded
+// fp32 master (rows, cols) -> bf16 (rows, cols_padded), zero padded.  bias != NULL: the layer's bias is folded into the
+// product -- padding columns `cols` and `cols + 1` receive bias[r] split into a bf16 head and a bf16 tail (hi + lo carries
+// 16 mantissa bits; the input holds 1.0 in those two columns), so the accumulator already contains x W^T + b.
 __global__ void cast_weight_kernel(const float *__restrict__ w, int rows, int cols, int cols_padded,
-                                   __nv_bfloat16 *__restrict__ out) {
+                                   __nv_bfloat16 *__restrict__ out, const float *__restrict__ bias) {
     const int64_t total = (int64_t)rows * cols_padded;
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
         const int r = (int)(e / cols_padded), c = (int)(e - (int64_t)r * cols_padded);
-        out[e] = __float2bfloat16_rn(c < cols ? w[(int64_t)r * cols + c] : 0.0f);
+        float v = c < cols ? w[(int64_t)r * cols + c] : 0.0f;
+        if (bias && c >= cols && c < cols + 2) {
+            const float b = bias[r];
+            const float hi = __bfloat162float(__float2bfloat16_rn(b));
+            v = c == cols ? hi : b - hi;
+        }
+        out[e] = __float2bfloat16_rn(v);
     }
 }
 
@@ -702,6 +728,7 @@ struct amp_disc {
     CUtensorMap tmap_h_load, tmap_h_store;  // h1 workspace: 128-row loads, 32-row epilogue slab stores
     long long *prof;                        // AMP_DISC_PROFILE builds: device counters (ws_ctas x 8)
     bool use_pair;                          // CTA-pair (cta_group::2) kernel, opt-in with AMP_B200_DISC_PAIR=1
+    bool fold_bias1;                        // Kp - in_features >= 2: b1 rides in two padding columns of W1 (x_hat holds 1.0 there)
     bool loaded;
 };
 
@@ -729,6 +756,7 @@ int amp_disc_create(int32_t in_features, int32_t h1, int32_t h2, int64_t max_row
     d->device = dev;
     d->in_features = in_features;
     d->Kp = (in_features + BK - 1) / BK * BK;
+    d->fold_bias1 = d->Kp - in_features >= 2 && !(getenv("AMP_B200_DISC_NO_FOLD") && getenv("AMP_B200_DISC_NO_FOLD")[0] == '1');
     d->h1 = h1;
     d->h2 = h2;
     // Rows per launch ("chunk").  Measured (tools/sweep_disc.py, 1 M rows): 2 / 4 / 8 / 16 / 32 tiles per CTA per launch give
@@ -818,8 +846,8 @@ int amp_disc_load(amp_disc_t *d, const float *W1, const float *b1, const float *
     AMP_REQUIRE(d && W1 && b1 && W2 && b2 && W3 && b3 && running_mean && running_variance, "amp_disc_load: NULL argument");
     cudaStream_t st = as_stream(stream);
     const int blocks = sm_count() * 4;
-    cast_weight_kernel<<<blocks, 256, 0, st>>>(W1, d->h1, d->in_features, d->Kp, d->W1);
-    cast_weight_kernel<<<blocks, 256, 0, st>>>(W2, d->h2, d->h1, d->h1, d->W2);
+    cast_weight_kernel<<<blocks, 256, 0, st>>>(W1, d->h1, d->in_features, d->Kp, d->W1, d->fold_bias1 ? b1 : nullptr);
+    cast_weight_kernel<<<blocks, 256, 0, st>>>(W2, d->h2, d->h1, d->h1, d->W2, nullptr);
     AMP_CUDA_TRY(cudaGetLastError());
     AMP_CUDA_TRY(cudaMemcpyAsync(d->b1, b1, (size_t)d->h1 * 4, cudaMemcpyDeviceToDevice, st));
     AMP_CUDA_TRY(cudaMemcpyAsync(d->b2, b2, (size_t)d->h2 * 4, cudaMemcpyDeviceToDevice, st));
@@ -861,10 +889,11 @@ static int style_reward_impl(amp_disc_t *d, const float *x, int64_t x_stride, co
         const int64_t *ic = row_index ? row_index + r0 : nullptr;
         const bool vec = (x_stride % 2 == 0) && ((reinterpret_cast<uintptr_t>(xc) & 7u) == 0);
         const int cast_grid = (int)std::min<int64_t>((rows + 7) / 8, (int64_t)sms * 8);
+        const int ones = d->fold_bias1 ? 2 : 0;
         int rc = vec ? launch_normalise_cast<true>(d->Kp / BK, cast_grid, cs, xc, x_stride, rows, d->in_features, d->mean, d->denom,
-                                                   d->xhat[b], ic, capacity, flags)
+                                                   d->xhat[b], ic, capacity, flags, ones)
                      : launch_normalise_cast<false>(d->Kp / BK, cast_grid, cs, xc, x_stride, rows, d->in_features, d->mean, d->denom,
-                                                    d->xhat[b], ic, capacity, flags);
+                                                    d->xhat[b], ic, capacity, flags, ones);
         if (rc != AMP_OK) return rc;
         AMP_CUDA_TRY(cudaGetLastError());
         if (overlap) AMP_CUDA_TRY(cudaEventRecord(d->ev_ready[b], cs));
@@ -889,7 +918,8 @@ static int style_reward_impl(amp_disc_t *d, const float *x, int64_t x_stride, co
         FusedParams fp{};
         fp.M = (int)rows;
         fp.kb1 = d->Kp / BK;
-        fp.ksteps1_last = (d->in_features - BK * (fp.kb1 - 1) + UMMA_K - 1) / UMMA_K;
+        fp.fold_bias1 = d->fold_bias1 ? 1 : 0;
+        fp.ksteps1_last = (d->in_features + (d->fold_bias1 ? 2 : 0) - BK * (fp.kb1 - 1) + UMMA_K - 1) / UMMA_K;
         fp.n1_tiles = d->h1 / BN;
         fp.n2_tiles = d->h2 / BN;
         fp.b1 = d->b1;

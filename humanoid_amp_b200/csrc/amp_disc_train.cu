@@ -632,18 +632,23 @@ __global__ void sumsq_kernel(const float *__restrict__ x, int n, float *__restri
 
 template <bool A_MN, bool B_MN, int EPI>
 static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const GemmParams &p, cudaStream_t st) {
-    static bool configured = false;
-    auto kern = train_gemm_kernel<A_MN, B_MN, EPI>;
-    if (!configured) {
-        AMP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-        configured = true;
-    }
+    auto kern = train_gemm_kernel<A_MN, B_MN, EPI>;  // dynamic shared memory opt-in: configure_gemm_kernels(), at create
     const int items = p.m_tiles * p.n_tiles * p.splits;
     if (items <= 0) return AMP_OK;
     const int grid = std::min(items, sm_count());
     kern<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(ta, tb, p);
     AMP_CUDA_TRY(cudaGetLastError());
     return AMP_OK;
+}
+
+// every instantiation the step launches, for the CURRENT device (the attribute is per device; amp_disc_train_create calls
+// this, so a captured CUDA graph never contains a first-use configuration call)
+static cudaError_t configure_gemm_kernels() {
+    cudaError_t e = cudaFuncSetAttribute(train_gemm_kernel<false, false, EPI_BIAS_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(train_gemm_kernel<false, false, EPI_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(train_gemm_kernel<false, false, EPI_SCALE_SUMSQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(train_gemm_kernel<true, true, EPI_SLICE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+    return e;
 }
 
 }  // namespace train
@@ -717,6 +722,13 @@ int amp_disc_train_create(int32_t in_features, int32_t h1, int32_t h2, int64_t m
         if (e != cudaSuccess) {
             amp_disc_train_destroy(t);
             return cuda_fail(e, "cudaMalloc(amp_disc_train_create)");
+        }
+    }
+    {
+        cudaError_t e = configure_gemm_kernels();
+        if (e != cudaSuccess) {
+            amp_disc_train_destroy(t);
+            return cuda_fail(e, "cudaFuncSetAttribute(train_gemm_kernel)");
         }
     }
     if ((size_t)32 * h2 * 2 > 48 * 1024) {  // head_kernel keeps a 32-row tile of a2 in shared memory

@@ -145,6 +145,48 @@ def test_with_running_standard_scaler_in_train_mode():
         compare(got, ref, 6e-3, name)  # a normalised value on a bf16 rounding boundary may round the other way
 
 
+def test_whole_update_replays_as_a_cuda_graph():
+    """Staging + loss + gradients enqueue only stream work (no host synchronisation, no allocation in the library), so one
+    mini-batch update with static buffers is capturable; the replay must reproduce the eager result and track new inputs
+    written into the same buffers."""
+    import humanoid_amp_b200 as amp
+
+    in_features, hidden, B = 166, (1024, 512), 512
+    W, b, batches = make_problem(in_features, hidden, B, seed=41)
+    W, b = [w.to(DEV) for w in W], [x.to(DEV) for x in b]
+    bufs = [x.to(DEV).clone() for x in batches]
+    gW, gb = [torch.zeros_like(w) for w in W], [torch.zeros_like(x) for x in b]
+    scaler = amp.RunningStandardScaler(in_features, device=DEV)
+    scaler.update(torch.cat(bufs))
+    upd = amp.AmpDiscriminatorUpdate(in_features, hidden, max_batch_rows=B, device=DEV)
+    terms_box = {}
+
+    def step():
+        terms_box["t"] = upd(W, b, *bufs, scaler=scaler, train=False, grad_weights=gW, grad_biases=gb)[0]
+
+    step()
+    eager = [g.clone() for g in gW + gb]
+    graph = amp.capture_step(step, DEV)
+    for g in gW + gb:
+        g.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    for got, ref in zip(gW + gb, eager):
+        compare(got, ref, 1e-5, "graph replay vs eager")  # atomics order only
+    # new data in the same buffers: the replay follows
+    _, _, fresh = make_problem(in_features, hidden, B, seed=42)
+    for dst, src in zip(bufs, fresh):
+        dst.copy_(src)
+    graph.replay()
+    torch.cuda.synchronize()
+    replayed = [g.clone() for g in gW + gb]
+    step()
+    torch.cuda.synchronize()
+    for got, ref in zip(replayed, gW + gb):
+        compare(got, ref, 1e-5, "graph replay on new inputs vs eager")
+    assert not torch.allclose(replayed[0], eager[0])
+
+
 def test_errors():
     import humanoid_amp_b200 as amp
 

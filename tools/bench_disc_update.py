@@ -95,12 +95,15 @@ def main():
         upd.loss_and_grads(W, b, gW, gb)
 
     ms_eval_scaler = time_cuda(staged_only, a.steps, a.warmup)
+    graph = amp.capture_step(staged_only, dev)
+    ms_graph = time_cuda(graph.replay, a.steps, a.warmup)
     out = {
         "what": "discriminator loss + gradients (skrl AMP._update block), one step",
         "config": {"in_features": n_in, "hidden": [h1, h2], "rows_per_source": B, "sources": 3},
         "algorithmic_gflop": flops / 1e9,
         "ms_step_with_scaler_update": ms_full,
         "ms_step_scaler_eval": ms_eval_scaler,
+        "ms_step_scaler_eval_cuda_graph": ms_graph,
         "tflops_step_with_scaler_update": flops / ms_full / 1e9,
         "tflops_step_scaler_eval": flops / ms_eval_scaler / 1e9,
     }
