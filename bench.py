@@ -283,7 +283,7 @@ def run_ours(args, spec, rank, world, local_rank):
         disc.style_reward(rows_for_reward, out=reward)
         exchange_gradients()
 
-    launches_per_step = 1 + (1 if state is not None else 0) + 2 * ((reward_rows + disc.chunk_rows - 1) // disc.chunk_rows)
+    launches_per_step = 1 + (1 if state is not None else 0) + disc.launch_count(reward_rows)
     launches_per_step += 1 if bucket is not None else 0  # the peer-memory all-reduce kernel
 
     def sync_all():

@@ -79,6 +79,7 @@ SIGNATURES = {
     "amp_disc_create": (C.c_int, [_I32, _I32, _I32, _I64, _P, C.POINTER(_P)]),
     "amp_disc_destroy": (C.c_int, [_P]),
     "amp_disc_chunk_rows": (C.c_int64, [_P]),
+    "amp_disc_launch_count": (C.c_int64, [_P, _I64]),
     "amp_disc_load": (C.c_int, [_P] * 9 + [_P]),
     "amp_disc_style_reward": (C.c_int, [_P, _P, _I64, _I64, _F32, _P, _P, _P]),
     "amp_disc_style_reward_indexed": (C.c_int, [_P, _P, _I64, _I64, _P, _I64, _F32, _P, _P, _P, _P]),

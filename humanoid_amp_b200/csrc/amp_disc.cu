@@ -735,6 +735,10 @@ struct amp_disc {
 using namespace amp;
 using namespace amp::disc;
 
+struct ChunkPlan;
+static ChunkPlan plan_chunks(const amp_disc *d, int64_t M);
+static int64_t chunk_count(const amp_disc *d, int64_t M);
+
 extern "C" {
 
 int amp_disc_create(int32_t in_features, int32_t h1, int32_t h2, int64_t max_rows, void *stream, amp_disc_t **out) {
@@ -841,6 +845,8 @@ int amp_disc_destroy(amp_disc_t *d) {
 
 int64_t amp_disc_chunk_rows(const amp_disc_t *d) { return d ? d->chunk_rows : 0; }
 
+int64_t amp_disc_launch_count(const amp_disc_t *d, int64_t M) { return (d && M > 0) ? 2 * chunk_count(d, M) : 0; }
+
 int amp_disc_load(amp_disc_t *d, const float *W1, const float *b1, const float *W2, const float *b2, const float *W3,
                   const float *b3, const double *running_mean, const double *running_variance, void *stream) {
     AMP_REQUIRE(d && W1 && b1 && W2 && b2 && W3 && b3 && running_mean && running_variance, "amp_disc_load: NULL argument");
@@ -862,6 +868,31 @@ int amp_disc_load(amp_disc_t *d, const float *W1, const float *b1, const float *
 
 }  // extern "C"
 
+// Chunk plan of an M-row batch.  One chunk when M fits a workspace buffer, else equal big chunks; optionally a short LEAD-IN
+// chunk first (AMP_B200_DISC_LEAD_TILES row tiles per CTA): the scaler/cast of chunk c+1 hides under the fused kernel of
+// chunk c but the cast of chunk 0 has nothing to hide under.  Measured on the 1 M-row bench: 0 / 2 / 4 / 8 lead-in tiles ->
+// 1.396 / 1.469 / 1.415 / 1.401 ms -- the extra launch (prologue + tail) costs what the smaller first cast saves, so the
+// default is no lead-in.
+struct ChunkPlan {
+    int64_t n, lead, big;  // number of chunks, rows of the lead-in chunk (0 = none), rows of every following chunk
+    int64_t start(int64_t c) const { return c == 0 ? 0 : (lead ? lead + (c - 1) * big : c * big); }
+};
+static ChunkPlan plan_chunks(const amp_disc *d, int64_t M) {
+    ChunkPlan p{1, 0, d->chunk_rows};
+    if (M <= d->chunk_rows) return p;
+    const int64_t wave_rows = (int64_t)d->ws_ctas * BM;
+    int64_t lead_tiles = 0;
+    if (const char *t = getenv("AMP_B200_DISC_LEAD_TILES")) lead_tiles = std::max(0, atoi(t));  // tuning knob, 0 = no lead-in
+    p.lead = std::min<int64_t>(lead_tiles * wave_rows, d->chunk_rows / 4) / wave_rows * wave_rows;
+    const int64_t rest = M - p.lead;
+    const int64_t k = (rest + d->chunk_rows - 1) / d->chunk_rows;
+    p.big = std::min<int64_t>(d->chunk_rows, ((rest + k - 1) / k + wave_rows - 1) / wave_rows * wave_rows);
+    p.n = (p.lead ? 1 : 0) + (rest + p.big - 1) / p.big;
+    return p;
+}
+
+static int64_t chunk_count(const amp_disc *d, int64_t M) { return plan_chunks(d, M).n; }
+
 // x rows are taken in order (row_index == NULL) or gathered: row r of the batch = x[row_index[r]] with x holding `capacity` rows
 static int style_reward_impl(amp_disc_t *d, const float *x, int64_t x_stride, const int64_t *row_index, int64_t capacity,
                              uint32_t *flags, int64_t M, float reward_scale, float *reward, float *logits, void *stream) {
@@ -873,7 +904,8 @@ static int style_reward_impl(amp_disc_t *d, const float *x, int64_t x_stride, co
                 d->in_features);
     cudaStream_t st = as_stream(stream);
     const int sms = sm_count();
-    const int64_t n_chunks = (M + d->chunk_rows - 1) / d->chunk_rows;
+    const ChunkPlan plan = plan_chunks(d, M);
+    const int64_t n_chunks = plan.n;
     AMP_REQUIRE(n_chunks == 1 || d->xhat[1], "amp_disc_style_reward: %lld rows exceed the max_rows given to amp_disc_create",
                 (long long)M);
     // With several chunks the scaler/cast of chunk c+1 runs on the handle's side stream underneath the fused kernel of
@@ -882,7 +914,7 @@ static int style_reward_impl(amp_disc_t *d, const float *x, int64_t x_stride, co
     const bool overlap = n_chunks > 1;
     auto issue_cast = [&](int64_t c) -> int {
         const int b = (int)(c & 1);
-        const int64_t r0 = c * d->chunk_rows, rows = std::min<int64_t>(d->chunk_rows, M - r0);
+        const int64_t r0 = plan.start(c), rows = std::min<int64_t>(plan.start(c + 1), M) - r0;
         cudaStream_t cs = overlap ? d->side : st;
         if (overlap && c >= 2) AMP_CUDA_TRY(cudaStreamWaitEvent(cs, d->ev_free[b], 0));  // fused(c-2) is done with xhat[b]
         const float *xc = row_index ? x : x + r0 * x_stride;
@@ -907,7 +939,7 @@ static int style_reward_impl(amp_disc_t *d, const float *x, int64_t x_stride, co
     if (rc != AMP_OK) return rc;
     for (int64_t c = 0; c < n_chunks; ++c) {
         const int b = (int)(c & 1);
-        const int64_t r0 = c * d->chunk_rows, rows = std::min<int64_t>(d->chunk_rows, M - r0);
+        const int64_t r0 = plan.start(c), rows = std::min<int64_t>(plan.start(c + 1), M) - r0;
         if (c + 1 < n_chunks && (rc = issue_cast(c + 1)) != AMP_OK) return rc;
         if (overlap) AMP_CUDA_TRY(cudaStreamWaitEvent(st, d->ev_ready[b], 0));
         const int m_tiles = (int)((rows + BM - 1) / BM);

@@ -33,6 +33,10 @@ class AmpDiscriminator:
         self._masters = None
         self.chunk_rows = int(lib.amp_disc_chunk_rows(h))  # rows per internal chunk: 2 kernel launches each (cast + fused two-layer kernel)
 
+    def launch_count(self, rows: int) -> int:
+        """Kernel launches one ``style_reward`` call over ``rows`` rows issues (two per internal chunk)."""
+        return int(_lib.load().amp_disc_launch_count(self._h, int(rows)))
+
     def load(self, weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor], running_mean: torch.Tensor, running_variance: torch.Tensor) -> None:
         """Refresh the staged copies from ``[W1 (h1,in), W2 (h2,h1), W3 (1,h2)]``, ``[b1, b2, b3]`` (torch.nn.Linear layout)
         and the ``RunningStandardScaler`` buffers (float64).  Call after every optimiser step that changed them."""

@@ -196,6 +196,8 @@ AMP_API int amp_disc_create(int32_t in_features, int32_t h1, int32_t h2, int64_t
 AMP_API int amp_disc_destroy(amp_disc_t *d);
 /* Rows processed per internal chunk (two kernel launches per chunk: scaler + cast, fused MLP); 0 for a NULL handle. */
 AMP_API int64_t amp_disc_chunk_rows(const amp_disc_t *d);
+/* Kernel launches amp_disc_style_reward issues for a batch of M rows (two per chunk). */
+AMP_API int64_t amp_disc_launch_count(const amp_disc_t *d, int64_t M);
 /* Refresh the staged bf16 weights / fp32 biases / scaler statistics from the fp32 masters the trainer owns
  * (device pointers; W row-major (out,in) as torch.nn.Linear stores them; mean/var are the scaler's float64 buffers). */
 AMP_API int amp_disc_load(amp_disc_t *d, const float *W1, const float *b1, const float *W2, const float *b2, const float *W3,

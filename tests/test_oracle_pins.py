@@ -120,3 +120,29 @@ def test_oracle_vs_live_reference_full_clip(name, kat):
         # values quoted (rounded) in SURVEY.md 8c
         assert np.allclose(g["obs_row_sums"][:3], [2.52549723, 2.555956552, 2.592755598], atol=1e-8)
         assert HUMANOID28.reference_body == "torso"
+
+
+def test_upstream_quaternion_helpers_against_an_independent_library():
+    """``quat_apply`` / ``quat_rotate_inverse`` are upstream Isaac Lab functions that are not vendored with the reference
+    (parity unpinned).  As a known-answer check from an INDEPENDENT implementation, the restatements must agree with
+    scipy's ``Rotation`` (float64) to fp32 rounding on random unit quaternions -- this pins the convention (wxyz, active
+    rotation for ``quat_apply``, the inverse rotation for ``quat_rotate_inverse``), which is what a restatement can get wrong."""
+    import torch
+    from scipy.spatial.transform import Rotation
+
+    from oracle import env_oracle
+
+    rng = np.random.default_rng(7)
+    q = rng.normal(size=(4096, 4))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    v = rng.uniform(-3, 3, size=(4096, 3))
+    rot = Rotation.from_quat(q[:, [1, 2, 3, 0]])  # scipy is xyzw
+    qt, vt = torch.from_numpy(q.astype(np.float32)), torch.from_numpy(v.astype(np.float32))
+    fwd = env_oracle.quat_apply(qt, vt).double().numpy()
+    inv = env_oracle.quat_rotate_inverse(qt, vt).double().numpy()
+    assert np.abs(fwd - rot.apply(v)).max() < 5e-6
+    assert np.abs(inv - rot.inv().apply(v)).max() < 5e-6
+    # tangent / normal = first and third column of the rotation matrix (g1_amp_env.py:489-497)
+    tn = env_oracle.quaternion_to_tangent_and_normal(qt).double().numpy()
+    R = rot.as_matrix()
+    assert np.abs(tn[:, :3] - R[:, :, 0]).max() < 5e-6 and np.abs(tn[:, 3:] - R[:, :, 2]).max() < 5e-6
