@@ -90,7 +90,7 @@ SIGNATURES = {
     "amp_scaler_apply": (C.c_int, [_P, _I64, _I64, _I32, _P, _P, _F32, _F32, _P, _I64, _P]),
     "amp_disc_train_create": (C.c_int, [_I32, _I32, _I32, _I64, _P, C.POINTER(_P)]),
     "amp_disc_train_destroy": (C.c_int, [_P]),
-    "amp_disc_train_stage": (C.c_int, [_P, _I32, _P, _I64, _I64, _I64, _P, _P, _P]),
+    "amp_disc_train_stage": (C.c_int, [_P, _I32, _P, _I64, _I64, _P, _P, _P]),
     "amp_disc_train_step": (C.c_int, [_P] * 7 + [_I64, _F32, _F32, _F32, _F32] + [_P] * 9),
     "amp_bucket_create": (C.c_int, [_I64, _I32, _I32, C.POINTER(_P)]),
     "amp_bucket_destroy": (C.c_int, [_P]),

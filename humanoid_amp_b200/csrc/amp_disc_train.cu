@@ -742,12 +742,12 @@ int amp_disc_train_create(int32_t in_features, int32_t h1, int32_t h2, int64_t m
     return AMP_OK;
 }
 
-int amp_disc_train_stage(amp_disc_train_t *t, int32_t source, const float *x, int64_t x_stride, int64_t rows, int64_t batch_rows,
+int amp_disc_train_stage(amp_disc_train_t *t, int32_t source, const float *x, int64_t x_stride, int64_t batch_rows,
                          const double *running_mean, const double *running_variance, void *stream) {
+    const int64_t rows = batch_rows;
     AMP_REQUIRE(t && source >= 0 && source < 3, "amp_disc_train_stage: bad handle or source %d (0 agent, 1 replay, 2 motion)", source);
     AMP_REQUIRE(batch_rows >= 1 && batch_rows <= t->max_batch, "amp_disc_train_stage: batch_rows %lld outside [1, %lld]",
                 (long long)batch_rows, (long long)t->max_batch);
-    AMP_REQUIRE(rows == batch_rows, "amp_disc_train_stage: rows (%lld) must equal batch_rows (%lld)", (long long)rows, (long long)batch_rows);
     AMP_REQUIRE(x && x_stride >= t->in_features, "amp_disc_train_stage: NULL x or x_stride < in_features");
     AMP_REQUIRE((running_mean == nullptr) == (running_variance == nullptr), "amp_disc_train_stage: give both scaler buffers or neither");
     cudaStream_t st = as_stream(stream);

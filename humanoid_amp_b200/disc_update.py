@@ -71,7 +71,7 @@ class AmpDiscriminatorUpdate:
                 scaler.update(x)
             mean, var = scaler.running_mean, scaler.running_variance
         lib, stream = _lib.enter(self.device)
-        _lib.check(lib.amp_disc_train_stage(self._h, int(source), _lib.ptr(x), x.stride(0), rows, rows, _lib.ptr(mean), _lib.ptr(var), stream))
+        _lib.check(lib.amp_disc_train_stage(self._h, int(source), _lib.ptr(x), x.stride(0), rows, _lib.ptr(mean), _lib.ptr(var), stream))
         self._keep.append(x)
 
     # ---- the step --------------------------------------------------------------------------------------------------
@@ -100,13 +100,13 @@ class AmpDiscriminatorUpdate:
         terms = torch.empty(6, dtype=torch.float32, device=dev)
         logits = torch.empty(3 * Bp, dtype=torch.float32, device=dev) if return_logits else None
         lib, stream = _lib.enter(dev)
+        self._batch_rows = None  # whatever happens next, the following step starts from fresh staging
         _lib.check(lib.amp_disc_train_step(
             self._h, _lib.ptr(W[0]), _lib.ptr(b[0]), _lib.ptr(W[1]), _lib.ptr(b[1]), _lib.ptr(W[2]), _lib.ptr(b[2]), B,
             self.discriminator_loss_scale, self.discriminator_logit_regularization_scale,
             self.discriminator_gradient_penalty_scale, self.discriminator_weight_decay_scale,
             _lib.ptr(gW[0]), _lib.ptr(gb[0]), _lib.ptr(gW[1]), _lib.ptr(gb[1]), _lib.ptr(gW[2]), _lib.ptr(gb[2]),
             _lib.ptr(terms), _lib.ptr(logits), stream))
-        self._batch_rows = None
         self._keep = [W, b]
         if return_logits:
             return terms, gW, gb, logits.view(3, Bp)[:, :B]

@@ -224,12 +224,13 @@ AMP_API int amp_disc_train_create(int32_t in_features, int32_t h1, int32_t h2, i
                                   amp_disc_train_t **out);
 AMP_API int amp_disc_train_destroy(amp_disc_train_t *t);
 /* Stage one of the three batches of the step: source 0 = agent AMP states (rollout memory), 1 = replay buffer, 2 = motion
- * dataset.  x device f32 (rows, in_features), row stride x_stride floats; rows must equal batch_rows.
+ * dataset.  x device f32 (batch_rows, in_features), row stride x_stride floats; the three sources of a step have the same
+ * batch_rows.
  * running_mean / running_variance: the amp_state_preprocessor's float64 buffers AFTER its train-mode update for this batch
  * (skrl calls the preprocessor with train=True on each batch in turn; use amp_scaler_update for that) -- the rows are
  * normalised, clipped to +-5 and rounded to bf16; both NULL = x is already normalised. */
-AMP_API int amp_disc_train_stage(amp_disc_train_t *t, int32_t source, const float *x, int64_t x_stride, int64_t rows,
-                                 int64_t batch_rows, const double *running_mean, const double *running_variance, void *stream);
+AMP_API int amp_disc_train_stage(amp_disc_train_t *t, int32_t source, const float *x, int64_t x_stride, int64_t batch_rows,
+                                 const double *running_mean, const double *running_variance, void *stream);
 /* Loss and gradients of  loss_scale * (0.5 (BCE(cat(agent, replay), 0) + BCE(motion, 1)) + logit_reg * |W3|^2
  *                                      + grad_penalty * mean_rows |d logit / d motion_state|^2 + weight_decay * sum |W|^2)
  * for the three staged batches.  W1 (h1,in) b1 W2 (h2,h1) b2 W3 (1,h2) b3: fp32 masters, device, torch.nn.Linear layout.
