@@ -145,6 +145,31 @@ def test_with_running_standard_scaler_in_train_mode():
         compare(got, ref, 6e-3, name)  # a normalised value on a bf16 rounding boundary may round the other way
 
 
+def test_full_minibatch_size_through_a_size_independent_property():
+    """skrl's full mini-batch (rollouts 16 x 4096 envs / 2 mini-batches = 32 768 rows per source, what the update sees when
+    ``discriminator_batch_size`` is 0) is too large for the CPU oracle to finish in seconds.  Property: every loss term is a
+    MEAN over rows or does not depend on the rows, so the gradient of the whole batch equals the average of the gradients
+    of its two halves (each half paired across the three sources)."""
+    import humanoid_amp_b200 as amp
+
+    in_features, hidden, B = 830, (1024, 512), 32768
+    W, b, batches = make_problem(in_features, hidden, B, seed=77)
+    W, b = [w.to(DEV) for w in W], [x.to(DEV) for x in b]
+    batches = [x.to(DEV) for x in batches]
+    upd = amp.AmpDiscriminatorUpdate(in_features, hidden, max_batch_rows=B, device=DEV)
+    t_full, gW, gb = upd(W, b, *batches)
+    full = [g.clone() for g in gW + gb]
+    halves = []
+    for sl in (slice(0, B // 2), slice(B // 2, B)):
+        t_half, hW, hb = upd(W, b, *[x[sl] for x in batches])
+        halves.append(([g.clone() for g in hW + hb], t_half.clone()))
+    for i, name in enumerate(["gW1", "gW2", "gW3", "gb1", "gb2", "gb3"]):
+        compare(full[i], 0.5 * (halves[0][0][i] + halves[1][0][i]), 2e-3, f"{name}: whole batch vs mean of halves")
+    t = 0.5 * (halves[0][1] + halves[1][1])
+    assert torch.allclose(t_full, t, rtol=2e-3, atol=1e-5)
+    assert bool(torch.isfinite(t_full).all())
+
+
 def test_whole_update_replays_as_a_cuda_graph():
     """Staging + loss + gradients enqueue only stream work (no host synchronisation, no allocation in the library), so one
     mini-batch update with static buffers is capturable; the replay must reproduce the eager result and track new inputs
