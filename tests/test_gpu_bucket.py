@@ -69,3 +69,34 @@ def test_peer_memory_allreduce_matches_nccl_world2():
     rec = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
     assert rec["ok"], rec["notes"]
     assert rec["world"] == 2
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs on the box (run with gpurun --gpus 2)")
+def test_second_device_from_one_process():
+    """One process driving two GPUs (the current device stays cuda:0): every entry point must launch on the tensor's device
+    -- the shims call amp_set_device before each call, kernel attributes are configured per device."""
+    import numpy as np
+
+    import humanoid_amp_b200 as amp
+    from conftest import clip_path
+    from humanoid_amp_b200.synthetic import skrl_style_discriminator_params
+
+    results = []
+    for dev in ("cuda:0", "cuda:1"):
+        clip = clip_path("G1_walk")
+        env = amp.AmpEnvPath(amp.AmpEnvCfg(motion_file=clip, num_envs=64, num_amp_observations=2, robot=amp.G1), dev)
+        rng = np.random.default_rng(0)
+        times = rng.uniform(0, 0.6, 2048)
+        obs = env.collect_reference_motions(2048, times, np.zeros(2048, dtype=np.int64))
+        W, b = skrl_style_discriminator_params(166, seed=3)
+        disc = amp.AmpDiscriminator(166, device=dev, max_rows=2048)
+        disc.load(W, b, torch.zeros(166, dtype=torch.float64), torch.ones(166, dtype=torch.float64))
+        reward = disc.style_reward(obs)
+        upd = amp.AmpDiscriminatorUpdate(166, (1024, 512), max_batch_rows=512, device=dev)
+        _, gW, gb = upd(W, b, obs[:512], obs[512:1024], obs[1024:1536])
+        assert obs.device == torch.device(dev) and reward.device == torch.device(dev) and gW[0].device == torch.device(dev)
+        results.append((obs.cpu(), reward.cpu(), gW[0].cpu(), gb[0].cpu()))
+    assert torch.cuda.current_device() == 0
+    assert torch.equal(results[0][0], results[1][0]) and torch.equal(results[0][1], results[1][1])
+    assert torch.allclose(results[0][2], results[1][2], rtol=1e-4, atol=1e-7)
+    assert torch.allclose(results[0][3], results[1][3], rtol=1e-4, atol=1e-7)
