@@ -45,10 +45,10 @@ METRIC = "amp_obs_samples_per_s(sample+obs+disc_reward)"
 UNIT = "samples/s"
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of the DEFAULT workload
-# (profiles/r01_ncu_full_v4_collect_cast.metrics.txt, profiles/r01_ncu_fused_dram_with_l2_hints.csv); None for other workloads
+# (profiles/r01_ncu_full_v4_collect_cast.metrics.txt, profiles/r01_ncu_full_v5_step.metrics.txt); None for other workloads
 NCU_TRAFFIC_BYTES = {
     "collect_reference_kernel": 16_283_392 + 605_972_736,  # 1 M samples x K=2 (algorithmic 680 MB; the tail still sat in L2)
-    "disc_fused_kernel": 278_443_520 + 534_667_520,        # one 500 k-row launch: x_hat read + h1 slot write-backs
+    "disc_fused_kernel": 254_728_448 + 549_733_376,        # one 500 k-row launch: x_hat read + h1 slot write-backs
 }
 
 WORKLOADS = {
