@@ -187,6 +187,42 @@ def cpu_reference_pass(spec, clip_files, n_cpu, steps, warmup, seed=0):
     return n_cpu / dt, dt * 1e3, torch.get_num_threads(), f"{n_cpu} of {spec['n']} samples x K={K} per step, oracle port (fp32 CPU torch), {steps} steps after {warmup} warm-up"
 
 
+def torch_gpu_reference_pass(spec, clip_files, n, steps, warmup, dev, seed=0):
+    """SURVEY.md 8d's optional second baseline: the SAME reference algorithm (oracle port) with its tensors on the B200, i.e.
+    torch eager on the GPU -- what a user of the reference runs today.  Host index math + ~200 ATen launches + H2D copies per
+    step, fp32 cuBLAS for the discriminator.  Timed with CUDA events around `steps` whole passes."""
+    from humanoid_amp_b200.robots import robot_for_clip
+    from humanoid_amp_b200.synthetic import skrl_style_discriminator_params
+    from oracle import OracleDiscriminator, OracleMotionLoader, env_oracle
+
+    ora = OracleMotionLoader(clip_files.split(","), device=dev)
+    robot = robot_for_clip(ora.dof_names)
+    K = spec["K"]
+    width = K * robot.amp_observation_space
+    W, b = skrl_style_discriminator_params(width, seed=42, logit_gain=5.0)
+    disc = OracleDiscriminator(width, weights=W, biases=b, device=dev)
+    dof_idx = ora.get_dof_index(robot.joint_names)
+    ref_idx = ora.get_body_index([robot.reference_body])[0]
+    key_idx = ora.get_body_index(robot.key_body_names)
+    ids, times = host_inputs(ora.durations, n, seed)
+
+    def one():
+        obs = env_oracle.collect_reference_motions(ora, n, K, dof_idx, ref_idx, key_idx, current_times=times, motion_ids=ids)
+        rows = obs if spec["reward_mult"] == 1 else obs.repeat(spec["reward_mult"], 1)
+        return disc.style_reward(rows)
+
+    for _ in range(warmup):
+        one()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    torch.cuda.synchronize(dev)
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": n / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "kind": "oracle port on device=cuda (torch eager, fp32)",
+            "sample": f"{n} samples x K={K} per step, {steps} steps after {warmup} warm-up, wall clock with synchronize on both sides"}
+
+
 def run_reference(args, spec, rank, world):
     if rank != 0:
         return
@@ -439,6 +475,11 @@ def run_ours(args, spec, rank, world, local_rank):
             n_cpu = min(n, 262144)  # bounded sample: ~0.6 s per step on 16 cores -> ~6-10 s of CPU work in total
             v, ms, threads, sample = cpu_reference_pass(spec, clip_files, n_cpu, steps=10 if n_cpu >= 65536 else 30, warmup=1)
             cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "ms_per_step": ms}
+        torch_gpu = None
+        if world == 1 and args.torch_gpu_baseline:
+            del obs, reward  # give the eager pass (tens of full-size temporaries) the memory back
+            torch.cuda.empty_cache()
+            torch_gpu = torch_gpu_reference_pass(spec, clip_files, n, steps=5, warmup=2, dev=dev)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if spec["strong"] else "weak", "vs_baseline": None,
@@ -450,6 +491,7 @@ def run_ours(args, spec, rank, world, local_rank):
                 "launch": "cuda_graph replay per stage" if use_graph else "eager (Python -> ctypes -> C ABI)",
             },
             "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu,
+            **({"torch_gpu_baseline": torch_gpu} if torch_gpu is not None else {}),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 16, "d2h_bytes_per_step": reward_rows * 4,
                     "mode": "double-buffered host staging: H2D of step i+1 and D2H of step i-1 overlap step i's kernels" if pipelined
                     else "serial: H2D -> kernels -> D2H -> sync every step",
@@ -473,6 +515,8 @@ def main():
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="refill_1m")
     ap.add_argument("--samples", type=int, default=0, help="override samples per GPU (debugging)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--torch-gpu-baseline", action="store_true",
+                    help="also time the reference algorithm as torch eager on this GPU (SURVEY 8d's optional second baseline)")
     ap.add_argument("--no-graph", action="store_true", help="launch the small workloads eagerly instead of replaying CUDA graphs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
