@@ -580,8 +580,11 @@ __global__ void tangent_normal_kernel(const float *__restrict__ q, int64_t n, fl
 // then all stores.  History: slot s -> s+1 for s = K-2 .. 0 (oldest first, eight slots per trip: nothing is overwritten
 // before it is read; a lane touches only its own columns, so there is no cross-lane hazard), then slot 0 = the new row.
 // Reference g1_amp_env.py:176-193.
+// Register budget: at 64 registers (4 CTAs/SM) the 3-slot instantiation (A = 81 / 83, every shipped robot) spilled its loaded
+// values to local memory inside the env loop -- ncu: 30 % of all stall samples on one STL waiting for the load it spills, i.e.
+// one load in flight at a time.  128 registers (2 CTAs/SM) keep every load of an env in flight together.
 template <int NSLOT>
-__global__ void __launch_bounds__(256, NSLOT <= 3 ? 4 : 2)
+__global__ void __launch_bounds__(256, 2)
 obs_step_kernel(const float *__restrict__ joint_pos, const float *__restrict__ joint_vel,
                 const float *__restrict__ body_pos, const float *__restrict__ body_quat,
                 const float *__restrict__ body_lin, const float *__restrict__ body_ang, int64_t N, int D, int Bsim,
@@ -618,31 +621,35 @@ obs_step_kernel(const float *__restrict__ joint_pos, const float *__restrict__ j
         }
     }
 
-    for (int64_t i = warp; i < N; i += nwarps) {
-        const float4 q = __ldg(reinterpret_cast<const float4 *>(body_quat) + i * Bsim + ref);
-        float val[NSLOT], minus[NSLOT];
+    constexpr int HB = 4;   // history slots moved per trip, all loads ahead of the stores
+    // envs in flight per warp: the loads of both are issued before the first store (memory-level parallelism is what bounds
+    // this kernel: ~10 narrow loads per env, DRAM latency each); wide observations (> 128 columns) keep one env per trip,
+    // two would not fit the register file
+    constexpr bool TWO = NSLOT <= 4;
+    constexpr int EPW = TWO ? 2 : 1;
+    auto load_inputs = [&](int64_t i, float4 &q, float(&val)[NSLOT], float(&minus)[NSLOT]) {
+        q = __ldg(reinterpret_cast<const float4 *>(body_quat) + i * Bsim + ref);
 #pragma unroll
         for (int s = 0; s < NSLOT; ++s) {
             val[s] = (active[s] && tn_idx[s] < 0) ? __ldg(src[s] + i * stride[s]) : 0.0f;
             minus[s] = sub[s] ? __ldg(sub[s] + i * stride[s]) : 0.0f;
         }
-        float *env = amp_buf + i * (int64_t)K * A + lane;
-        // history shift, oldest slots first, up to four slots per trip with all loads ahead of the stores
-        constexpr int HB = 4;
-        for (int hi = K - 2; hi >= 0; hi -= HB) {
-            const int lo = max(hi - (HB - 1), 0);
-            float h[HB][NSLOT];
+    };
+    auto load_history = [&](const float *env, int hi, int lo, float(&h)[HB][NSLOT]) {
 #pragma unroll
-            for (int t = 0; t < HB; ++t)
+        for (int t = 0; t < HB; ++t)
 #pragma unroll
-                for (int s = 0; s < NSLOT; ++s)
-                    if (hi - t >= lo && active[s]) h[t][s] = env[(int64_t)(hi - t) * A + 32 * s];
+            for (int s = 0; s < NSLOT; ++s)
+                if (hi - t >= lo && active[s]) h[t][s] = env[(int64_t)(hi - t) * A + 32 * s];
+    };
+    auto store_history = [&](float *env, int hi, int lo, const float(&h)[HB][NSLOT]) {
 #pragma unroll
-            for (int t = 0; t < HB; ++t)
+        for (int t = 0; t < HB; ++t)
 #pragma unroll
-                for (int s = 0; s < NSLOT; ++s)
-                    if (hi - t >= lo && active[s]) env[(int64_t)(hi - t + 1) * A + 32 * s] = h[t][s];
-        }
+            for (int s = 0; s < NSLOT; ++s)
+                if (hi - t >= lo && active[s]) env[(int64_t)(hi - t + 1) * A + 32 * s] = h[t][s];
+    };
+    auto write_slot0 = [&](int64_t i, float *env, const float4 &q, const float(&val)[NSLOT], const float(&minus)[NSLOT]) {
         float tn[6];
         tangent_normal(q, tn);
 #pragma unroll
@@ -652,6 +659,44 @@ obs_step_kernel(const float *__restrict__ joint_pos, const float *__restrict__ j
             if (tn_idx[s] >= 0) r = pick6(tn, tn_idx[s]);
             env[32 * s] = r;
             if (policy_obs && lane + 32 * s < policy_width) policy_obs[i * policy_stride + lane + 32 * s] = r;
+        }
+    };
+
+    for (int64_t i0 = warp; i0 < N; i0 += EPW * nwarps) {
+        const int64_t i1 = i0 + nwarps;
+        const bool two = TWO && i1 < N;
+        const int64_t j1 = two ? i1 : i0;  // second env of the trip (aliases the first when there is none: loads only)
+        float4 q0, q1;
+        float val0[NSLOT], minus0[NSLOT], val1[NSLOT], minus1[NSLOT];
+        load_inputs(i0, q0, val0, minus0);
+        if constexpr (TWO) load_inputs(j1, q1, val1, minus1);
+        float *env0 = amp_buf + i0 * (int64_t)K * A + lane;
+        float *env1 = amp_buf + j1 * (int64_t)K * A + lane;
+        // history shift, oldest slots first.  The first trip of both envs is loaded before anything is stored (K <= 5: the
+        // only trip); longer histories continue env by env.
+        int hi = K - 2;
+        if (hi >= 0) {
+            const int lo = max(hi - (HB - 1), 0);
+            float h0[HB][NSLOT], h1[HB][NSLOT];
+            load_history(env0, hi, lo, h0);
+            if constexpr (TWO) load_history(env1, hi, lo, h1);
+            store_history(env0, hi, lo, h0);
+            if constexpr (TWO) {
+                if (two) store_history(env1, hi, lo, h1);
+            }
+            for (hi -= HB; hi >= 0; hi -= HB) {
+                const int lo2 = max(hi - (HB - 1), 0);
+                load_history(env0, hi, lo2, h0);
+                if constexpr (TWO) load_history(env1, hi, lo2, h1);
+                store_history(env0, hi, lo2, h0);
+                if constexpr (TWO) {
+                    if (two) store_history(env1, hi, lo2, h1);
+                }
+            }
+        }
+        write_slot0(i0, env0, q0, val0, minus0);
+        if constexpr (TWO) {
+            if (two) write_slot0(i1, env1, q1, val1, minus1);
         }
     }
 }
