@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 
 import torch
 
@@ -128,9 +129,23 @@ def load() -> C.CDLL:
     return lib
 
 
+_restore = threading.local()  # device to hand back to the calling thread after the library call that enter() prepared
+
+
+def _restore_device() -> None:
+    prev = getattr(_restore, "device", None)
+    if prev is not None:
+        _restore.device = None
+        load().amp_set_device(prev)
+
+
 def check(status: int) -> None:
+    """Raise on a failed library call; also puts the thread's current CUDA device back where it was before :func:`enter`
+    (the library's runtime shares the driver's per-thread current context with torch's, so a call on another device would
+    otherwise silently change ``torch.cuda.current_device()``)."""
+    msg = load().amp_last_error() if status != AMP_OK else None
+    _restore_device()
     if status != AMP_OK:
-        msg = load().amp_last_error()
         raise AmpB200Error(status, msg.decode(errors="replace") if msg else "unknown error")
 
 
@@ -149,7 +164,13 @@ def require_cuda(device) -> torch.device:
 def enter(device: torch.device):
     """Make ``device`` current in the library's runtime and return (lib, cudaStream_t of torch's current stream)."""
     lib = load()
-    check(lib.amp_set_device(device.index))
+    _restore_device()  # a previous enter() whose call was never check()ed
+    current = torch.cuda.current_device()
+    if current != device.index:
+        status = lib.amp_set_device(device.index)
+        if status != AMP_OK:
+            check(status)
+        _restore.device = current
     return lib, C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 

@@ -59,11 +59,13 @@ class GradientBucket:
         self.flat = torch.as_tensor(_DevicePointer(int(lib.amp_bucket_data(h)), self.capacity), device=self.device)
         if self.world > 1:
             blob = (C.c_ubyte * 128)()
+            lib, _stream = _lib.enter(self.device)
             _lib.check(lib.amp_bucket_export(h, blob))
             mine = torch.tensor(list(blob), dtype=torch.uint8, device=self.device)
             gathered = [torch.empty_like(mine) for _ in range(self.world)]
             dist.all_gather(gathered, mine, group=group)
             everyone = bytes(torch.cat(gathered).cpu().numpy().tobytes())
+            lib, _stream = _lib.enter(self.device)  # the peers' memory is mapped into THIS device's context
             _lib.check(lib.amp_bucket_connect(h, everyone))
             dist.barrier(group)  # every rank has mapped every peer before the first all-reduce touches peer memory
 
