@@ -14,7 +14,8 @@
 //   barrier B   "my stores are out" -- when a rank has seen that flag from all peers its whole bucket is final
 //
 // so each rank moves 2 (W-1)/W of the bucket over NVLink, all links busy in both directions at once, with no staging
-// copy and no second launch.  Flags are monotonically increasing epochs (two per call); spins are bounded (about two
+// copy and no second launch.  Two kernels implement the middle step: allreduce_mean_bulk_kernel (default, <= 8 ranks) moves
+// the payload with the bulk async-copy engine, allreduce_mean_kernel with per-thread 16-byte peer loads and stores.  Flags are monotonically increasing epochs (two per call); spins are bounded (about two
 // seconds) and report AMP_ECUDA-style failure through a device word instead of hanging the GPU if a peer never arrives.
 #include <algorithm>
 #include <cstdlib>
