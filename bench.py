@@ -243,7 +243,7 @@ def run_reference(args, spec, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "host": {"cpu_count": os.cpu_count(), "torch_threads": threads},
     }  # fmt: skip
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=JSON_OUT, flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -499,14 +499,20 @@ def run_ours(args, spec, rank, world, local_rank):
             "gpu_launches": launches_per_step * args.steps, "clocks": clocks.summary(),
             "stage_ms": {"sample+obs": obs_ms / args.steps, "disc_reward": disc_ms / args.steps},
         }  # fmt: skip
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=JSON_OUT, flush=True)
     tmp.cleanup()
     if distributed:
         dist.barrier()
         dist.destroy_process_group()
 
 
+JSON_OUT = sys.stdout  # the ONE JSON line goes here; everything else printed during a run (the loaders' two
+                       # "Loading ..." lines, like the reference's MotionLoader) is sent to stderr, see main()
+
+
 def main():
+    global JSON_OUT
+    JSON_OUT, sys.stdout = sys.stdout, sys.stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
