@@ -663,6 +663,8 @@ struct amp_disc_train {
     float *slices1, *slices2;                   // split-K slices of dW1 (splits1, h1, Kp) and dW2 (splits2, h2, h1)
     int splits1, splits2;
     int64_t staged_rows[3];                     // rows staged per source since the last step (-1: none)
+    int maps_Bp;                                // padded batch size the tensor maps below were encoded for (0: none yet)
+    CUtensorMap tX_k, tX_mn, tA1_k, tA1_mn, tE2_k, tE2_mn, tE1_mn, tW1b, tW1t, tW2b, tW2t, tXgp_k, tA1gp_k, tE1gp_k;
 };
 
 using namespace amp;
@@ -783,31 +785,35 @@ int amp_disc_train_step(amp_disc_train_t *t, const float *W1, const float *b1, c
     sumsq_kernel<<<1, 256, 0, st>>>(W3, h2, acc + ACC_W3_SQ);
     AMP_CUDA_TRY(cudaGetLastError());
 
-    // ---- tensor maps (buffers are fixed; row counts depend on this step's batch) ----
-    CUtensorMap tX_k, tX_mn, tA1_k, tA1_mn, tE2_k, tE2_mn, tE1_k, tE1_mn, tW1b, tW1t, tW2b, tW2t;
+    // ---- tensor maps: the buffers never move, only the row counts depend on the batch -> encoded once per padded batch size
+    // (fifteen cuTensorMapEncodeTiled calls were ~15 us of host time on every step) ----
+    if (t->maps_Bp != Bp) {
+        int rc = AMP_OK;
+        auto mk = [&](CUtensorMap *m, const void *ptr, int64_t rows, int64_t cols, int box_rows, int box_cols) {
+            if (rc == AMP_OK) rc = make_tmap(m, ptr, rows, cols, cols, box_rows, box_cols);
+        };
+        mk(&t->tX_k, t->X, 4LL * Bp, Kp, BM, BK);
+        mk(&t->tX_mn, t->X, 4LL * Bp, Kp, BK, 64);
+        mk(&t->tA1_k, t->A1, 4LL * Bp, h1, BM, BK);
+        mk(&t->tA1_mn, t->A1, 4LL * Bp, h1, BK, 64);
+        mk(&t->tE2_k, t->E2, 4LL * Bp, h2, BM, BK);
+        mk(&t->tE2_mn, t->E2, 4LL * Bp, h2, BK, 64);
+        mk(&t->tE1_mn, t->E1, 4LL * Bp, h1, BK, 64);
+        mk(&t->tW1b, t->W1b, h1, Kp, BN, BK);
+        mk(&t->tW1t, t->W1t, Kp, h1, BN, BK);
+        mk(&t->tW2b, t->W2b, h2, h1, BN, BK);
+        mk(&t->tW2t, t->W2t, h1, h2, BN, BK);
+        // row-block views: a TMA coordinate is relative to the map's base, so sub-ranges get their own maps
+        mk(&t->tXgp_k, t->X + (size_t)3 * Bp * Kp, Bp, Kp, BM, BK);
+        mk(&t->tA1gp_k, t->A1 + (size_t)3 * Bp * h1, Bp, h1, BM, BK);
+        mk(&t->tE1gp_k, t->E1 + (size_t)3 * Bp * h1, Bp, h1, BM, BK);
+        if (rc != AMP_OK) return rc;
+        t->maps_Bp = Bp;
+    }
+    const CUtensorMap &tX_k = t->tX_k, &tX_mn = t->tX_mn, &tA1_k = t->tA1_k, &tA1_mn = t->tA1_mn, &tE2_k = t->tE2_k, &tE2_mn = t->tE2_mn,
+                      &tE1_mn = t->tE1_mn, &tW1b = t->tW1b, &tW1t = t->tW1t, &tW2b = t->tW2b, &tW2t = t->tW2t,
+                      &tXgp_k = t->tXgp_k, &tA1gp_k = t->tA1gp_k, &tE1gp_k = t->tE1gp_k;
     int rc = AMP_OK;
-    auto mk = [&](CUtensorMap *m, const void *ptr, int64_t rows, int64_t cols, int box_rows, int box_cols) {
-        if (rc == AMP_OK) rc = make_tmap(m, ptr, rows, cols, cols, box_rows, box_cols);
-    };
-    mk(&tX_k, t->X, 4LL * Bp, Kp, BM, BK);
-    mk(&tX_mn, t->X, 4LL * Bp, Kp, BK, 64);
-    mk(&tA1_k, t->A1, 4LL * Bp, h1, BM, BK);
-    mk(&tA1_mn, t->A1, 4LL * Bp, h1, BK, 64);
-    mk(&tE2_k, t->E2, 4LL * Bp, h2, BM, BK);
-    mk(&tE2_mn, t->E2, 4LL * Bp, h2, BK, 64);
-    mk(&tE1_k, t->E1, 4LL * Bp, h1, BM, BK);
-    mk(&tE1_mn, t->E1, 4LL * Bp, h1, BK, 64);
-    mk(&tW1b, t->W1b, h1, Kp, BN, BK);
-    mk(&tW1t, t->W1t, Kp, h1, BN, BK);
-    mk(&tW2b, t->W2b, h2, h1, BN, BK);
-    mk(&tW2t, t->W2t, h1, h2, BN, BK);
-    if (rc != AMP_OK) return rc;
-    // row-block views: a TMA coordinate is relative to the map's base, so sub-ranges get their own maps
-    CUtensorMap tXgp_k, tA1gp_k, tE1gp_k;
-    mk(&tXgp_k, t->X + (size_t)3 * Bp * Kp, Bp, Kp, BM, BK);
-    mk(&tA1gp_k, t->A1 + (size_t)3 * Bp * h1, Bp, h1, BM, BK);
-    mk(&tE1gp_k, t->E1 + (size_t)3 * Bp * h1, Bp, h1, BM, BK);
-    if (rc != AMP_OK) return rc;
 
     GemmParams g{};
     // F1: A1[:3Bp] = relu(X[:3Bp] W1^T + b1)
