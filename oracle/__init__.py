@@ -7,6 +7,8 @@ reference's per-step AMP path so the CUDA kernels in ``humanoid_amp_b200`` can b
 * ``env_oracle``     -- ``compute_obs`` / ``quaternion_to_tangent_and_normal`` / ``collect_reference_motions`` /
                         history shift / reset fill (reference ``g1_amp_env.py:175-193, 414-419, 445-497, 535-561``)
 * ``memory_oracle``  -- skrl ``RandomMemory`` ring write / ``sample_by_index`` (upstream skrl, PARITY UNPINNED)
+* ``disc_train_oracle`` -- skrl ``AMP._update`` discriminator LOSS block (BCE + logit regularisation + gradient penalty + weight decay)
+                        evaluated by torch autograd, and the closed-form gradients the CUDA path implements (PARITY UNPINNED)
 * ``disc_oracle``    -- skrl ``RunningStandardScaler`` (eval + train-mode statistics) + MLP + AMP style reward (upstream skrl >= 1.4.3,
                         ``agents/torch/amp/amp.py::_update``; configured by ``agents/skrl_g1_dance_amp_cfg.yaml:31-39, 80, 94-95``)
 
@@ -45,3 +47,4 @@ from .env_oracle import (  # noqa: F401
 )
 from .disc_oracle import OracleDiscriminator, running_standard_scaler_eval, style_reward_from_logits  # noqa: F401
 from .memory_oracle import OracleRandomMemory  # noqa: F401
+from .disc_train_oracle import DiscLossCfg, discriminator_loss_autograd, discriminator_loss_manual  # noqa: F401
