@@ -115,6 +115,28 @@ def test_multi_chunk_rows_and_row_independence():
     assert disc.style_reward(x[:0]).shape == (0, 1)
 
 
+def test_lead_in_chunk_plan_gives_the_same_bits(monkeypatch):
+    """The optional lead-in chunk (AMP_B200_DISC_LEAD_TILES, a tuning knob that is off by default) only changes how the batch
+    is cut into launches: rewards must be bit-identical and the launch count must follow the plan."""
+    import humanoid_amp_b200 as amp
+    from humanoid_amp_b200.synthetic import skrl_style_discriminator_params
+
+    monkeypatch.setenv("AMP_B200_DISC_TILES_PER_CTA", "8")  # chunks of 8 row tiles per CTA
+    W, b = skrl_style_discriminator_params(166, seed=4, logit_gain=3.0)
+    disc = amp.AmpDiscriminator(166, device="cuda:0", max_rows=700_000)
+    disc.load(W, b, torch.zeros(166, dtype=torch.float64), torch.ones(166, dtype=torch.float64))
+    M = 4 * disc.chunk_rows
+    assert M <= 700_000
+    x = torch.randn(M, 166, device="cuda", generator=torch.Generator(device="cuda").manual_seed(0))
+    monkeypatch.setenv("AMP_B200_DISC_LEAD_TILES", "0")
+    plain, launches_plain = disc.style_reward(x), disc.launch_count(M)
+    monkeypatch.setenv("AMP_B200_DISC_LEAD_TILES", "2")
+    lead, launches_lead = disc.style_reward(x), disc.launch_count(M)
+    assert torch.equal(plain, lead)
+    assert launches_plain == 2 * 4 and launches_lead == 2 * 5  # four chunks; a 2-tile lead-in + four (smaller) chunks
+    assert disc.launch_count(100) == 2 and disc.launch_count(0) == 0
+
+
 def test_weight_refresh_changes_result():
     disc, ora, inputs = build(162, 1.0)
     x = inputs(256, 1).cuda()
