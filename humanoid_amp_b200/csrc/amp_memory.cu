@@ -104,18 +104,19 @@ __global__ void __launch_bounds__(kStatThreads) scaler_partial_kernel(const floa
     }
 }
 
-// 32 columns per block; the 8 warps split the partial sums (warp w takes parts w, w+8, ...) and meet in shared memory in a
-// fixed order, so the result does not depend on scheduling.
-__global__ void __launch_bounds__(256) scaler_merge_kernel(const double *__restrict__ scratch, int parts, int64_t M, int W,
-                                                           double *__restrict__ running_mean, double *__restrict__ running_var,
-                                                           const double *__restrict__ count_in) {
-    __shared__ double sh[2][8][32];
+// 32 columns per block; the 32 warps split the partial sums (warp w takes parts w, w+32, ...: at most a handful each, all
+// loads in flight together) and meet in shared memory in a fixed order, so the result does not depend on scheduling.
+constexpr int kMergeWarps = 32;
+__global__ void __launch_bounds__(32 * kMergeWarps) scaler_merge_kernel(const double *__restrict__ scratch, int parts, int64_t M, int W,
+                                                                        double *__restrict__ running_mean, double *__restrict__ running_var,
+                                                                        const double *__restrict__ count_in) {
+    __shared__ double sh[2][kMergeWarps][32];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + tx;
     double s = 0.0, ss = 0.0;
     if (c < W) {
-#pragma unroll 4
-        for (int p = ty; p < parts; p += 8) {
+#pragma unroll 8
+        for (int p = ty; p < parts; p += kMergeWarps) {
             s += scratch[(size_t)p * 2 * W + c];
             ss += scratch[(size_t)p * 2 * W + W + c];
         }
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(256) scaler_merge_kernel(const double *__restr
     if (ty != 0 || c >= W) return;
     s = ss = 0.0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) {
+    for (int w = 0; w < kMergeWarps; ++w) {
         s += sh[0][w][tx];
         ss += sh[1][w][tx];
     }
@@ -232,7 +233,7 @@ int amp_scaler_update(const float *x, int64_t x_stride, int64_t M, int32_t W, do
     cudaStream_t st = as_stream(stream);
     const int col_blocks = (W + kStatThreads - 1) / kStatThreads;
     scaler_partial_kernel<<<dim3(parts, col_blocks), kStatThreads, 0, st>>>(x, x_stride, M, W, static_cast<double *>(scratch));
-    scaler_merge_kernel<<<(W + 31) / 32, 256, 0, st>>>(static_cast<const double *>(scratch), parts, M, W, running_mean,
+    scaler_merge_kernel<<<(W + 31) / 32, 32 * kMergeWarps, 0, st>>>(static_cast<const double *>(scratch), parts, M, W, running_mean,
                                                              running_variance, current_count);
     scaler_count_kernel<<<1, 1, 0, st>>>(current_count, M);
     AMP_CUDA_TRY(cudaGetLastError());
