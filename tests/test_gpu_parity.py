@@ -282,6 +282,30 @@ def test_env_step_history_vs_oracle(loaders, amp, K, robot_name):
     assert env.extras["amp_obs"].shape == (N, K * robot.amp_observation_space)
 
 
+@pytest.mark.parametrize("K", [2, 7])
+def test_env_step_with_several_envs_per_warp(loaders, amp, K):
+    """More envs than resident warps (the grid is capped at 8 CTAs per SM = 9472 warps): every warp walks several envs, two
+    in flight per trip, and an odd count leaves unpaired tails -- the path the 300-env test above never enters."""
+    from oracle import env_oracle
+    from humanoid_amp_b200.synthetic import synthetic_sim_state
+
+    loader = loaders("G1_dance")
+    N = 30001
+    env = make_env(amp, loader, K, num_envs=N)
+    robot = env.cfg.robot
+    ref_buf = torch.zeros(N, K, robot.amp_observation_space)
+    for step in range(K + 1):
+        state = synthetic_sim_state(N, robot, "cpu", seed=500 + step)
+        jp, jv, bp, bq, bl, ba = state
+        obs = env_oracle.compute_obs(jp, jv, bp[:, env.ref_body_index], bq[:, env.ref_body_index], bl[:, env.ref_body_index],
+                                     ba[:, env.ref_body_index], bp[:, env.key_body_indexes])  # fmt: skip
+        want_view = env_oracle.shift_and_write_history(ref_buf, obs)
+        policy = torch.empty((N, robot.amp_observation_space - 12), device="cuda")
+        got_view = env.update_amp_observations(*[t.cuda() for t in state], policy_obs=policy)
+        close(got_view, want_view)
+        close(policy, obs[:, :-12])
+
+
 @pytest.mark.parametrize("n_actor,track,inc_act,inc_cmd", [(1, 0.0, True, True), (1, 1.0, True, True), (2, 1.0, True, True),
                                                          (4, 1.0, False, True), (3, 1.0, True, False), (5, 0.0, True, True)])
 def test_actor_observation_history_vs_oracle(loaders, amp, n_actor, track, inc_act, inc_cmd):
