@@ -347,13 +347,12 @@ def test_actor_observation_history_vs_oracle(loaders, amp, n_actor, track, inc_a
 
 
 @pytest.mark.parametrize("track", [0.0, 1.0])
-def test_task_reward_vs_oracle(loaders, amp, track):
+def test_task_reward_vs_oracle(loaders, amp, track, N=777):
     """``_get_rewards`` (g1_amp_env.py:246-288) with compute_rewards / exp_reward_with_floor."""
     from oracle import env_oracle
     from humanoid_amp_b200.synthetic import synthetic_sim_state
 
     loader = loaders("G1_dance")
-    N = 777
     scales = dict(rew_termination=-1.0, rew_action_l2=-0.1, rew_joint_pos_limits=-10.0, rew_joint_acc_l2=-1.0e-06,
                   rew_joint_vel_l2=-0.001, rew_track_vel=track)  # the _CUSTOM cfg values (g1_amp_env_cfg.py:86-91)
     cfg = amp.AmpEnvCfg(motion_file="<preloaded>", num_envs=N, num_amp_observations=2, robot=amp.G1, **scales)
@@ -381,6 +380,11 @@ def test_task_reward_vs_oracle(loaders, amp, track):
         assert (want_err**2 > 1.0).any() and (want_err**2 < 1.0).any()  # both branches of exp_reward_with_floor exercised
     only_total = env.get_rewards(terminated.cuda(), actions.cuda(), jp.cuda(), limits.cuda(), acc.cuda(), jv.cuda(), bl.cuda(), bq.cuda())
     assert torch.equal(only_total, total)
+
+
+def test_task_reward_with_several_envs_per_warp(loaders, amp):
+    """More envs than resident warps (grid capped at 9472 warps): the grid-stride loop of the reward kernel."""
+    test_task_reward_vs_oracle(loaders, amp, 1.0, N=25003)
 
 
 def test_reset_strategy_random_state_vs_oracle(loaders, amp):
