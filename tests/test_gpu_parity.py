@@ -308,13 +308,13 @@ def test_env_step_with_several_envs_per_warp(loaders, amp, K):
 
 @pytest.mark.parametrize("n_actor,track,inc_act,inc_cmd", [(1, 0.0, True, True), (1, 1.0, True, True), (2, 1.0, True, True),
                                                          (4, 1.0, False, True), (3, 1.0, True, False), (5, 0.0, True, True)])
-def test_actor_observation_history_vs_oracle(loaders, amp, n_actor, track, inc_act, inc_cmd):
+def test_actor_observation_history_vs_oracle(loaders, amp, n_actor, track, inc_act, inc_cmd, N=200):
     """the policy observation of ``_get_observations`` (g1_amp_env.py:195-242) incl. warm start."""
     from oracle import env_oracle
     from humanoid_amp_b200.synthetic import synthetic_sim_state
 
     loader = loaders("G1_dance")
-    N, K = 200, 3
+    K = 3
     cfg = amp.AmpEnvCfg(motion_file="<preloaded>", num_envs=N, num_amp_observations=K, robot=amp.G1, num_actor_observations=n_actor,
                         rew_track_vel=track, history_include_last_actions=inc_act, history_include_command=inc_cmd)
     env = amp.AmpEnvPath(cfg, "cuda:0", motion_loader=loader)
@@ -344,6 +344,11 @@ def test_actor_observation_history_vs_oracle(loaders, amp, n_actor, track, inc_a
         if n_actor > 1:
             close(env.actor_obs_history_buffer, ref_hist)
             assert not env._just_reset_mask.any() and not ref_mask.any()
+
+
+def test_actor_observation_with_several_envs_per_warp(loaders, amp):
+    """More envs than resident warps (grid capped at 9472 warps): the grid-stride loops of both observation kernels."""
+    test_actor_observation_history_vs_oracle(loaders, amp, 3, 1.0, True, True, N=21001)
 
 
 @pytest.mark.parametrize("track", [0.0, 1.0])
