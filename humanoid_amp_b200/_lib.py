@@ -55,6 +55,28 @@ class LibDesc(C.Structure):
     ]
 
 
+class EnvStepArgs(C.Structure):
+    """``amp_env_step_t``"""
+
+    _fields_ = [
+        ("joint_pos", C.c_void_p), ("joint_vel", C.c_void_p),
+        ("body_pos_w", C.c_void_p), ("body_quat_w", C.c_void_p), ("body_lin_vel_w", C.c_void_p), ("body_ang_vel_w", C.c_void_p),
+        ("num_envs", C.c_int64),
+        ("num_dofs", C.c_int32), ("num_sim_bodies", C.c_int32), ("ref_body", C.c_int32), ("num_key_bodies", C.c_int32),
+        ("key_bodies", C.c_void_p),
+        ("num_amp_observations", C.c_int32), ("_pad0", C.c_int32),
+        ("amp_buf", C.c_void_p),
+        ("last_actions", C.c_void_p), ("command", C.c_void_p),
+        ("action_size", C.c_int32), ("command_size", C.c_int32), ("num_actor_observations", C.c_int32),
+        ("hist_include_actions", C.c_int32), ("hist_include_command", C.c_int32), ("_pad1", C.c_int32),
+        ("hist_buf", C.c_void_p), ("just_reset", C.c_void_p), ("actor_obs", C.c_void_p),
+        ("actor_stride", C.c_int64),
+        ("reward_scales", C.c_void_p), ("reset_terminated", C.c_void_p), ("actions", C.c_void_p), ("soft_limits", C.c_void_p),
+        ("joint_acc", C.c_void_p),
+        ("reward_total", C.c_void_p), ("reward_terms", C.c_void_p), ("track_err", C.c_void_p),
+    ]  # fmt: skip
+
+
 _P, _I32, _I64, _F32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
 # name -> (restype, argtypes); mirrors include/amp_b200.h one to one (tests/test_abi.py checks the header against this)
@@ -67,6 +89,7 @@ SIGNATURES = {
     "amp_lib_destroy": (C.c_int, [_P]),
     "amp_lib_obs_width": (C.c_int, [_P]),
     "amp_lib_poll_flags": (C.c_int, [_P, _P, C.POINTER(C.c_uint32)]),
+    "amp_lib_set_option": (C.c_int, [_P, _I32, _I64]),
     "amp_frame_blend": (C.c_int, [_P, _P, _P, _I64, _P, _P, _P, _P, _P]),
     "amp_sample_full": (C.c_int, [_P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P]),
     "amp_lerp": (C.c_int, [_P, _P, _P, _I64, _I64, _P, _P]),
@@ -77,6 +100,7 @@ SIGNATURES = {
     "amp_obs_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _I32, _I32, _P, _P, _I64, _P]),
     "amp_actor_obs_step": (C.c_int, [_P, _I64, _I32, _I32, _I32, _P, _I32, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _I64, _P]),
     "amp_task_reward": (C.c_int, [_P, _P, _P, _I32, _P, _P, _P, _P, _I32, _P, _P, _I32, _I32, _P, _I64, _P, _P, _P, _P]),
+    "amp_env_step": (C.c_int, [C.POINTER(EnvStepArgs), _P]),
     "amp_disc_create": (C.c_int, [_I32, _I32, _I32, _I64, _P, C.POINTER(_P)]),
     "amp_disc_destroy": (C.c_int, [_P]),
     "amp_disc_chunk_rows": (C.c_int64, [_P]),

@@ -263,6 +263,65 @@ class AmpEnvPath:
         )
         return {"policy": out[:, :width]}
 
+    # ---- the whole per-step path in one launch -------------------------------------------------------
+    def step_observations(self, joint_pos, joint_vel, body_pos_w, body_quat_w, body_lin_vel_w, body_ang_vel_w, out: Optional[torch.Tensor] = None,
+                          reward_inputs: Optional[dict] = None) -> dict:
+        """``_get_observations`` (AMP history + actor observation, reference ``:175-242``) as ONE kernel launch
+        (``amp_env_step``); same results as :meth:`get_observations`.  ``reward_inputs`` (optional dict with
+        ``reset_terminated, actions, soft_joint_pos_limits, joint_acc``, optionally ``return_terms``) adds
+        ``_get_rewards`` (``:246-319``) on the SAME state to the launch -- valid when no reset happens between the two in
+        the caller's step; the result dict then carries ``"reward"`` (and ``"reward_terms"``, ``"track_err"``)."""
+        cfg, dev = self.cfg, self.device
+        tensors = [_f32c(t, dev) for t in (joint_pos, joint_vel, body_pos_w, body_quat_w, body_lin_vel_w, body_ang_vel_w)]
+        N, D = tensors[0].shape
+        if N != self.num_envs or D != cfg.robot.num_joints:
+            raise RuntimeError(f"expected joint_pos ({self.num_envs}, {cfg.robot.num_joints}), got {(N, D)}")
+        n, width = cfg.num_actor_observations, cfg.observation_space
+        if out is None:
+            out = torch.empty((N, width), dtype=torch.float32, device=dev)
+        if out.dtype != torch.float32 or out.stride(-1) != 1 or out.shape[-1] < width:
+            raise RuntimeError("actor observation output must be float32 rows of at least observation_space columns")
+        a = _lib.EnvStepArgs()
+        keep = []  # tensors the argument block points at must outlive the call
+
+        def dptr(t):
+            keep.append(t)
+            return None if t is None else (t.data_ptr() if isinstance(t, torch.Tensor) else t.ctypes.data)
+
+        (a.joint_pos, a.joint_vel, a.body_pos_w, a.body_quat_w, a.body_lin_vel_w, a.body_ang_vel_w) = [dptr(t) for t in tensors]
+        a.num_envs, a.num_dofs, a.num_sim_bodies = N, D, tensors[2].shape[1]
+        a.ref_body, a.num_key_bodies, a.key_bodies = self.ref_body_index, len(self.key_body_indexes), dptr(self._key_idx_host)
+        a.num_amp_observations, a.amp_buf = cfg.num_amp_observations, dptr(self.amp_observation_buffer)
+        a.last_actions = dptr(_f32c(self.last_actions, dev))
+        a.command = dptr(self.command_target_speed if cfg.command_size else None)
+        a.action_size, a.command_size, a.num_actor_observations = cfg.action_space, cfg.command_size, n
+        a.hist_include_actions, a.hist_include_command = int(cfg.history_include_last_actions), int(cfg.history_include_command)
+        a.hist_buf = dptr(self.actor_obs_history_buffer if n > 1 else None)
+        a.just_reset = dptr(self._just_reset_mask if n > 1 else None)
+        a.actor_obs, a.actor_stride = dptr(out), out.stride(0)
+        result = {}
+        if reward_inputs is not None:
+            scales = np.array([cfg.rew_termination, cfg.rew_action_l2, cfg.rew_joint_pos_limits, cfg.rew_joint_acc_l2,
+                               cfg.rew_joint_vel_l2, cfg.rew_track_vel], dtype=np.float32)  # fmt: skip
+            a.reward_scales = dptr(scales)
+            a.reset_terminated = dptr(reward_inputs["reset_terminated"].to(dev).to(torch.uint8).contiguous())
+            a.actions = dptr(_f32c(reward_inputs["actions"], dev))
+            a.soft_limits = dptr(_f32c(reward_inputs["soft_joint_pos_limits"], dev))
+            a.joint_acc = dptr(_f32c(reward_inputs["joint_acc"], dev))
+            if cfg.rew_track_vel > 0.0:
+                a.command = dptr(_f32c(self.command_target_speed, dev))
+            result["reward"] = torch.empty(N, dtype=torch.float32, device=dev)
+            a.reward_total = dptr(result["reward"])
+            if reward_inputs.get("return_terms"):
+                result["reward_terms"] = torch.empty((N, 6), dtype=torch.float32, device=dev)
+                result["track_err"] = torch.empty(N, dtype=torch.float32, device=dev)
+                a.reward_terms, a.track_err = dptr(result["reward_terms"]), dptr(result["track_err"])
+        lib, stream = _lib.enter(dev)
+        _lib.check(lib.amp_env_step(C.byref(a), stream))
+        self.extras = {"amp_obs": self.amp_observation_buffer.view(-1, self.amp_observation_size)}
+        result["policy"] = out[:, :width]
+        return result
+
     # ---- task reward (reference _get_rewards :246-319; SURVEY 8f item 1) ----------------------------------------------
     def get_rewards(self, reset_terminated, actions, joint_pos, soft_joint_pos_limits, joint_acc, joint_vel, body_lin_vel_w=None,
                     body_quat_w=None, return_terms: bool = False):
@@ -308,8 +367,10 @@ class AmpEnvPath:
         """Reference ``_reset_strategy_random`` (``g1_amp_env.py:371-419``) without the simulator writes and the command
         resampling: draws (motion id, time) per env with the reference's host RNG stream, samples the frame, builds
         ``root_state (n, 13)`` (position + env origin, z lifted by 0.05, rotation, linear / angular velocity of the
-        ``pelvis``), the robot-order dof state, and fills ``amp_observation_buffer[env_ids]`` with the reference history
-        (fused collect + scatter).  Returns ``(root_state, dof_pos, dof_vel, motion_ids, times)``.
+        robot's reset root body: ``pelvis`` for G1, ``torso`` lifted by 0.15 for the 28-DoF humanoid,
+        ``humanoid_amp_env.py:194-201``), the robot-order dof state, and fills ``amp_observation_buffer[env_ids]`` with the
+        reference history (fused collect + scatter).  Returns ``(root_state, dof_pos, dof_vel, motion_ids, times)``.
+        A clip without that body raises ``AssertionError`` like the reference's ``get_body_index``.
 
         The root/dof assembly is a handful of torch index ops on the sampled tensors (reset-time glue, SURVEY 8f item 3);
         sampling and the history fill run in ``libamp_b200.so``."""
@@ -318,10 +379,11 @@ class AmpEnvPath:
         n = ids_dev.numel()
         motion_ids, times = loader.sample_times(n, start=start)
         dof_p, dof_v, body_p, body_r, body_lv, body_av = loader.sample(num_samples=n, times=times, motion_ids=motion_ids)
-        torso = loader.get_body_index(["pelvis"])[0] if "pelvis" in loader.body_names else self.motion_ref_body_index
+        robot = self.cfg.robot
+        torso = loader.get_body_index([robot.reset_root_body])[0]
         root_state = default_root_state.to(self.device, torch.float32).clone()
         root_state[:, 0:3] = body_p[:, torso] + env_origins.to(self.device, torch.float32)
-        root_state[:, 2] += 0.05
+        root_state[:, 2] += robot.reset_root_lift
         root_state[:, 3:7] = body_r[:, torso]
         root_state[:, 7:10] = body_lv[:, torso]
         root_state[:, 10:13] = body_av[:, torso]

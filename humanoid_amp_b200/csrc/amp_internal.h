@@ -67,4 +67,5 @@ struct amp_lib {
     int device;
     void *owned[8];  // device allocations freed by amp_lib_destroy
     int n_owned;
+    int collect_table;  // AMP_OPT_COLLECT_TABLE: 0 auto, 1 global-memory table, 2 shared-memory table
 };

@@ -757,6 +757,61 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// one env, whole warp: the per-joint sums are lane-strided partial sums combined with a fixed shuffle tree, lane 0 finishes
+__device__ __forceinline__ void task_reward_env(const RewardScales &sc, int64_t i, int lane, const uint8_t *__restrict__ terminated,
+                                                const float *__restrict__ actions, int act, const float *__restrict__ joint_pos,
+                                                const float *__restrict__ limits, const float *__restrict__ joint_acc,
+                                                const float *__restrict__ joint_vel, int D, const float *__restrict__ body_lin,
+                                                const float *__restrict__ body_quat, int Bsim, int ref,
+                                                const float *__restrict__ command, float *__restrict__ total,
+                                                float *__restrict__ terms, float *__restrict__ track_err) {
+    float s_act = 0.0f, s_lim = 0.0f, s_acc = 0.0f, s_vel = 0.0f;
+    for (int j = lane; j < act; j += 32) {
+        const float a = __ldg(actions + i * act + j);
+        s_act += a * a;
+    }
+    for (int j = lane; j < D; j += 32) {
+        const float p = __ldg(joint_pos + i * D + j);
+        const float2 lim = __ldg(reinterpret_cast<const float2 *>(limits) + i * D + j);
+        s_lim += -fminf(p - lim.x, 0.0f) + fmaxf(p - lim.y, 0.0f);
+        const float a = __ldg(joint_acc + i * D + j), w = __ldg(joint_vel + i * D + j);
+        s_acc += a * a;
+        s_vel += w * w;
+    }
+    s_act = warp_sum(s_act);
+    s_lim = warp_sum(s_lim);
+    s_acc = warp_sum(s_acc);
+    s_vel = warp_sum(s_vel);
+    if (lane == 0) {
+        const float r_term = sc.termination * (terminated[i] ? 1.0f : 0.0f);
+        const float r_act = sc.action_l2 * s_act, r_lim = sc.joint_pos_limits * s_lim;
+        const float r_acc = sc.joint_acc_l2 * s_acc, r_vel = sc.joint_vel_l2 * s_vel;
+        float r_track = 0.0f, err = 0.0f;
+        if (sc.track_vel > 0.0f) {
+            const float4 q = __ldg(reinterpret_cast<const float4 *>(body_quat) + i * Bsim + ref);  // w x y z
+            const float *vp = body_lin + (i * Bsim + ref) * 3;
+            const float vx = __ldg(vp), vy = __ldg(vp + 1), vz = __ldg(vp + 2);
+            // quat_rotate_inverse: v*(2w^2-1) - 2w (xyz x v) + 2 xyz (xyz . v); only x and y are needed
+            const float k = 2.0f * (q.x * q.x) - 1.0f;
+            const float cx = q.z * vz - q.w * vy, cy = q.w * vx - q.y * vz;  // (xyz x v).x, .y
+            const float dotv = q.y * vx + q.z * vy + q.w * vz;
+            const float bx = vx * k - cx * q.x * 2.0f + q.y * dotv * 2.0f;
+            const float by = vy * k - cy * q.x * 2.0f + q.z * dotv * 2.0f;
+            const float dx = bx - __ldg(command + i * 2), dy = by - __ldg(command + i * 2 + 1);
+            err = sqrtf(dx * dx + dy * dy);
+            const float e2 = err * err;
+            // exp_reward_with_floor(e2, weight, sigma = 0.5, floor = 4.0): threshold = floor * sigma^2 = 1.0
+            r_track = e2 > 1.0f ? sc.exp_at_floor - sc.linear_slope * (e2 - 1.0f) : sc.track_vel * expf(-e2 / 0.25f);
+        }
+        total[i] = ((((r_term + r_act) + r_lim) + r_acc) + r_vel) + r_track;
+        if (terms) {
+            float *t = terms + i * 6;
+            t[0] = r_term; t[1] = r_act; t[2] = r_lim; t[3] = r_acc; t[4] = r_vel; t[5] = r_track;
+        }
+        if (track_err) track_err[i] = err;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 task_reward_kernel(RewardScales sc, const uint8_t *__restrict__ terminated, const float *__restrict__ actions, int act,
                    const float *__restrict__ joint_pos, const float *__restrict__ limits, const float *__restrict__ joint_acc,
@@ -766,52 +821,148 @@ task_reward_kernel(RewardScales sc, const uint8_t *__restrict__ terminated, cons
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t i = warp; i < N; i += nwarps) {
-        float s_act = 0.0f, s_lim = 0.0f, s_acc = 0.0f, s_vel = 0.0f;
-        for (int j = lane; j < act; j += 32) {
-            const float a = __ldg(actions + i * act + j);
-            s_act += a * a;
+    for (int64_t i = warp; i < N; i += nwarps)
+        task_reward_env(sc, i, lane, terminated, actions, act, joint_pos, limits, joint_acc, joint_vel, D, body_lin, body_quat, Bsim,
+                        ref, command, total, terms, track_err);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// amp_env_step: the whole per-step env path in ONE launch: compute_obs from simulator state, AMP
+// history shift + slot 0 (g1_amp_env.py:176-193), actor observation + its history with warm start (:195-242) and,
+// optionally, the task reward (:246-319) -- one warp per env, lane l owns observation columns l, l+32, ...; the new
+// observation row lives in registers and feeds the AMP buffer, the actor observation and the actor history without being
+// read back; every simulator tensor is fetched from DRAM once per env.
+// ------------------------------------------------------------------------------------------------------------------
+struct EnvStepParams {
+    const float *joint_pos, *joint_vel, *body_pos, *body_quat, *body_lin, *body_ang;
+    int64_t N;
+    int D, Bsim, ref, Kb, K;
+    KeyList keys;
+    float *amp_buf;
+    // actor observation
+    const float *last_actions, *command;
+    int act, cmd, n_hist, inc_act, inc_cmd;
+    float *hist_buf;
+    uint8_t *just_reset;
+    float *actor_obs;
+    int64_t actor_stride;
+    // task reward (total == NULL: skipped)
+    RewardScales sc;
+    const uint8_t *terminated;
+    const float *actions, *limits, *joint_acc;
+    float *total, *terms, *track_err;
+};
+
+template <int NSLOT>
+__global__ void __launch_bounds__(256, 2) env_step_kernel(const __grid_constant__ EnvStepParams p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int D = p.D, D2 = 2 * D, Bsim = p.Bsim, ref = p.ref, K = p.K;
+    const int A = D2 + 13 + 3 * p.Kb, base = A - 3 * p.Kb;
+
+    const float *src[NSLOT], *sub[NSLOT];
+    int stride[NSLOT], tn_idx[NSLOT];
+    bool active[NSLOT];
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) {
+        const int c = lane + 32 * s;
+        active[s] = c < A;
+        tn_idx[s] = -1;
+        sub[s] = nullptr;
+        src[s] = p.joint_pos;
+        stride[s] = 0;
+        if (c < D) { src[s] = p.joint_pos + c; stride[s] = D; }
+        else if (c < D2) { src[s] = p.joint_vel + (c - D); stride[s] = D; }
+        else if (c == D2) { src[s] = p.body_pos + ref * 3 + 2; stride[s] = Bsim * 3; }
+        else if (c < D2 + 7) { tn_idx[s] = c - D2 - 1; }
+        else if (c < D2 + 10) { src[s] = p.body_lin + ref * 3 + (c - D2 - 7); stride[s] = Bsim * 3; }
+        else if (c < D2 + 13) { src[s] = p.body_ang + ref * 3 + (c - D2 - 10); stride[s] = Bsim * 3; }
+        else if (c < A) {
+            const int e = c - D2 - 13, j = e / 3, a = e - 3 * j;
+            src[s] = p.body_pos + p.keys.k[j] * 3 + a;
+            sub[s] = p.body_pos + ref * 3 + a;
+            stride[s] = Bsim * 3;
         }
-        for (int j = lane; j < D; j += 32) {
-            const float p = __ldg(joint_pos + i * D + j);
-            const float2 lim = __ldg(reinterpret_cast<const float2 *>(limits) + i * D + j);
-            s_lim += -fminf(p - lim.x, 0.0f) + fmaxf(p - lim.y, 0.0f);
-            const float a = __ldg(joint_acc + i * D + j), w = __ldg(joint_vel + i * D + j);
-            s_acc += a * a;
-            s_vel += w * w;
+    }
+    const int cur = base + p.act + p.cmd;
+    const int hact = p.inc_act ? p.act : 0, hcmd = p.inc_cmd ? p.cmd : 0, P = base + hact + hcmd;
+    constexpr int HB = 4;
+
+    for (int64_t i = warp; i < p.N; i += nwarps) {
+        // ---- all simulator-state loads of this env, then the history loads, before the first store ------------------
+        const float4 q = __ldg(reinterpret_cast<const float4 *>(p.body_quat) + i * Bsim + ref);
+        float val[NSLOT], minus[NSLOT];
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) {
+            val[s] = (active[s] && tn_idx[s] < 0) ? __ldg(src[s] + i * stride[s]) : 0.0f;
+            minus[s] = sub[s] ? __ldg(sub[s] + i * stride[s]) : 0.0f;
         }
-        s_act = warp_sum(s_act);
-        s_lim = warp_sum(s_lim);
-        s_acc = warp_sum(s_acc);
-        s_vel = warp_sum(s_vel);
-        if (lane == 0) {
-            const float r_term = sc.termination * (terminated[i] ? 1.0f : 0.0f);
-            const float r_act = sc.action_l2 * s_act, r_lim = sc.joint_pos_limits * s_lim;
-            const float r_acc = sc.joint_acc_l2 * s_acc, r_vel = sc.joint_vel_l2 * s_vel;
-            float r_track = 0.0f, err = 0.0f;
-            if (sc.track_vel > 0.0f) {
-                const float4 q = __ldg(reinterpret_cast<const float4 *>(body_quat) + i * Bsim + ref);  // w x y z
-                const float *vp = body_lin + (i * Bsim + ref) * 3;
-                const float vx = __ldg(vp), vy = __ldg(vp + 1), vz = __ldg(vp + 2);
-                // quat_rotate_inverse: v*(2w^2-1) - 2w (xyz x v) + 2 xyz (xyz . v); only x and y are needed
-                const float k = 2.0f * (q.x * q.x) - 1.0f;
-                const float cx = q.z * vz - q.w * vy, cy = q.w * vx - q.y * vz;  // (xyz x v).x, .y
-                const float dotv = q.y * vx + q.z * vy + q.w * vz;
-                const float bx = vx * k - cx * q.x * 2.0f + q.y * dotv * 2.0f;
-                const float by = vy * k - cy * q.x * 2.0f + q.z * dotv * 2.0f;
-                const float dx = bx - __ldg(command + i * 2), dy = by - __ldg(command + i * 2 + 1);
-                err = sqrtf(dx * dx + dy * dy);
-                const float e2 = err * err;
-                // exp_reward_with_floor(e2, weight, sigma = 0.5, floor = 4.0): threshold = floor * sigma^2 = 1.0
-                r_track = e2 > 1.0f ? sc.exp_at_floor - sc.linear_slope * (e2 - 1.0f) : sc.track_vel * expf(-e2 / 0.25f);
+        float *env = p.amp_buf + i * (int64_t)K * A + lane;
+        for (int hi = K - 2; hi >= 0; hi -= HB) {  // AMP history, oldest slots first, HB slots per trip
+            const int lo = max(hi - (HB - 1), 0);
+            float h[HB][NSLOT];
+#pragma unroll
+            for (int t = 0; t < HB; ++t)
+#pragma unroll
+                for (int s = 0; s < NSLOT; ++s)
+                    if (hi - t >= lo && active[s]) h[t][s] = env[(int64_t)(hi - t) * A + 32 * s];
+#pragma unroll
+            for (int t = 0; t < HB; ++t)
+#pragma unroll
+                for (int s = 0; s < NSLOT; ++s)
+                    if (hi - t >= lo && active[s]) env[(int64_t)(hi - t + 1) * A + 32 * s] = h[t][s];
+        }
+        float tn[6];
+        tangent_normal(q, tn);
+        float row[NSLOT];
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) {
+            float r = sub[s] ? __fsub_rn(val[s], minus[s]) : val[s];
+            if (tn_idx[s] >= 0) r = pick6(tn, tn_idx[s]);
+            row[s] = r;
+            if (active[s]) env[32 * s] = r;
+        }
+        // ---- actor observation: [base | last_actions | command | history frames] ----------------------------------------
+        if (p.actor_obs) {
+            float *arow = p.actor_obs + i * p.actor_stride;
+            const bool reset = p.n_hist > 0 && p.just_reset && p.just_reset[i] != 0;
+            float *hist = p.n_hist > 0 ? p.hist_buf + i * (int64_t)p.n_hist * P : nullptr;
+            auto history_column = [&](int pc, float frame) {  // slot s takes slot s-1 (or the new frame everywhere after a reset)
+                for (int sl = p.n_hist - 1; sl >= 1; --sl) {
+                    const float moved = reset ? frame : hist[(int64_t)(sl - 1) * P + pc];
+                    hist[(int64_t)sl * P + pc] = moved;
+                    arow[cur + (int64_t)sl * P + pc] = moved;
+                }
+                hist[pc] = frame;
+                arow[cur + pc] = frame;
+            };
+#pragma unroll
+            for (int s = 0; s < NSLOT; ++s) {
+                const int c = lane + 32 * s;
+                if (c < base) {
+                    arow[c] = row[s];
+                    if (p.n_hist > 0) history_column(c, row[s]);
+                }
             }
-            total[i] = ((((r_term + r_act) + r_lim) + r_acc) + r_vel) + r_track;
-            if (terms) {
-                float *t = terms + i * 6;
-                t[0] = r_term; t[1] = r_act; t[2] = r_lim; t[3] = r_acc; t[4] = r_vel; t[5] = r_track;
+            for (int e = lane; e < p.act + p.cmd; e += 32) {
+                const bool is_act = e < p.act;
+                const float v = is_act ? __ldg(p.last_actions + i * p.act + e) : __ldg(p.command + i * p.cmd + (e - p.act));
+                arow[base + e] = v;
+                if (p.n_hist > 0) {
+                    if (is_act && p.inc_act) history_column(base + e, v);
+                    if (!is_act && p.inc_cmd) history_column(base + hact + (e - p.act), v);
+                }
             }
-            if (track_err) track_err[i] = err;
+            if (reset) {
+                __syncwarp();
+                if (lane == 0) p.just_reset[i] = 0;
+            }
         }
+        // ---- task reward on the same state ----------------------------------------------------------------------------
+        if (p.total)
+            task_reward_env(p.sc, i, lane, p.terminated, p.actions, p.act, p.joint_pos, p.limits, p.joint_acc, p.joint_vel, D, p.body_lin,
+                            p.body_quat, Bsim, ref, p.command, p.total, p.terms, p.track_err);
     }
 }
 
@@ -933,6 +1084,20 @@ int amp_lib_create(const amp_lib_desc_t *d, void *stream, amp_lib_t **out) {
         e = cudaGetLastError();
         if (e != cudaSuccess) return bail(cuda_fail(e, "pack_rows_kernel launch"));
     }
+    if (with_env) {
+        // the shared-memory-table variant needs the opt-in limit; set once per handle, here, not on the launch path
+        // (cudaFuncSetAttribute is per device and idempotent, so concurrent handles need no guard)
+        cudaError_t ea = cudaSuccess;
+#define AMP_COLLECT_ATTR(NS)                                                                                            \
+    if (ea == cudaSuccess)                                                                                              \
+        ea = cudaFuncSetAttribute(collect_reference_kernel<NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin)
+        AMP_COLLECT_ATTR(1); AMP_COLLECT_ATTR(2); AMP_COLLECT_ATTR(3); AMP_COLLECT_ATTR(4);
+        AMP_COLLECT_ATTR(5); AMP_COLLECT_ATTR(6); AMP_COLLECT_ATTR(7); AMP_COLLECT_ATTR(8);
+#undef AMP_COLLECT_ATTR
+        if (ea != cudaSuccess) return bail(cuda_fail(ea, "cudaFuncSetAttribute(collect_reference_kernel)"));
+        const char *e = getenv("AMP_B200_COLLECT_TABLE");  // read once per handle; amp_lib_set_option overrides it
+        lib->collect_table = !e ? 0 : (e[0] == 'g' ? 1 : (e[0] == 's' ? 2 : 0));
+    }
     if (!with_env) {
         // plain handle (MotionLoader.sample): stage the lerp row table for the row-table sample kernel
         v.lerp_width = 2 * v.num_dofs + 9 * v.num_bodies;
@@ -955,6 +1120,18 @@ int amp_lib_create(const amp_lib_desc_t *d, void *stream, amp_lib_t **out) {
     if (e != cudaSuccess) return bail(cuda_fail(e, "cudaStreamSynchronize(amp_lib_create)"));
     *out = lib;
     return AMP_OK;
+}
+
+int amp_lib_set_option(amp_lib_t *lib, int32_t option, int64_t value) {
+    AMP_REQUIRE(lib, "amp_lib_set_option: NULL handle");
+    switch (option) {
+        case AMP_OPT_COLLECT_TABLE:
+            AMP_REQUIRE(value >= 0 && value <= 2, "amp_lib_set_option: AMP_OPT_COLLECT_TABLE takes 0 (auto), 1 (global) or 2 (shared)");
+            lib->collect_table = (int)value;
+            return AMP_OK;
+        default:
+            return fail(AMP_EINVAL, "amp_lib_set_option: unknown option %d", option);
+    }
 }
 
 int amp_lib_destroy(amp_lib_t *lib) {
@@ -1068,10 +1245,7 @@ int amp_collect_reference(amp_lib_t *lib, const double *cur_times, const int64_t
     const size_t per_warp = (size_t)tile_cap * sizeof(FrameMeta);
     int smem_warps = table_bytes + 8 * per_warp <= (size_t)kMaxSmemOptin ? (int)std::min<size_t>(32, (kMaxSmemOptin - table_bytes) / per_warp) : 0;
     const int64_t full_tiles = (n + max_tile - 1) / max_tile;
-    static const int force_variant = [] {  // developer knob: AMP_B200_COLLECT_TABLE=global|smem overrides the heuristic
-        const char *e = getenv("AMP_B200_COLLECT_TABLE");
-        return !e ? 0 : (e[0] == 'g' ? 1 : (e[0] == 's' ? 2 : 0));
-    }();
+    const int force_variant = lib->collect_table;  // AMP_OPT_COLLECT_TABLE (amp_lib_set_option / AMP_B200_COLLECT_TABLE at create)
     bool use_smem = smem_warps >= 8 && full_tiles >= (int64_t)2 * sms * smem_warps;
     if (force_variant == 1) use_smem = false;
     if (force_variant == 2 && smem_warps >= 1) use_smem = true;
@@ -1097,12 +1271,6 @@ int amp_collect_reference(amp_lib_t *lib, const double *cur_times, const int64_t
 #define AMP_LAUNCH_COLLECT(NS)                                                                                          \
     do {                                                                                                                \
         if (use_smem) {                                                                                                 \
-            static bool attr_set[64] = {false};                                                                         \
-            if (!attr_set[lib->device & 63]) {                                                                          \
-                AMP_CUDA_TRY(cudaFuncSetAttribute(collect_reference_kernel<NS, true>,                                   \
-                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));         \
-                attr_set[lib->device & 63] = true;                                                                      \
-            }                                                                                                           \
             collect_reference_kernel<NS, true><<<grid, threads, smem, st>>>(lib->v, cur_times, ids, n, K, tile_samples, \
                                                                             tile_cap, out, row_stride, capacity_rows,   \
                                                                             start_row, row_index, tiles);               \
@@ -1229,6 +1397,81 @@ int amp_actor_obs_step(const float *amp_buf, int64_t N, int32_t K, int32_t A, in
     return AMP_OK;
 }
 
+static int make_reward_scales(const float *scales, RewardScales *out) {
+    RewardScales sc{};
+    sc.termination = scales[0];
+    sc.action_l2 = scales[1];
+    sc.joint_pos_limits = scales[2];
+    sc.joint_acc_l2 = scales[3];
+    sc.joint_vel_l2 = scales[4];
+    sc.track_vel = scales[5];
+    if (sc.track_vel > 0.0f) {
+        const double w = (double)scales[5], sigma_sq = 0.25, floor_v = 4.0;  // the scripted reference evaluates these in double
+        sc.exp_at_floor = (float)(w * std::exp(-floor_v));
+        sc.linear_slope = (float)(w / sigma_sq * std::exp(-floor_v));
+    }
+    *out = sc;
+    return AMP_OK;
+}
+
+int amp_env_step(const amp_env_step_t *a, void *stream) {
+    AMP_REQUIRE(a, "amp_env_step: NULL argument block");
+    const int64_t N = a->num_envs;
+    const int D = a->num_dofs, Bsim = a->num_sim_bodies, Kb = a->num_key_bodies, K = a->num_amp_observations;
+    AMP_REQUIRE(N >= 0 && D >= 1 && Bsim >= 1 && K >= 1, "amp_env_step: bad sizes");
+    AMP_REQUIRE(Kb >= 0 && Kb <= kMaxKeyBodies && (Kb == 0 || a->key_bodies), "amp_env_step: bad key body list");
+    AMP_REQUIRE(a->ref_body >= 0 && a->ref_body < Bsim, "amp_env_step: ref body out of range");
+    if (N == 0) return AMP_OK;
+    AMP_REQUIRE(a->joint_pos && a->joint_vel && a->body_pos_w && a->body_quat_w && a->body_lin_vel_w && a->body_ang_vel_w && a->amp_buf,
+                "amp_env_step: NULL buffer");
+    AMP_REQUIRE(aligned16(a->body_quat_w), "amp_env_step: body_quat_w must be 16-byte aligned");
+    EnvStepParams p{};
+    for (int i = 0; i < Kb; ++i) {
+        AMP_REQUIRE(a->key_bodies[i] >= 0 && a->key_bodies[i] < Bsim, "amp_env_step: key body %d out of range", a->key_bodies[i]);
+        p.keys.k[i] = a->key_bodies[i];
+    }
+    const int A = 2 * D + 13 + 3 * Kb, base = A - 3 * Kb;
+    p.joint_pos = a->joint_pos; p.joint_vel = a->joint_vel; p.body_pos = a->body_pos_w; p.body_quat = a->body_quat_w;
+    p.body_lin = a->body_lin_vel_w; p.body_ang = a->body_ang_vel_w;
+    p.N = N; p.D = D; p.Bsim = Bsim; p.ref = a->ref_body; p.Kb = Kb; p.K = K;
+    p.amp_buf = a->amp_buf;
+    p.act = a->action_size; p.cmd = a->command_size;
+    AMP_REQUIRE(p.act >= 0 && p.cmd >= 0, "amp_env_step: negative action / command size");
+    if (a->actor_obs) {
+        AMP_REQUIRE(a->num_actor_observations >= 1, "amp_env_step: num_actor_observations must be >= 1");
+        AMP_REQUIRE((p.act == 0 || a->last_actions) && (p.cmd == 0 || a->command), "amp_env_step: NULL last_actions / command");
+        p.n_hist = a->num_actor_observations - 1;
+        p.inc_act = a->hist_include_actions ? 1 : 0;
+        p.inc_cmd = a->hist_include_command ? 1 : 0;
+        AMP_REQUIRE(p.n_hist == 0 || a->hist_buf, "amp_env_step: history buffer required when num_actor_observations > 1");
+        const int P = base + (p.inc_act ? p.act : 0) + (p.inc_cmd ? p.cmd : 0);
+        AMP_REQUIRE(a->actor_stride >= base + p.act + p.cmd + (int64_t)p.n_hist * P, "amp_env_step: actor_stride too small");
+        p.last_actions = a->last_actions; p.command = a->command; p.hist_buf = a->hist_buf; p.just_reset = a->just_reset;
+        p.actor_obs = a->actor_obs; p.actor_stride = a->actor_stride;
+    }
+    if (a->reward_total) {
+        AMP_REQUIRE(a->reward_scales && a->reset_terminated && (p.act == 0 || a->actions) && a->soft_limits && a->joint_acc,
+                    "amp_env_step: NULL reward input");
+        make_reward_scales(a->reward_scales, &p.sc);
+        AMP_REQUIRE(p.sc.track_vel <= 0.0f || (a->command && p.cmd == 2), "amp_env_step: velocity tracking needs the (N, 2) command");
+        AMP_REQUIRE((reinterpret_cast<uintptr_t>(a->soft_limits) & 7u) == 0, "amp_env_step: soft_limits must be 8-byte aligned");
+        p.terminated = a->reset_terminated; p.actions = a->actions; p.limits = a->soft_limits; p.joint_acc = a->joint_acc;
+        p.command = a->command;
+        p.total = a->reward_total; p.terms = a->reward_terms; p.track_err = a->track_err;
+    }
+    const int grid = grid_for(N, 8, 8);
+    cudaStream_t st = as_stream(stream);
+#define AMP_LAUNCH_ENV_STEP(NS) case NS: env_step_kernel<NS><<<grid, 256, 0, st>>>(p); break
+    switch ((A + 31) / 32) {
+        AMP_LAUNCH_ENV_STEP(1); AMP_LAUNCH_ENV_STEP(2); AMP_LAUNCH_ENV_STEP(3); AMP_LAUNCH_ENV_STEP(4);
+        AMP_LAUNCH_ENV_STEP(5); AMP_LAUNCH_ENV_STEP(6); AMP_LAUNCH_ENV_STEP(7); AMP_LAUNCH_ENV_STEP(8);
+        default: return fail(AMP_EINVAL, "amp_env_step: observation width %d > 256 is not supported", A);
+    }
+#undef AMP_LAUNCH_ENV_STEP
+    AMP_CUDA_TRY(cudaGetLastError());
+    return AMP_OK;
+}
+
 int amp_task_reward(const float *scales, const uint8_t *reset_terminated, const float *actions, int32_t act, const float *joint_pos,
                     const float *soft_limits, const float *joint_acc, const float *joint_vel, int32_t D, const float *body_lin_vel_w,
                     const float *body_quat_w, int32_t Bsim, int32_t ref_body, const float *command, int64_t N, float *total,
@@ -1238,19 +1481,11 @@ int amp_task_reward(const float *scales, const uint8_t *reset_terminated, const 
     AMP_REQUIRE(reset_terminated && total && (act == 0 || actions) && (D == 0 || (joint_pos && soft_limits && joint_acc && joint_vel)),
                 "amp_task_reward: NULL buffer");
     RewardScales sc{};
-    sc.termination = scales[0];
-    sc.action_l2 = scales[1];
-    sc.joint_pos_limits = scales[2];
-    sc.joint_acc_l2 = scales[3];
-    sc.joint_vel_l2 = scales[4];
-    sc.track_vel = scales[5];
+    make_reward_scales(scales, &sc);
     if (sc.track_vel > 0.0f) {
         AMP_REQUIRE(body_lin_vel_w && body_quat_w && command && Bsim >= 1 && ref_body >= 0 && ref_body < Bsim,
                     "amp_task_reward: velocity tracking needs body_lin_vel_w, body_quat_w, command and a valid reference body");
         AMP_REQUIRE(aligned16(body_quat_w), "amp_task_reward: body_quat_w must be 16-byte aligned");
-        const double w = (double)scales[5], sigma_sq = 0.25, floor_v = 4.0;  // the scripted reference evaluates these in double
-        sc.exp_at_floor = (float)(w * std::exp(-floor_v));
-        sc.linear_slope = (float)(w / sigma_sq * std::exp(-floor_v));
     }
     AMP_REQUIRE(D == 0 || (reinterpret_cast<uintptr_t>(soft_limits) & 7u) == 0, "amp_task_reward: soft_limits must be 8-byte aligned");
     task_reward_kernel<<<grid_for(N, 8, 8), 256, 0, as_stream(stream)>>>(sc, reset_terminated, actions, act, joint_pos, soft_limits,

@@ -109,6 +109,14 @@ class _LibHandle:
             raise _lib.AmpB200Error(_lib.AMP_EINVAL, "motion library handle was destroyed")
         return self._h
 
+    COLLECT_TABLE = {"auto": 0, "global": 1, "smem": 2}
+
+    def set_collect_table(self, mode: str) -> None:
+        """``AMP_OPT_COLLECT_TABLE``: where the fused collect kernel keeps the packed row table (``auto`` | ``global`` |
+        ``smem``).  A tuning / test knob: results do not depend on it."""
+        lib, _ = _lib.enter(self.device)
+        _lib.check(lib.amp_lib_set_option(self.raw, 1, self.COLLECT_TABLE[mode]))
+
     def close(self):
         if getattr(self, "_h", None) is not None:
             try:

@@ -17,6 +17,10 @@ class RobotSpec:
     body_names: tuple  # simulator body order (Bsim entries) -> indexes body_pos_w / body_quat_w
     reference_body: str  # cfg.reference_body (g1_amp_env_cfg.py:53, humanoid_amp_env_cfg.py:42)
     key_body_names: tuple  # order matters: RH, LH, RF, LF (g1_amp_env.py:40-45)
+    # _reset_strategy_random takes the root transform from a HARD-CODED clip body and lifts it off the ground:
+    # G1 "pelvis" + 0.05 (g1_amp_env.py:398, 403-405), 28-DoF humanoid "torso" + 0.15 (humanoid_amp_env.py:194, 199-201)
+    reset_root_body: str = "pelvis"
+    reset_root_lift: float = 0.05
 
     @property
     def num_joints(self) -> int:
@@ -69,6 +73,8 @@ HUMANOID28 = RobotSpec(
     ),
     reference_body="torso",
     key_body_names=("right_hand", "left_hand", "right_foot", "left_foot"),
+    reset_root_body="torso",
+    reset_root_lift=0.15,
 )  # fmt: skip
 
 

@@ -96,6 +96,13 @@ AMP_API int amp_lib_obs_width(const amp_lib_t *lib);
 /* Reads and clears the device-side sticky flags (bit0: motion id out of range, bit1: NaN time). Synchronises the
  * stream.  The kernels clamp such inputs for memory safety; the reference raises IndexError instead. */
 AMP_API int amp_lib_poll_flags(amp_lib_t *lib, void *stream, uint32_t *flags);
+/* Per-handle tuning knobs (never change results, only which kernel variant runs).  Options:
+ *   AMP_OPT_COLLECT_TABLE  where amp_collect_reference keeps the packed row table: 0 = choose by size (default),
+ *                          1 = global memory (L1/L2), 2 = copied into shared memory once per persistent CTA (falls back to 1
+ *                          when the table does not fit in 227 KB).  Initial value: environment variable
+ *                          AMP_B200_COLLECT_TABLE = global | smem, read ONCE in amp_lib_create. */
+enum { AMP_OPT_COLLECT_TABLE = 1 };
+AMP_API int amp_lib_set_option(amp_lib_t *lib, int32_t option, int64_t value);
 
 /* MotionLoader._compute_frame_blend (motion_loader.py:281-307), float64 on device, bit-exact.
  *   times  device f64[S]; motion_ids device i64[S] or NULL (= all zeros, the reference default at :366)
@@ -172,6 +179,39 @@ AMP_API int amp_task_reward(const float *scales, const uint8_t *reset_terminated
                             const float *joint_pos, const float *soft_limits, const float *joint_acc, const float *joint_vel,
                             int32_t D, const float *body_lin_vel_w, const float *body_quat_w, int32_t Bsim, int32_t ref_body,
                             const float *command, int64_t N, float *total, float *terms, float *track_err, void *stream);
+
+/* The whole per-step env path in ONE launch: G1AmpEnv._get_observations (g1_amp_env.py:175-242: compute_obs, AMP history
+ * shift + slot 0, actor observation + its history with warm start) and, when reward_total != NULL, _get_rewards (:246-319)
+ * evaluated on the SAME simulator state (valid when no reset happens between the two in the caller's step, e.g. play.py's
+ * loop; otherwise call amp_task_reward before the resets and this entry point without the reward part after them, as
+ * DirectRLEnv.step orders them).  Same results as amp_obs_step + amp_actor_obs_step + amp_task_reward; each simulator tensor
+ * is read once.  Field meanings are those of the three entry points above. */
+typedef struct {
+    const float *joint_pos, *joint_vel;                                        /* device (N, D) */
+    const float *body_pos_w, *body_quat_w, *body_lin_vel_w, *body_ang_vel_w;   /* device (N, Bsim, 3|4) */
+    int64_t num_envs;
+    int32_t num_dofs, num_sim_bodies, ref_body, num_key_bodies;
+    const int32_t *key_bodies;        /* host [num_key_bodies] */
+    int32_t num_amp_observations;     /* K */
+    int32_t _pad0;
+    float *amp_buf;                   /* device (N, K, A), in place */
+    /* actor observation (actor_obs == NULL: skipped) */
+    const float *last_actions;        /* device (N, action_size) */
+    const float *command;             /* device (N, command_size) or NULL with command_size = 0 */
+    int32_t action_size, command_size, num_actor_observations, hist_include_actions, hist_include_command, _pad1;
+    float *hist_buf;                  /* device (N, n-1, P) or NULL when n == 1 */
+    uint8_t *just_reset;              /* device (N) or NULL */
+    float *actor_obs;                 /* device, rows actor_stride floats apart */
+    int64_t actor_stride;
+    /* task reward (reward_total == NULL: skipped) */
+    const float *reward_scales;       /* host [6], as amp_task_reward */
+    const uint8_t *reset_terminated;  /* device (N) */
+    const float *actions;             /* device (N, action_size) */
+    const float *soft_limits;         /* device (N, D, 2) */
+    const float *joint_acc;           /* device (N, D) */
+    float *reward_total, *reward_terms, *track_err; /* device (N), (N,6) or NULL, (N) or NULL */
+} amp_env_step_t;
+AMP_API int amp_env_step(const amp_env_step_t *args, void *stream);
 
 /* ---- AMP memories and the state preprocessor (upstream skrl >= 1.4.3, not vendored) ------------------ */
 /* skrl memories/torch/base.py Memory.sample_by_index (RandomMemory.sample draws the indexes): out[r,:] = src[row_index[r],:].

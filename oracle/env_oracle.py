@@ -143,13 +143,14 @@ def actor_observations(obs, last_actions, command, history_buffer, just_reset_ma
     return actor_obs
 
 
-def reset_root_and_dof_state(loader, times, motion_ids, default_root_state, env_origins, motion_dof_indexes, torso_index):
+def reset_root_and_dof_state(loader, times, motion_ids, default_root_state, env_origins, motion_dof_indexes, torso_index, lift=0.05):
     """Reference ``g1_amp_env.py:386-411`` (state part of ``_reset_strategy_random``): root pose / velocity and dof state of
-    the sampled frame; the root is lifted by 0.05 to avoid ground collisions."""
+    the sampled frame; the root is lifted to avoid ground collisions (G1: body ``pelvis``, 0.05, ``:398-405``; the 28-DoF
+    humanoid: body ``torso``, 0.15, ``humanoid_amp_env.py:194-201``)."""
     dof_p, dof_v, body_p, body_r, body_lv, body_av = loader.sample(num_samples=len(times), times=times, motion_ids=motion_ids)
     root_state = default_root_state.clone()
     root_state[:, 0:3] = body_p[:, torso_index] + env_origins
-    root_state[:, 2] += 0.05
+    root_state[:, 2] += lift
     root_state[:, 3:7] = body_r[:, torso_index]
     root_state[:, 7:10] = body_lv[:, torso_index]
     root_state[:, 10:13] = body_av[:, torso_index]

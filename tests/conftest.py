@@ -50,6 +50,28 @@ def pooled_spec() -> str:
     return ",".join(clip_path(n) for n in ("humanoid_walk", "humanoid_run", "humanoid_dance"))
 
 
+def full_clip_path(name: str) -> str:
+    """The shipped clip itself (``tests/golden/clips_full``: data files of the reference, committed as fixtures)."""
+    return os.path.join(GOLDEN, "clips_full", f"{name}.npz")
+
+
+def full_pooled_spec() -> str:
+    return ",".join(full_clip_path(n) for n in ("humanoid_walk", "humanoid_run", "humanoid_dance"))
+
+
+def fixture_files(tag: str) -> list:
+    """Clip files behind a fixture tag of ``vectors.npz``: ``<name>`` (40-frame window), ``full/<name>`` (whole clip),
+    ``pooled_humanoid`` / ``full/pooled_humanoid`` (three clips as one comma-separated spec)."""
+    full = tag.startswith("full/")
+    name = tag[5:] if full else tag
+    if name == "pooled_humanoid":
+        return (full_pooled_spec() if full else pooled_spec()).split(",")
+    return [full_clip_path(name) if full else clip_path(name)]
+
+
+FIXTURE_TAGS = CLIP_NAMES + ["pooled_humanoid"] + [f"full/{n}" for n in CLIP_NAMES] + ["full/pooled_humanoid"]
+
+
 @pytest.fixture(scope="session")
 def golden():
     with np.load(os.path.join(GOLDEN, "vectors.npz")) as d:

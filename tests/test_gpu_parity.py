@@ -20,7 +20,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import CLIP_NAMES, clip_path, pooled_spec
+from conftest import CLIP_NAMES, FIXTURE_TAGS, clip_path, fixture_files, full_clip_path, pooled_spec
 
 pytestmark = pytest.mark.gpu
 
@@ -73,10 +73,9 @@ def amp():
 def loaders(amp):
     cache = {}
 
-    def get(name):
+    def get(name):  # a fixture tag of vectors.npz: <clip> (40-frame window), full/<clip>, [full/]pooled_humanoid
         if name not in cache:
-            spec = pooled_spec() if name == "pooled_humanoid" else clip_path(name)
-            cache[name] = amp.MotionLoader(spec, "cuda:0")
+            cache[name] = amp.MotionLoader(",".join(fixture_files(name)), "cuda:0")
         return cache[name]
 
     return get
@@ -91,7 +90,7 @@ def make_env(amp, loader, K, num_envs=64):
 # ---------------------------------------------------------------------------------------------------------------------
 # golden fixtures written by the LIVE reference
 # ---------------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("name", CLIP_NAMES + ["pooled_humanoid"])
+@pytest.mark.parametrize("name", FIXTURE_TAGS)
 def test_frame_blend_bit_exact_vs_reference_fixture(golden, loaders, name):
     loader = loaders(name)
     times, ids = golden[f"{name}/times"], golden[f"{name}/ids"]
@@ -103,7 +102,7 @@ def test_frame_blend_bit_exact_vs_reference_fixture(golden, loaders, name):
     assert np.array_equal(b32.cpu().numpy(), golden[f"{name}/blend"].astype(np.float32))
 
 
-@pytest.mark.parametrize("name", CLIP_NAMES + ["pooled_humanoid"])
+@pytest.mark.parametrize("name", FIXTURE_TAGS)
 def test_sample_vs_reference_fixture(golden, loaders, name):
     loader = loaders(name)
     times, ids = golden[f"{name}/times"], golden[f"{name}/ids"]
@@ -116,15 +115,21 @@ def test_sample_vs_reference_fixture(golden, loaders, name):
     assert loader.poll_flags() == 0
 
 
-@pytest.mark.parametrize("name", CLIP_NAMES + ["pooled_humanoid"])
+@pytest.mark.parametrize("name", FIXTURE_TAGS)
 @pytest.mark.parametrize("K", [2, 10])
 def test_collect_reference_vs_reference_fixture(golden, loaders, amp, name, K):
+    """Rows written by the reference's own ``collect_reference_motions`` text (tests/golden/make_golden.py), on the
+    40-frame windows and on the full shipped clips; the stated bar, unscaled."""
     loader = loaders(name)
     env = make_env(amp, loader, K)
     times, ids = golden[f"{name}/times"], golden[f"{name}/ids"]
     obs = env.collect_reference_motions(len(times), times, ids)
     assert obs.shape == (len(times), K * env.cfg.amp_observation_space)
     close(obs, golden[f"{name}/amp_obs_k{K}"])
+    D = env.cfg.robot.num_joints  # everything but the six slerp-derived columns is bit-identical to the reference
+    A = env.cfg.amp_observation_space
+    lerp_cols = np.r_[0 : 2 * D + 1, 2 * D + 7 : A]
+    bit_equal(obs.cpu().numpy().reshape(-1, A)[:, lerp_cols], golden[f"{name}/amp_obs_k{K}"].reshape(-1, A)[:, lerp_cols])
     # same thing with device-resident inputs
     obs2 = env.collect_reference_motions(len(times), torch.from_numpy(times).cuda(), torch.from_numpy(ids).cuda())
     assert torch.equal(obs, obs2)
@@ -511,3 +516,114 @@ def test_one_million_sample_refill_properties(tmp_path, amp):
                                                 motion_ids=ids.cpu().numpy()[pick])  # fmt: skip
     close(a[torch.from_numpy(pick).cuda()], want)
     assert env.poll_flags() == 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# every variant of the fused collect kernel: table in global / shared memory x history length x destination form,
+# on the FULL shipped clips (G1_walk 134 KB, G1_dance 202 KB packed tables; the pooled humanoid table, 382 KB, does not
+# fit in shared memory and must fall back to the global-table variant)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dest", ["contiguous", "ring", "scatter"])
+@pytest.mark.parametrize("K", [1, 2, 3, 10])
+@pytest.mark.parametrize("table", ["global", "smem"])
+@pytest.mark.parametrize("name", ["full/G1_walk", "full/G1_dance", "full/pooled_humanoid"])
+def test_collect_variants_vs_oracle(loaders, amp, name, table, K, dest):
+    from oracle import OracleMotionLoader, env_oracle
+
+    loader = loaders(name)
+    ora = OracleMotionLoader(fixture_files(name))
+    env = make_env(amp, loader, K)
+    env._handle.set_collect_table(table)
+    robot = env.cfg.robot
+    A = robot.amp_observation_space
+    rng = np.random.default_rng(hash((name, K)) % 2**31)
+    n = 3001
+    ids = rng.integers(0, ora.num_trajectories, n)
+    times = rng.uniform(-0.05, 1.05, n) * ora.durations[ids]
+    times[:64] = (rng.integers(0, 30, 64) + 0.5) * ora.dt  # half-frame ties
+    want = env_oracle.collect_reference_motions(
+        ora, n, K, ora.get_dof_index(robot.joint_names), ora.get_body_index([robot.reference_body])[0],
+        ora.get_body_index(robot.key_body_names), current_times=times, motion_ids=ids,
+    )  # fmt: skip
+    _, _, frame_blend = ora.compute_frame_blend(env_oracle.history_times(times, ora.dt, K), np.repeat(ids, K))
+    t_d, i_d = torch.from_numpy(times).cuda(), torch.from_numpy(ids).cuda()
+    if dest == "contiguous":
+        got = env.collect_reference_motions(n, t_d, i_d)
+    elif dest == "ring":  # a skrl RandomMemory-like ring with padded rows, written from row 2900 on: wraps at 3500
+        mem = torch.full((3500, 1, K * A + 5), -3.0, device="cuda")
+        rows = mem.view(3500, -1)
+        env._launch_collect(t_d, i_d, n, rows, None, start_row=2900, capacity_rows=3500)
+        order = (2900 + np.arange(n)) % 3500
+        got = rows[torch.from_numpy(order).cuda(), : K * A]
+        assert (rows[:, K * A :] == -3.0).all(), "padding columns of the destination rows must not be touched"
+        untouched = np.setdiff1d(np.arange(3500), order)
+        assert (rows[torch.from_numpy(untouched).cuda()] == -3.0).all()
+    else:  # scatter into amp_observation_buffer[env_ids] (reset fill)
+        big = make_env(amp, loader, K, num_envs=2 * n)
+        big._handle.set_collect_table(table)
+        big.amp_observation_buffer.fill_(-3.0)
+        env_ids = torch.from_numpy(rng.permutation(2 * n)[:n]).cuda()
+        big.reset_amp_history(env_ids, t_d, i_d)
+        got = big.amp_observation_buffer[env_ids].view(n, -1)
+        mask = torch.ones(2 * n, dtype=torch.bool, device="cuda")
+        mask[env_ids] = False
+        assert (big.amp_observation_buffer[mask] == -3.0).all()
+    check_amp_obs(got, want, frame_blend, robot.num_joints, K)
+    inside = np.abs(frame_blend.reshape(n, K)).max(axis=1) <= 1.0  # samples whose every history frame interpolates:
+    close(got[torch.from_numpy(inside).cuda()], want[torch.from_numpy(inside)])  # the stated bar, unscaled
+    assert env.poll_flags() == 0
+
+
+def test_collect_smem_table_large_batch_matches_global_table(loaders, amp):
+    """The shared-memory-table variant at the size that selects it by itself (>= 2 full tiles per resident warp), K = 10 on
+    the 202 KB G1_dance table -- what a 200 000 x 10 motion_dataset fill (skrl_g1_dance_amp_cfg.yaml:50-58) runs -- must equal
+    the global-table variant bit for bit (same arithmetic, different staging) and the oracle on a subset of the rows."""
+    from oracle import OracleMotionLoader, env_oracle
+
+    name, K, n = "full/G1_dance", 10, 200_000
+    loader = loaders(name)
+    env = make_env(amp, loader, K)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    ids, times = loader.sample_times_device(n, generator=g)
+    outs = {}
+    for table in ("auto", "global", "smem"):
+        env._handle.set_collect_table(table)
+        outs[table] = env.collect_reference_motions(n, times, ids).clone()
+    assert torch.equal(outs["global"], outs["smem"]) and torch.equal(outs["auto"], outs["smem"])
+    ora = OracleMotionLoader(fixture_files(name))
+    pick = np.random.default_rng(1).choice(n, 2048, replace=False)
+    robot = env.cfg.robot
+    want = env_oracle.collect_reference_motions(ora, len(pick), K, ora.get_dof_index(robot.joint_names), 0, ora.get_body_index(robot.key_body_names),
+                                                current_times=times.cpu().numpy()[pick], motion_ids=ids.cpu().numpy()[pick])  # fmt: skip
+    _, _, fb = ora.compute_frame_blend(env_oracle.history_times(times.cpu().numpy()[pick], ora.dt, K), np.repeat(ids.cpu().numpy()[pick], K))
+    check_amp_obs(outs["smem"][torch.from_numpy(pick).cuda()], want, fb, robot.num_joints, K)
+
+
+def test_extrapolated_slerp_spread_is_torch_cpu_vs_torch_cuda_spread(loaders):
+    """Justifies the conditioning term of ``check_amp_obs`` (``atol = 1e-6 * max(1, |blend|)`` for EXTRAPOLATED history
+    frames, |blend| up to K-1): the reference algorithm itself, run by torch on the CPU (SLEEF ``acos`` / ``sin``) and by
+    torch on this GPU (libdevice), differs by that much on the same inputs.  Measured here on the oracle's slerp with both
+    devices; the CUDA kernel under test must (a) meet the UNSCALED bar wherever 0 <= blend <= 1 and (b) stay within the
+    scaled bar, and the torch-CPU-vs-torch-CUDA spread must itself exceed the unscaled bar somewhere -- otherwise the scaling
+    would be unjustified and this test fails."""
+    from oracle import slerp_f32
+
+    loader = loaders("full/G1_dance")
+    rot = loader.body_rotations.cpu()
+    rng = np.random.default_rng(3)
+    n = 20000
+    f0 = rng.integers(0, rot.shape[0] - 1, n)
+    blend = torch.from_numpy(rng.uniform(-9.0, -1.0, n).astype(np.float32))
+    q0, q1 = rot[f0], rot[f0 + 1]
+    ref_cpu = slerp_f32(q0, q1, blend)
+    ref_cuda = slerp_f32(q0.cuda(), q1.cuda(), blend.cuda()).cpu()
+    ours = loader._slerp(q0.cuda(), q1=q1.cuda(), blend=blend.cuda()).cpu()
+    bound = ATOL + RTOL * ref_cpu.abs()
+    torch_ratio = float(((ref_cuda - ref_cpu).abs() / bound).max())
+    ours_ratio = float(((ours - ref_cpu).abs() / bound).max())
+    scaled = (ATOL * blend.abs().clamp(min=1.0))[:, None, None] + RTOL * ref_cpu.abs()
+    print(f"extrapolated slerp, |blend| in [1, 9]: torch CUDA vs torch CPU max err / unscaled bound = {torch_ratio:.2f}; "
+          f"this kernel vs torch CPU = {ours_ratio:.2f}")
+    assert bool(((ours - ref_cpu).abs() <= scaled).all())
+    assert ours_ratio <= 1.0 or torch_ratio > 1.0, (ours_ratio, torch_ratio)
+    assert ours_ratio <= max(1.0, 3.0 * torch_ratio), (ours_ratio, torch_ratio)
