@@ -15,8 +15,8 @@
 //
 // so each rank moves 2 (W-1)/W of the bucket over NVLink, all links busy in both directions at once, with no staging
 // copy and no second launch.  Two kernels implement the middle step: allreduce_mean_bulk_kernel (default, <= 8 ranks) moves
-// the payload with the bulk async-copy engine, allreduce_mean_kernel with per-thread 16-byte peer loads and stores.  Flags are monotonically increasing epochs (two per call); spins are bounded (about two
-// seconds) and report AMP_ECUDA-style failure through a device word instead of hanging the GPU if a peer never arrives.
+// the payload with the bulk async-copy engine, allreduce_mean_kernel with per-thread 16-byte peer loads and stores.  Flags are monotonically increasing epochs (two per call, kept in device memory so a
+// captured launch replays correctly); spins are bounded and a timeout is loud (see kDefaultSpinLimitCycles).
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -29,7 +29,19 @@ namespace bucket {
 
 constexpr int kMaxWorld = 16;
 constexpr int kThreads = 256;
-constexpr long long kSpinLimitCycles = 4000000000LL;  // ~2 s at 2 GHz
+// Bounded spins: a rank that waits longer than this for a peer gives up (default 30 s of SM clock at ~2 GHz; NCCL would block
+// and then abort).  A timeout is LOUD: the failing rank poisons the start of the requested range of its own bucket with NaN
+// (so the optimiser step that follows cannot silently apply un-reduced gradients), raises a bit in a host-visible status word
+// that the next amp_bucket_allreduce_mean call on that handle reports as an error, and still walks the arrival counter so the
+// handle stays consistent.  AMP_B200_BUCKET_TIMEOUT_MS (read once in amp_bucket_create) overrides the limit.
+constexpr long long kDefaultSpinLimitCycles = 60000000000LL;
+
+struct Control {            // device words behind the flag array
+    unsigned int arrivals;  // CTAs of the running call that have finished their slice
+    uint32_t status;        // sticky failure bits (1: barrier A timed out, 2: barrier B timed out, 4: a bulk load never landed)
+    uint32_t epoch;         // last epoch used; bumped by 2 by the last CTA of every call (device state: graph replays stay in step)
+    uint32_t _pad;
+};
 
 struct Peers {
     float *data[kMaxWorld];
@@ -57,38 +69,53 @@ __device__ __forceinline__ void st_peer(float4 *p, float4 v) {
 }
 
 // wait until every rank's word in the LOCAL flag array has reached `epoch`; returns false on timeout
-__device__ __forceinline__ bool wait_all(const uint32_t *local_flags, int world, uint32_t epoch) {
+__device__ __forceinline__ bool wait_all(const uint32_t *local_flags, int world, uint32_t epoch, long long spin_limit) {
     const long long t0 = clock64();
     for (int p = 0; p < world; ++p) {
         while ((int32_t)(ld_acquire_sys(local_flags + p) - epoch) < 0) {
-            if (clock64() - t0 > kSpinLimitCycles) return false;
+            if (clock64() - t0 > spin_limit) return false;
             __nanosleep(64);
         }
     }
     return true;
 }
 
+// failure path shared by both kernels: sticky device bit + host-visible word + NaN poison of the local range
+__device__ __forceinline__ void report_failure(Control *ctl, volatile uint32_t *host_status, uint32_t bit, float *local, long long offset,
+                                               long long count) {
+    atomicOr(&ctl->status, bit);
+    if (host_status) host_status[0] = bit | 0x80000000u;  // plain store into mapped pinned memory; the host ORs what it sees
+    const float nan = __int_as_float(0x7fc00000);
+    for (long long i = 0; i < min(count, 4LL); ++i) local[offset + i] = nan;
+    __threadfence_system();
+}
+
 // count % 4 == 0, base pointers 16-byte aligned.  Slice r = quads [r * per, min((r + 1) * per, quads)).
 template <int MAXW, int U>
 __global__ void __launch_bounds__(kThreads) allreduce_mean_kernel(Peers peers, int rank, int world, long long offset, long long count,
-                                                                  uint32_t epoch, unsigned int *arrivals, uint32_t *status,
+                                                                  Control *ctl, volatile uint32_t *host_status, long long spin_limit,
                                                                   unsigned long long *timing) {
     __shared__ bool ok;
+    __shared__ uint32_t s_epoch;
     unsigned long long t_start = 0, t_a = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
     uint32_t *local_flags = peers.flags[rank];
+    // the epoch lives in device memory and is advanced by the last CTA of every call (after ALL CTAs have read it: they pass
+    // the arrival counter first), so a CUDA-graph replay of this launch uses fresh epochs like an eager call does
+    if (threadIdx.x == 0) s_epoch = *reinterpret_cast<volatile uint32_t *>(&ctl->epoch) + 1;
+    __syncthreads();
+    const uint32_t epoch = s_epoch;
     // ---- barrier A: announce (block 0) and wait (every block, on the local flag array) ----
     if (blockIdx.x == 0 && threadIdx.x < world) {
         __threadfence_system();
         st_release_sys(peers.flags[threadIdx.x] + rank, epoch);
     }
-    if (threadIdx.x == 0) ok = wait_all(local_flags, world, epoch);
-    __syncthreads();
-    if (!ok) {
-        if (threadIdx.x == 0) atomicOr(status, 1u);
-        return;
+    if (threadIdx.x == 0) {
+        ok = wait_all(local_flags, world, epoch, spin_limit);
+        if (!ok && blockIdx.x == 0) report_failure(ctl, host_status, 1u, peers.data[rank], offset, count);
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    __syncthreads();
+    if (ok && blockIdx.x == 0 && threadIdx.x == 0) {
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_a));
         timing[0] = t_start;
         timing[1] = t_a;
@@ -101,7 +128,8 @@ __global__ void __launch_bounds__(kThreads) allreduce_mean_kernel(Peers peers, i
     // NVLink round trips (~2 us) are the cost here, not bandwidth, so what matters is bytes in flight: every thread issues
     // the loads of U quads from ALL peers (fully unrolled over up to MAXW ranks) before the first add.
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long q = q0 + blockIdx.x * (long long)blockDim.x + threadIdx.x; q < q1; q += U * stride) {
+    // a rank whose barrier A timed out skips the exchange (its bucket is poisoned) but still walks barrier B below
+    for (long long q = q0 + blockIdx.x * (long long)blockDim.x + threadIdx.x; ok && q < q1; q += U * stride) {
         float4 v[MAXW][U];
 #pragma unroll
         for (int p = 0; p < MAXW; ++p) {
@@ -140,10 +168,13 @@ __global__ void __launch_bounds__(kThreads) allreduce_mean_kernel(Peers peers, i
     __threadfence_system();
     __syncthreads();
     __shared__ bool last;
-    if (threadIdx.x == 0) last = atomicAdd(arrivals, 1u) == gridDim.x - 1;
+    if (threadIdx.x == 0) last = atomicAdd(&ctl->arrivals, 1u) == gridDim.x - 1;
     __syncthreads();
     if (!last) return;
-    if (threadIdx.x == 0) *arrivals = 0;  // ready for the next call (stream-ordered)
+    if (threadIdx.x == 0) {
+        ctl->arrivals = 0;       // ready for the next call (stream-ordered)
+        ctl->epoch = epoch + 1;  // two epochs per call
+    }
     if (threadIdx.x < world) {
         __threadfence_system();
         st_release_sys(peers.flags[threadIdx.x] + rank, epoch + 1);
@@ -152,7 +183,7 @@ __global__ void __launch_bounds__(kThreads) allreduce_mean_kernel(Peers peers, i
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         timing[2] = t;  // this rank's reduce + publish is complete
-        if (!wait_all(local_flags, world, epoch + 1)) atomicOr(status, 2u);
+        if (ok && !wait_all(local_flags, world, epoch + 1, spin_limit)) report_failure(ctl, host_status, 2u, peers.data[rank], offset, count);
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         timing[3] = t;
     }
@@ -169,7 +200,7 @@ constexpr int kChunkQuads = kChunkBytes / 16;
 constexpr int kBulkStages = 4;
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ bool mbar_wait_bounded(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_wait_bounded(uint32_t bar, uint32_t parity, long long spin_limit) {
     const long long t0 = clock64();
     uint32_t done = 0;
     while (!done) {
@@ -178,18 +209,19 @@ __device__ __forceinline__ bool mbar_wait_bounded(uint32_t bar, uint32_t parity)
             : "=r"(done)
             : "r"(bar), "r"(parity)
             : "memory");
-        if (!done && clock64() - t0 > kSpinLimitCycles) return false;
+        if (!done && clock64() - t0 > spin_limit) return false;
     }
     return true;
 }
 
 template <int MAXW>
 __global__ void __launch_bounds__(kThreads) allreduce_mean_bulk_kernel(Peers peers, int rank, int world, long long offset, long long count,
-                                                                       uint32_t epoch, unsigned int *arrivals, uint32_t *status,
+                                                                       Control *ctl, volatile uint32_t *host_status, long long spin_limit,
                                                                        unsigned long long *timing) {
     extern __shared__ __align__(128) unsigned char bulk_smem[];  // [stage][MAXW + 1][kChunkBytes]: W inputs + 1 output per stage
     __shared__ __align__(8) unsigned long long full_bar[kBulkStages];
     __shared__ bool ok;
+    __shared__ uint32_t s_epoch;
     unsigned long long t_start = 0, t_a = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
     uint32_t *local_flags = peers.flags[rank];
@@ -197,19 +229,21 @@ __global__ void __launch_bounds__(kThreads) allreduce_mean_bulk_kernel(Peers pee
         for (int s = 0; s < kBulkStages; ++s)
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&full_bar[s])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_epoch = *reinterpret_cast<volatile uint32_t *>(&ctl->epoch) + 1;  // device-resident epoch, see allreduce_mean_kernel
     }
+    __syncthreads();
+    const uint32_t epoch = s_epoch;
     // ---- barrier A ----
     if (blockIdx.x == 0 && threadIdx.x < world) {
         __threadfence_system();
         st_release_sys(peers.flags[threadIdx.x] + rank, epoch);
     }
-    if (threadIdx.x == 0) ok = wait_all(local_flags, world, epoch);
-    __syncthreads();
-    if (!ok) {
-        if (threadIdx.x == 0) atomicOr(status, 1u);
-        return;
+    if (threadIdx.x == 0) {
+        ok = wait_all(local_flags, world, epoch, spin_limit);
+        if (!ok && blockIdx.x == 0) report_failure(ctl, host_status, 1u, peers.data[rank], offset, count);
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    __syncthreads();
+    if (ok && blockIdx.x == 0 && threadIdx.x == 0) {
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_a));
         timing[0] = t_start;
         timing[1] = t_a;
@@ -218,7 +252,8 @@ __global__ void __launch_bounds__(kThreads) allreduce_mean_bulk_kernel(Peers pee
     const long long quads = count / 4;
     const long long per = (quads + world - 1) / world;
     const long long q0 = (long long)rank * per, q1 = min(quads, q0 + per);
-    const long long n_chunks = q1 > q0 ? (q1 - q0 + kChunkQuads - 1) / kChunkQuads : 0;
+    // a rank whose barrier A timed out skips the exchange (its bucket is poisoned) but still walks barrier B below
+    const long long n_chunks = (ok && q1 > q0) ? (q1 - q0 + kChunkQuads - 1) / kChunkQuads : 0;
     const float inv = 1.0f / (float)world;
     auto stage_base = [&](int st) { return bulk_smem + (size_t)st * (MAXW + 1) * kChunkBytes; };
     auto chunk_bytes = [&](long long c) { return (uint32_t)(min((long long)kChunkQuads, q1 - (q0 + c * kChunkQuads)) * 16); };
@@ -252,7 +287,7 @@ __global__ void __launch_bounds__(kThreads) allreduce_mean_bulk_kernel(Peers pee
             asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kBulkStages - 1) : "memory");
             if (ahead < n_chunks) issue_loads(ahead, (int)((k + kBulkStages - 1) % kBulkStages));
         }
-        if (!mbar_wait_bounded(smem_addr(&full_bar[st]), (uint32_t)((k / kBulkStages) & 1))) good = false;
+        if (!mbar_wait_bounded(smem_addr(&full_bar[st]), (uint32_t)((k / kBulkStages) & 1), spin_limit)) good = false;
         const uint32_t bytes = chunk_bytes(c);
         const float4 *in = reinterpret_cast<const float4 *>(stage_base(st));
         float4 *out = reinterpret_cast<float4 *>(stage_base(st) + (size_t)MAXW * kChunkBytes);
@@ -278,15 +313,18 @@ __global__ void __launch_bounds__(kThreads) allreduce_mean_bulk_kernel(Peers pee
         }
     }
     if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // every store of this CTA has completed
-    if (!good && threadIdx.x == 0) atomicOr(status, 4u);
+    if (!good && threadIdx.x == 0) report_failure(ctl, host_status, 4u, peers.data[rank], offset, count);
     // ---- barrier B ----
     __threadfence_system();
     __syncthreads();
     __shared__ bool last;
-    if (threadIdx.x == 0) last = atomicAdd(arrivals, 1u) == gridDim.x - 1;
+    if (threadIdx.x == 0) last = atomicAdd(&ctl->arrivals, 1u) == gridDim.x - 1;
     __syncthreads();
     if (!last) return;
-    if (threadIdx.x == 0) *arrivals = 0;
+    if (threadIdx.x == 0) {
+        ctl->arrivals = 0;
+        ctl->epoch = epoch + 1;
+    }
     if (threadIdx.x < world) {
         __threadfence_system();
         st_release_sys(peers.flags[threadIdx.x] + rank, epoch + 1);
@@ -295,7 +333,7 @@ __global__ void __launch_bounds__(kThreads) allreduce_mean_bulk_kernel(Peers pee
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         timing[2] = t;
-        if (!wait_all(local_flags, world, epoch + 1)) atomicOr(status, 2u);
+        if (ok && !wait_all(local_flags, world, epoch + 1, spin_limit)) report_failure(ctl, host_status, 2u, peers.data[rank], offset, count);
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         timing[3] = t;
     }
@@ -313,7 +351,11 @@ struct amp_bucket {
     amp::bucket::Peers peers;
     void *opened[2 * amp::bucket::kMaxWorld];
     int n_opened;
-    uint32_t epoch;       // last epoch used
+    int64_t user_floats;  // size the caller asked for (floats is rounded up to a whole quad)
+    long long spin_limit; // SM cycles a rank waits for its peers before it gives up (loudly)
+    volatile uint32_t *host_status;  // mapped pinned word the kernels write on failure; read without a sync by the next call
+    uint32_t *host_status_dev;       // its device alias
+    bool bulk;            // AMP_B200_BUCKET_BULK, read once at create
     bool connected;
 };
 
@@ -329,6 +371,7 @@ int amp_bucket_destroy(amp_bucket_t *b) {
     if (b->data) cudaFree(b->data);
     if (b->flags) cudaFree(b->flags);
     if (b->timing) cudaFree(b->timing);
+    if (b->host_status) cudaFreeHost(const_cast<uint32_t *>(b->host_status));
     delete b;
     return AMP_OK;
 }
@@ -345,11 +388,30 @@ int amp_bucket_create(int64_t floats, int32_t world, int32_t rank, amp_bucket_t 
     b->world = world;
     b->rank = rank;
     b->floats = (floats + 3) / 4 * 4;
+    b->user_floats = floats;
+    b->spin_limit = kDefaultSpinLimitCycles;
+    if (const char *ms = getenv("AMP_B200_BUCKET_TIMEOUT_MS")) b->spin_limit = std::max(1LL, atoll(ms)) * 2000000LL;  // ~2 GHz
+    const char *bulk_env = getenv("AMP_B200_BUCKET_BULK");  // 0 selects the load/store kernel; read once per handle
+    b->bulk = !(bulk_env && bulk_env[0] == '0') && world <= 8;
     AMP_CUDA_TRY(cudaGetDevice(&b->device));
     cudaError_t e = cudaMalloc((void **)&b->data, (size_t)b->floats * 4);
     if (e == cudaSuccess) e = cudaMemset(b->data, 0, (size_t)b->floats * 4);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&b->flags, (kMaxWorld + 2) * sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaMemset(b->flags, 0, (kMaxWorld + 2) * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&b->flags, kMaxWorld * sizeof(uint32_t) + sizeof(Control));
+    if (e == cudaSuccess) e = cudaMemset(b->flags, 0, kMaxWorld * sizeof(uint32_t) + sizeof(Control));
+    if (e == cudaSuccess) {
+        void *hs = nullptr;
+        e = cudaHostAlloc(&hs, sizeof(uint32_t), cudaHostAllocMapped);
+        if (e == cudaSuccess) {
+            b->host_status = static_cast<volatile uint32_t *>(hs);
+            *b->host_status = 0;
+            e = cudaHostGetDevicePointer((void **)&b->host_status_dev, hs, 0);
+        }
+    }
+    if (e == cudaSuccess && world <= 8) {  // opt-in shared memory of the bulk kernels: once per handle, not per call
+        e = cudaFuncSetAttribute(allreduce_mean_bulk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBulkStages * 3 * kChunkBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(allreduce_mean_bulk_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBulkStages * 5 * kChunkBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(allreduce_mean_bulk_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBulkStages * 9 * kChunkBytes);
+    }
     if (e == cudaSuccess) e = cudaMalloc((void **)&b->timing, 4 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(b->timing, 0, 4 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -408,36 +470,39 @@ int amp_bucket_allreduce_mean(amp_bucket_t *b, int64_t offset_floats, int64_t co
     AMP_REQUIRE(offset_floats >= 0 && count >= 0 && offset_floats % 4 == 0 && offset_floats + count <= b->floats,
                 "amp_bucket_allreduce_mean: range [%lld, +%lld) outside the bucket of %lld floats or not 16-byte aligned",
                 (long long)offset_floats, (long long)count, (long long)b->floats);
+    if (const uint32_t failed = *b->host_status)  // written by an EARLIER call's kernel on this handle; no synchronisation needed
+        return fail(AMP_ECUDA,
+                    "amp_bucket_allreduce_mean: an earlier all-reduce on this bucket timed out waiting for a peer (status bits 0x%x): the "
+                    "replicas have diverged; the local gradient range was poisoned with NaN", failed & 0x7fffffffu);
     if (count == 0 || b->world == 1) return AMP_OK;
-    const long long padded = (count + 3) / 4 * 4;  // the bucket is padded to whole quads; the tail floats are zero everywhere
-    AMP_REQUIRE(offset_floats + padded <= b->floats, "amp_bucket_allreduce_mean: range end is not quad-aligned inside the bucket");
+    // whole quads move; a ragged count is only accepted when the range ends at the end of the bucket (whose padding floats are
+    // zero on every rank) -- inside the bucket the floats after a ragged end may be another producer's unfinished gradients
+    AMP_REQUIRE(count % 4 == 0 || offset_floats + count == b->user_floats,
+                "amp_bucket_allreduce_mean: count %lld is not a multiple of 4 and the range does not end at the bucket's end (%lld floats)",
+                (long long)count, (long long)b->user_floats);
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    (void)cudaStreamIsCapturing(as_stream(stream), &cap);  // capture is fine: the epoch is device state (see the kernels)
+    const long long padded = (count + 3) / 4 * 4;
     const long long per = (padded / 4 + b->world - 1) / b->world;
-    b->epoch += 2;
-    unsigned int *arrivals = reinterpret_cast<unsigned int *>(b->flags + kMaxWorld);
-    uint32_t *status = b->flags + kMaxWorld + 1;
+    Control *ctl = reinterpret_cast<Control *>(b->flags + kMaxWorld);
     auto launch = [&](auto kern, int u) {
         const int grid = (int)std::max<long long>(1, std::min<long long>((per + (long long)u * kThreads - 1) / ((long long)u * kThreads), 8LL * sm_count()));
-        kern<<<grid, kThreads, 0, as_stream(stream)>>>(b->peers, b->rank, b->world, offset_floats, padded, b->epoch - 1, arrivals, status, b->timing);
+        kern<<<grid, kThreads, 0, as_stream(stream)>>>(b->peers, b->rank, b->world, offset_floats, padded, ctl, b->host_status_dev, b->spin_limit,
+                                                        b->timing);
     };
     // default: the bulk-copy kernel (2 GPUs, 2.65 M floats: 34.8 us against 39.3 us with per-thread peer loads / stores and
     // 51.5 us for NCCL all-reduce + divide); AMP_B200_BUCKET_BULK=0 selects the load/store kernel, which also serves > 8 ranks
-    const char *bulk_env = getenv("AMP_B200_BUCKET_BULK");
-    const bool bulk = !(bulk_env && bulk_env[0] == '0') && b->world <= 8;
-    if (bulk) {
+    if (b->bulk) {
         const long long chunks = (per + kChunkQuads - 1) / kChunkQuads;
         const int grid = (int)std::max<long long>(1, std::min<long long>(chunks, 4LL * sm_count()));
-        auto launch_bulk = [&](auto kern, int maxw) -> cudaError_t {
+        auto launch_bulk = [&](auto kern, int maxw) {
             const size_t smem = (size_t)kBulkStages * (maxw + 1) * kChunkBytes;
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            kern<<<grid, kThreads, smem, as_stream(stream)>>>(b->peers, b->rank, b->world, offset_floats, padded, b->epoch - 1, arrivals,
-                                                               status, b->timing);
-            return cudaSuccess;
+            kern<<<grid, kThreads, smem, as_stream(stream)>>>(b->peers, b->rank, b->world, offset_floats, padded, ctl, b->host_status_dev,
+                                                               b->spin_limit, b->timing);
         };
-        cudaError_t e = b->world <= 2 ? launch_bulk(allreduce_mean_bulk_kernel<2>, 2)
-                        : b->world <= 4 ? launch_bulk(allreduce_mean_bulk_kernel<4>, 4)
-                                        : launch_bulk(allreduce_mean_bulk_kernel<8>, 8);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(allreduce_mean_bulk_kernel)");
+        if (b->world <= 2) launch_bulk(allreduce_mean_bulk_kernel<2>, 2);
+        else if (b->world <= 4) launch_bulk(allreduce_mean_bulk_kernel<4>, 4);
+        else launch_bulk(allreduce_mean_bulk_kernel<8>, 8);
     } else if (b->world <= 2) launch(allreduce_mean_kernel<2, 4>, 4);
     else if (b->world <= 4) launch(allreduce_mean_kernel<4, 4>, 4);
     else if (b->world <= 8) launch(allreduce_mean_kernel<8, 2>, 2);
@@ -455,7 +520,7 @@ int amp_bucket_last_timing(amp_bucket_t *b, void *stream, uint64_t *stamps4) {
 
 int amp_bucket_poll_status(amp_bucket_t *b, void *stream, uint32_t *status) {
     AMP_REQUIRE(b && status, "amp_bucket_poll_status: NULL argument");
-    AMP_CUDA_TRY(cudaMemcpyAsync(status, b->flags + kMaxWorld + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, as_stream(stream)));
+    AMP_CUDA_TRY(cudaMemcpyAsync(status, b->flags + kMaxWorld + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, as_stream(stream)));  // Control::status
     AMP_CUDA_TRY(cudaStreamSynchronize(as_stream(stream)));
     return AMP_OK;
 }

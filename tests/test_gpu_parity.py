@@ -59,7 +59,7 @@ def check_amp_obs(got, want, blend, D, K):
     tn = slice(2 * D + 1, 2 * D + 7)
     lerp_cols = np.r_[0 : 2 * D + 1, 2 * D + 7 : A]
     bit_equal(g[:, lerp_cols], w[:, lerp_cols])
-    close(g[:, tn], w[:, tn], atol=ATOL * np.maximum(1.0, np.abs(blend))[:, None])
+    close(g[:, tn], w[:, tn])  # the stated bar, also for extrapolated history frames (|blend| up to K-1)
 
 
 @pytest.fixture(scope="module")
@@ -200,9 +200,7 @@ def test_sample_and_collect_vs_oracle_seeded(loaders, amp, name):
     assert np.array_equal(i0, r0) and np.array_equal(i1, r1) and np.array_equal(blend.view(np.int64), rb.view(np.int64))
     for key, got, want in zip(OUT_NAMES, loader.sample(n, times=times, motion_ids=ids), ora.sample(n, times=times, motion_ids=ids)):
         if key == "body_rot":
-            close(got, want, atol=ATOL * np.maximum(1.0, np.abs(rb))[:, None, None])
-            inside = (rb >= 0) & (rb <= 1)  # plain interpolation: the stated bar, unscaled
-            close(got[torch.from_numpy(inside).cuda()], want[torch.from_numpy(inside)])
+            close(got, want)  # the stated bar, extrapolated frames (blend outside [0, 1]) included
         else:
             bit_equal(got, want)
     robot = amp.robot_for_clip(loader.dof_names)

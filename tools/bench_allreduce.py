@@ -55,7 +55,7 @@ def main():
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
 
     # 1. correctness against NCCL, many calls back to back, odd sub-ranges
-    for it, (off, cnt) in enumerate([(0, a.numel), (0, a.numel), (4, a.numel - 7), (1024, 1001), (0, 4), (0, a.numel)]):
+    for it, (off, cnt) in enumerate([(0, a.numel), (0, a.numel), (4, a.numel - 4), (1024, 1000), (0, 4), (8, (a.numel - 8) // 4 * 4), (0, a.numel)]):
         src = torch.randn(a.numel, device=dev, generator=g) * (1.0 + rank)
         bucket.flat[: a.numel].copy_(src)
         want = src.clone()
@@ -81,6 +81,36 @@ def main():
     if bucket.poll_status() != 0:
         ok = False
         notes.append("device status word set")
+    try:  # a ragged range that ends INSIDE the bucket would average up to 3 floats it was not asked to touch: refused
+        bucket.all_reduce_mean(0, 1001)
+        ok = False
+        notes.append("ragged interior range was accepted")
+    except amp.AmpB200Error:
+        pass
+
+    # 1b. the all-reduce inside a CUDA graph: the barrier epochs are device state, so every replay uses fresh ones
+    src = torch.randn(a.numel, device=dev, generator=g) * (1.0 + rank)
+    staged = src.clone()
+
+    def graph_body():
+        bucket.flat[: a.numel].copy_(staged)
+        bucket.all_reduce_mean(0, a.numel)
+
+    graph = amp.capture_step(graph_body, dev, warmup=2)
+    want = src.clone()
+    dist.all_reduce(want, op=dist.ReduceOp.SUM)
+    want /= world
+    for rep in range(4):
+        graph.replay()
+        torch.cuda.synchronize(dev)
+        err = float((bucket.flat[: a.numel] - want).abs().max())
+        if not err <= 1e-5 * max(1.0, float(want.abs().max())):
+            ok = False
+            notes.append(f"graph replay {rep}: max err {err:.3e}")
+    bucket.all_reduce_mean(0, a.numel)  # and eager calls still interleave with replays
+    if bucket.poll_status() != 0:
+        ok = False
+        notes.append("device status word set after graph replays")
 
     # 2. gradients produced in place by the discriminator update
     in_features, hidden, B = 166, (1024, 512), 512
