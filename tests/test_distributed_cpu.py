@@ -93,5 +93,5 @@ def test_bench_reference_arm_under_torchrun_only_rank0_prints(tmp_path):
     lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 1
     rec = json.loads(lines[0])
-    assert rec["impl"] == "reference" and rec["n_gpus"] == 2 and rec["cpu_baseline"]["kind"] == "port"
+    assert rec["impl"] == "reference" and rec["n_gpus"] == 2 and rec["cpu_baseline"]["kind"] in ("reference", "port")
     assert rec["e2e"]["h2d_bytes_per_step"] == 0 and rec["value"] > 0 and rec["unit"] == "samples/s"
