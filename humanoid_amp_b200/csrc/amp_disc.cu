@@ -10,10 +10,11 @@
 //   logit  = h2 . w3 + b3                 fp32, folded into the TMEM read-out of layer 2 (one thread owns one row)
 //   reward = -log(max(1 - 1/(1+exp(-logit)), 1e-4)) * scale
 //
-// Structure: see disc_fused_kernel below (one persistent CTA per SM, 320 threads, warp-specialised: TMA producer, single
-// thread tcgen05.mma issuer, two sets of four epilogue warps).  Rows are processed in chunks whose bf16 x_hat stays
-// L2-resident between the scaler/cast kernel and the fused kernel; the cast of chunk c+1 runs on a side stream under the
-// fused kernel of chunk c.
+// Structure: see disc_fused_kernel below -- ONE persistent launch per call (one CTA per SM, 448 threads, warp-specialised:
+// TMA producer, single-thread tcgen05.mma issuer, two sets of four epilogue warps, four scaler/cast warps).  The scaler and
+// the bf16 cast run INSIDE the kernel: the cast warps read the fp32 rows of the CTA's next row tile straight from the
+// caller's buffer (or gather them through row_index), normalise, round to bf16 and park the tile in a per-CTA, L2-resident
+// scratch slot that the TMA producer then streams into the operand ring.  No x_hat workspace in HBM, no second kernel.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -22,6 +23,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "amp_internal.h"
 #include "amp_math.cuh"
@@ -69,15 +71,23 @@ constexpr uint32_t kInstrDescPair = (1u << 4) | (1u << 7) | (1u << 10) | ((uint3
 // (TMA delivery + shared-memory bandwidth: a 128x256x16 MMA reads 12 KB of smem per 128 cycles while TMA refills the ring
 // at the same rate) and ~2 k for accumulator hand-offs.
 //
-// Warp roles (320 threads): 0 TMA producer, 1 TMEM alloc + MMA issuer, 2..9 epilogue (warps w and w+4 share a TMEM lane
-// quarter and split the accumulator columns).  Producer, issuer and epilogue warps all walk the same static schedule.
+// Warp roles (512 threads): 0 TMA producer, 1 TMEM alloc + MMA issuer, 4..11 epilogue (warps w and w+4 share a TMEM lane
+// quarter and split the accumulator columns), 2-3 and 12-15 scaler + bf16 cast of the next row tile.  Producer, issuer and
+// epilogue warps all walk the same static schedule.
 // =====================================================================================================================
 // PAIR = true runs the same pipeline on a CTA pair (cluster of 2, tcgen05 cta_group::2): one MMA covers 256 rows (128 per
 // CTA) and each CTA stages only ITS half of the 256-row weight block, so the operand bytes delivered per SM per MMA drop
 // from 48 KB to 32 KB per K block.  ncu on the single-CTA version showed TMA loads pinned at 40 % of the xbar->L1 peak on
 // every SM (2.57 GB per 151 552 rows, ~51 B/cycle/SM) with the tensor pipe 55 % active: operand delivery, not math, is
 // the limiter, and a CTA pair is the only way to shrink it without more TMEM.
-constexpr int FUSED_THREADS = 320;
+// Warp roles by warpgroup (setmaxnreg moves registers between them: the TMEM read-out needs ~168, everything else < 88):
+//   WG0  warp 0 TMA producer, warp 1 tcgen05.mma issuer, warps 2-3 scaler/cast    (88 registers)
+//   WG1-2 warps 4-11 epilogue                                                      (168 registers)
+//   WG3  warps 12-15 scaler/cast                                                   (88 registers)
+constexpr int NUM_CONV_WARPS = 6;
+constexpr int FUSED_THREADS = 512;
+constexpr int EPI_WARP0 = 4;
+constexpr int REGS_LIGHT = 88, REGS_EPI = 168;  // 128 * (88 + 168 + 168 + 88) = 65536
 constexpr uint32_t ACC_COLS = 256;  // two accumulator regions: TMEM columns [0,256) and [256,512)
 __host__ __device__ constexpr int fused_stages(bool pair) { return pair ? 6 : 4; }
 __host__ __device__ constexpr int fused_b_bytes(bool pair) { return pair ? B_STAGE_BYTES / 2 : B_STAGE_BYTES; }
@@ -98,25 +108,44 @@ __host__ __device__ constexpr int fused_smem_bytes(bool pair) {
 template <class G1, class G2>
 __device__ __forceinline__ void walk_schedule(int T, int n1_tiles, int units, G1 &&g1, G2 &&g2) {
     if (T <= 0) return;
-    for (int nt = 0; nt < n1_tiles; ++nt) g1(0, nt, nt & 1);
     const int seg = (units + n1_tiles - 1) / n1_tiles;
-    for (int i = 0; i < T; ++i) {
+    // i = -1 is the prologue (layer 1 of the first row tile only); one call site per functor keeps the kernel small -- every
+    // role inlines its functors here and the roles share the instruction cache
+#pragma unroll 1
+    for (int i = -1; i < T; ++i) {
         int u = 0;
+#pragma unroll 1
         for (int nt = 0; nt < n1_tiles; ++nt) {
-            if (i + 1 < T) g1(i + 1, nt, 0);
-            for (const int e = min(units, u + seg); u < e; ++u) g2(i, u, 1);
+            if (i + 1 < T) g1(i + 1, nt, i < 0 ? (nt & 1) : 0);
+            if (i >= 0) {
+#pragma unroll 1
+                for (const int e = min(units, u + seg); u < e; ++u) g2(i, u, 1);
+            }
         }
     }
 }
 
 struct FusedParams {
-    int M;          // rows of this launch (x_hat rows)
+    int64_t M;      // rows of this call
+    // scaler + cast stage (converter warps): source rows, statistics, the CTA-private bf16 scratch slots
+    const float *x;            // (rows, in_features) fp32, row pitch x_stride floats
+    int64_t x_stride;
+    const int64_t *row_index;  // NULL: row r of the batch is x[r]; else x[row_index[r]] with x holding `capacity` rows
+    int64_t capacity;
+    uint32_t *flags;           // bit 1 raised by an out-of-range row_index (may be NULL)
+    const float *mean, *denom; // fp32 [in_features]: (float)running_mean, sqrt((float)running_variance) + 1e-8
+    __nv_bfloat16 *xs;         // (gridDim.x * 2 * 128, Kp) bf16: two x_hat row-tile slots per CTA, L2-resident
+    int in_features, Kp;
+    int x_vec;                 // rows are 8-byte aligned: float2 loads
+    int xhat_rows_in_order;    // wide inputs (Kp > 256): tmap_x covers a bf16 x_hat of the whole batch written by
+                               // normalise_cast_kernel, the converter warps idle
+    int x_prefetch;            // rows in order, 16-byte aligned row tiles, pitch < 2 x in_features: bulk L2 prefetch of the next tile
     int kb1;        // K blocks of layer 1 (Kp / 64)
-    int ksteps1_last;  // 16-wide K steps the LAST layer-1 block really needs: ceil((in_features [+ 2] - 64 (kb1 - 1)) / 16), 1..4
-    int fold_bias1;    // b1 travels inside the layer-1 product (two padding columns of x_hat / W1): D1 is cvt + max only
+    int ksteps1_last;  // 16-wide K steps the LAST layer-1 block really needs: ceil((in_features + 2 - 64 (kb1 - 1)) / 16), 1..4
+                       // (b1 travels inside the layer-1 product: two padding columns of x_hat hold 1.0, W1 holds b1 there)
     int n1_tiles;   // h1 / 256
     int n2_tiles;   // h2 / 256
-    const float *b1, *b2, *w3, *b3;
+    const float *b2, *w3, *b3;
     float scale;
     float *reward;  // [M]
     float *logits;  // [M] or NULL
@@ -154,13 +183,14 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     const uint32_t acc_full = bars + 16 * STAGES, acc_empty = acc_full + 16;  // 2 x 8 B each, one per accumulator region
     const uint32_t h1_ready = acc_full + 32;  // 2 x 8 B
     const uint32_t tmem_slot = h1_ready + 16;
+    const uint32_t xready = bars + 160, xfree = bars + 176;  // 2 x 8 B each: x_hat scratch slot filled / fully consumed
     const uint32_t part_smem = bars + 256;  // 2 x 4 x 32 floats
     uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
     const bool leader = rank == 0;
-    const int num_m_tiles = (p.M + BM - 1) / BM;
+    const int num_m_tiles = (int)((p.M + BM - 1) / BM);
     // work unit = one 128-row tile per CTA; a pair takes two consecutive tiles (a 256-row block) so both CTAs always walk
     // the same schedule (the second tile of the last block may lie entirely past M: TMA zero-fills, stores are clipped)
     const int group = PAIR ? (int)blockIdx.x / 2 : (int)blockIdx.x;
@@ -188,6 +218,10 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         }
         mbar_init(h1_ready, 8);  // one arrival per epilogue warp
         mbar_init(h1_ready + 8, 8);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(xready + 8 * i, NUM_CONV_WARPS);  // one arrival per converter warp
+            mbar_init(xfree + 8 * i, 1);                // the producer, once the slot's last TMA read has landed
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {  // the same warp of both CTAs of a pair allocates (all 512 columns) and later frees
@@ -203,13 +237,18 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    const bool is_epilogue_warp = warp >= EPI_WARP0 && warp < EPI_WARP0 + NUM_EPI_THREADS / 32;
     // accumulator-drained barriers live in the leader CTA; the epilogue threads of both CTAs arrive there
     const uint32_t acc_empty_at_leader = PAIR ? mapa_rank(acc_empty, 0) : acc_empty;  // + 8 * region
     auto arrive_drained = [&](uint32_t addr) {
         if constexpr (PAIR) mbar_arrive_cluster(addr); else mbar_arrive(addr);
     };
 
-    if (warp == 0) {
+    // setmaxnreg sits at the top of each warpgroup's own branch so that ptxas budgets the code it dominates accordingly
+    if (!is_epilogue_warp) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_LIGHT));
+    if (is_epilogue_warp) {
+        // handled in the last branch below
+    } else if (warp == 0) {
         // ================= TMA producer (every CTA loads its own rows of A and its own part of the weight block) =========
         if (lane == 0) {
             int stage = 0;
@@ -219,6 +258,11 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             // back within a few microseconds), evict_first on its last pass -- marking it evict_last made 192 MB of x_hat
             // per launch compete with the 77.6 MB of h1 slots for the protected part of L2.
             const uint64_t keep = l2_policy_evict_last(), stream = l2_policy_evict_first(), normal = l2_policy_evict_normal();
+            // x_hat scratch slots: slot s is handed back to the converter warps once every TMA read of it has landed, which
+            // is known STAGES ring acquisitions after its last load was issued (the MMA that freed that stage had waited
+            // for the load, and for every load before it)
+            long long loads_issued = 0, free_at = 0;
+            int free_slot = -1;
             auto load_pair = [&](const CUtensorMap *ma, int a_col, int a_row, uint64_t a_policy, const CUtensorMap *mb, int b_col,
                                  int b_row) {
                 {
@@ -227,6 +271,11 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                     AMP_PROF_ADD(w_empty);
                 }
                 const uint32_t fb = full_bar + 8 * stage;
+#ifdef AMP_DISC_PROFILE
+                if (p.prof_mode & 16) {  // timing experiment: no TMA loads, the MMAs run on whatever the stage holds
+                    if (!PAIR || leader) mbar_arrive(fb);
+                } else
+#endif
                 if constexpr (PAIR) {
                     if (leader) mbar_arrive_expect_tx(fb, STAGE_TX);  // bytes of both CTAs are credited to the leader's barrier
                     const uint32_t fb_leader = mapa_rank(fb, 0);
@@ -238,14 +287,36 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                     tma_load_2d_hint(smem_b + stage * B_BYTES, mb, b_col, b_row, fb, keep);
                 }
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                ++loads_issued;
+                if (free_slot >= 0 && loads_issued >= free_at) {
+                    mbar_arrive(xfree + 8 * free_slot);
+                    free_slot = -1;
+                }
             };
             walk_schedule(
                 T, p.n1_tiles, units,
                 [&](int ti, int nt, int) {
-                    const int m = tile_of(ti);
-                    // x_hat is read by the four N1 tiles of this row tile and never again: stream it on the last pass
+                    if (p.xhat_rows_in_order) {
+                        // x_hat of the whole batch was prepared by the cast kernel (wide inputs): plain row-tile reads, streamed
+#pragma unroll 1
+                        for (int kb = 0; kb < p.kb1; ++kb)
+                            load_pair(&tmap_x, kb * BK, tile_of(ti) * BM, nt == p.n1_tiles - 1 ? stream : normal, &tmap_w1, kb * BK, nt * BN);
+                        return;
+                    }
+                    if (nt == 0) {  // the converter warps have parked x_hat of this row tile in slot ti & 1
+                        AMP_PROF_T0;
+                        mbar_wait(xready + 8 * (ti & 1), (uint32_t)((ti >> 1) & 1));
+                        AMP_PROF_ADD(w_h1);
+                        asm volatile("fence.proxy.async.global;" ::: "memory");
+                    }
+                    // the slot is re-read by the four N1 tiles of this row tile and then overwritten in place: keep it in L2
+#pragma unroll 1
                     for (int kb = 0; kb < p.kb1; ++kb)
-                        load_pair(&tmap_x, kb * BK, m * BM, nt == p.n1_tiles - 1 ? stream : normal, &tmap_w1, kb * BK, nt * BN);
+                        load_pair(&tmap_x, kb * BK, slot_row0 + (ti & 1) * BM, keep, &tmap_w1, kb * BK, nt * BN);
+                    if (nt == p.n1_tiles - 1) {
+                        free_slot = ti & 1;
+                        free_at = loads_issued + STAGES;
+                    }
                 },
                 [&](int ti, int u, int) {
                     const int n2 = u / kb2, kb = u - n2 * kb2;
@@ -293,6 +364,9 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 #pragma unroll
                 for (int k = 0; k < BK / UMMA_K; ++k) {
                     if (k >= ksteps) break;
+#ifdef AMP_DISC_PROFILE
+                    if (p.prof_mode & 8) break;  // timing experiment: operands are delivered but no MMA is issued
+#endif
                     if constexpr (PAIR) umma_bf16_pair(d_tmem, a0 + 2 * k, b0 + 2 * k, kInstrDescPair, (uint32_t)(!first || k != 0));
                     else umma_bf16(d_tmem, a0 + 2 * k, b0 + 2 * k, kInstrDesc, (uint32_t)(!first || k != 0));
                 }
@@ -310,6 +384,7 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                 T, p.n1_tiles, units,
                 [&](int, int, int r) {
                     acquire_acc(r, w_d1);
+#pragma unroll 1
                     for (int kb = 0; kb < p.kb1; ++kb)
                         mma_block(tmem_base + r * ACC_COLS, kb == 0, kb == p.kb1 - 1 ? p.ksteps1_last : BK / UMMA_K);
                     commit(acc_full + 8 * r);
@@ -338,14 +413,115 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         }
         __syncwarp();
     } else {
-        // ================= epilogue warps 2..9: both accumulators, columns split between the two warps of a TMEM quarter ======
+        // ================= converter warps 2, 3, 12..15: RunningStandardScaler (eval form) + bf16 cast of the CTA's row tiles =====
+        //   x_hat = clamp((x - mean) * (1 / denom), -5, 5) -> bf16, zero padded to Kp (ones in the two bias columns)
+        // One pass per K-block (64 columns): lane l owns the column pair (2l, 2l+1) of the block, so a load is a coalesced
+        // 8-byte-per-lane row segment, a store a coalesced 4-byte-per-lane one, and the block's statistics are four
+        // registers.  Eight rows are in flight per warp.  (x - mean) / denom is evaluated with an IEEE reciprocal: at most
+        // 1 ulp (fp32) from the division and rounded to bf16 right after.  Rows past M are written as zeros.  Tile ti goes to
+        // slot ti & 1 of this CTA's scratch (two slots: the tile the layer-1 MMAs are reading and the one being prepared);
+        // the slot comes back through xfree.  The loop nest is deliberately NOT unrolled beyond the eight rows: this code
+        // shares the instruction cache with the TMEM read-out (ncu: no_instruction was the top stall of both).
+        const int cw = warp < EPI_WARP0 ? warp - 2 : warp - (EPI_WARP0 + NUM_EPI_THREADS / 32) + 2;
+        constexpr int RIF = 8;  // rows in flight per warp
+        __nv_bfloat16 *const my_slots = p.xs + (size_t)slot_row0 * p.Kp;
+        for (int ti = 0; ti < (p.xhat_rows_in_order ? 0 : T); ++ti) {
+            const int s = ti & 1;
+            if (ti >= 2) mbar_wait(xfree + 8 * s, (uint32_t)(((ti >> 1) - 1) & 1));
+            const int64_t row_base = (int64_t)tile_of(ti) * BM;
+            __nv_bfloat16 *const dst = my_slots + (size_t)s * BM * p.Kp;
+            // pull the fp32 rows of the NEXT tile into L2 while this one is converted: the loads below are latency-bound
+            // (registers cap the bytes in flight), an L2 hit costs a third of a DRAM access
+            if (cw == 0 && lane == 0 && p.x_prefetch && ti + 1 < T) {
+                const int64_t next_base = (int64_t)tile_of(ti + 1) * BM;
+                const int64_t rows_next = min((int64_t)BM, p.M - next_base);
+                if (rows_next > 0) {
+                    const char *a = reinterpret_cast<const char *>(p.x + next_base * p.x_stride);
+                    const uint32_t bytes = (uint32_t)((rows_next * p.x_stride * 4) & ~(int64_t)15);
+                    if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(bytes) : "memory");
+                }
+            }
+#ifdef AMP_DISC_PROFILE
+            if (p.prof_mode & 4) {  // timing experiment: no conversion work at all (wrong results)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(xready + 8 * s);
+                continue;
+            }
+#endif
+#pragma unroll 1
+            for (int kb = 0; kb < p.kb1; ++kb) {
+                const int c = 2 * (lane + 32 * kb);
+                const bool in0 = c < p.in_features, in1 = c + 1 < p.in_features;
+                const bool wide = p.x_vec && in1;
+                float2 mu = make_float2(in0 ? __ldg(p.mean + c) : 0.0f, in1 ? __ldg(p.mean + c + 1) : 0.0f);
+                float2 rc = make_float2(in0 ? __frcp_rn(__ldg(p.denom + c)) : 0.0f, in1 ? __frcp_rn(__ldg(p.denom + c + 1)) : 0.0f);
+                // bias columns: x is read as 0 there, (0 - (-1)) * 1 = 1
+                if (!in0 && c < p.in_features + 2) { mu.x = -1.0f; rc.x = 1.0f; }
+                if (!in1 && c + 1 < p.in_features + 2) { mu.y = -1.0f; rc.y = 1.0f; }
+                auto source_row = [&](int64_t grow) -> const float * {  // first float of this lane's pair in batch row grow
+                    int64_t sr = grow;
+                    if (p.row_index) {
+                        sr = __ldg(p.row_index + grow);
+                        if (sr < 0 || sr >= p.capacity) {
+                            if (lane == 0 && p.flags) atomicOr(p.flags, 2u);
+                            sr = 0;
+                        }
+                    }
+                    return p.x + sr * p.x_stride + c;
+                };
+                auto emit = [&](int r, float2 x, bool live) {
+                    const float a = fminf(fmaxf(__fmul_rn(__fsub_rn(x.x, mu.x), rc.x), -5.0f), 5.0f);
+                    const float b = fminf(fmaxf(__fmul_rn(__fsub_rn(x.y, mu.y), rc.y), -5.0f), 5.0f);
+                    reinterpret_cast<__nv_bfloat162 *>(dst + (size_t)r * p.Kp)[lane + 32 * kb] =
+                        live ? __floats2bfloat162_rn(a, b) : __floats2bfloat162_rn(0.0f, 0.0f);
+                };
+                if (wide || !in0) {  // 8-byte loads (or a pure padding pair: nothing to load), eight rows in flight
+#pragma unroll 1
+                    for (int r0 = cw; r0 < BM; r0 += NUM_CONV_WARPS * RIF) {
+                        float2 v[RIF];
+#pragma unroll
+                        for (int q = 0; q < RIF; ++q) {
+                            const int r = r0 + q * NUM_CONV_WARPS;
+                            const int64_t grow = row_base + r;
+                            v[q] = make_float2(0.0f, 0.0f);
+                            if (wide && r < BM && grow < p.M) v[q] = __ldcs(reinterpret_cast<const float2 *>(source_row(grow)));
+                        }
+#pragma unroll
+                        for (int q = 0; q < RIF; ++q) {
+                            const int r = r0 + q * NUM_CONV_WARPS;
+                            if (r < BM) emit(r, v[q], row_base + r < p.M);
+                        }
+                    }
+                } else {  // odd pitch / unaligned base / the last column of an odd width: 4-byte loads, one row at a time
+#pragma unroll 1
+                    for (int r = cw; r < BM; r += NUM_CONV_WARPS) {
+                        const int64_t grow = row_base + r;
+                        float2 x = make_float2(0.0f, 0.0f);
+                        if (grow < p.M) {
+                            const float *xr = source_row(grow);
+                            x.x = __ldcs(xr);
+                            if (in1) x.y = __ldcs(xr + 1);
+                        }
+                        emit(r, x, grow < p.M);
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy global writes -> visible to the TMA loads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(xready + 8 * s);
+        }
+    }
+    if (is_epilogue_warp) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
+        // ================= epilogue warps 4..11: both accumulators, columns split between the two warps of a TMEM quarter ======
         // Warp w and warp w+4 own the same 32 TMEM lanes (rows); w takes columns [0,128) of every 256-column accumulator and
-        // w+4 takes [128,256), so each drain is half as long as with one warp per quarter -- the issuer's in-kernel cycle
-        // counters showed it waiting ~20 % of the time for D2 and ~12 % for D1 to be drained.  The warps follow the issuer's
-        // schedule: D1 tiles (bias + ReLU -> bf16 -> swizzled slab -> TMA store of h1) and, after the last K block of each
-        // layer-2 N tile, D2 (bias + ReLU -> dot with w3).  tcgen05.ld of the next 32 columns is in flight while the current
-        // 32 are processed.
-        const int ew = warp - 2;
+        // w+4 takes [128,256), so each drain is half as long as with one warp per quarter.  The warps follow the issuer's
+        // schedule: D1 tiles (ReLU -> bf16 -> swizzled slab -> TMA store of h1; the bias rides inside the product) and, after
+        // the last K block of each layer-2 N tile, D2 (bias + ReLU -> dot with w3).  tcgen05.ld of the next 32 columns is in
+        // flight while the current 32 are processed.  Both read-out loops are unrolled by two only (the double-buffered TMEM
+        // registers need static indices): fully unrolled they were a third of a 113 KB kernel and instruction-cache misses
+        // (ncu: stall_no_inst) were the top stall reason of these warps.
+        const int ew = warp - EPI_WARP0;
         const int quarter = warp & 3;
         const int colhalf = ew >> 2;
         const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
@@ -372,80 +548,57 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                 tcgen05_fence_after();
                 uint32_t v[2][32];
                 tmem_ld_32x32(acc, v[0]);
+#pragma unroll 1
+                for (int hp = 0; hp < 4; hp += 2) {
 #pragma unroll
-                for (int h = 0; h < 4; ++h) {  // four steps of 32 columns = four slabs
-                    const int col = nt * BN + (int)col_base + h * 32;  // h1 column of this step
-                    const float4 *bias4 = reinterpret_cast<const float4 *>(p.b1 + col);
-                    float4 bb[8];
-                    if (!p.fold_bias1) {  // launch-uniform
-#ifdef AMP_DISC_PROFILE
-                        if (p.prof_mode & 2) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) bb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        } else
-#endif
+                    for (int hh = 0; hh < 2; ++hh) {  // four steps of 32 columns = four slabs
+                        const int h = hp + hh;
+                        const int col = nt * BN + (int)col_base + h * 32;  // h1 column of this step
+                        const uint32_t slab = staging + (uint32_t)((ew * 2 + (store_it & 1)) * STORE_SLAB_BYTES);
                         {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) bb[j] = __ldg(bias4 + j);
+                            AMP_PROF_T0;
+                            if (lane == 0) bulk_wait_read<1>();  // the store that last read this slab has drained it
+                            __syncwarp();
+                            AMP_PROF_ADD(e_slab);
                         }
-                    }
-                    const uint32_t slab = staging + (uint32_t)((ew * 2 + (store_it & 1)) * STORE_SLAB_BYTES);
-                    {
-                        AMP_PROF_T0;
-                        if (lane == 0) bulk_wait_read<1>();  // the store that last read this slab has drained it
-                        __syncwarp();
-                        AMP_PROF_ADD(e_slab);
-                    }
-                    tmem_ld_wait();  // v[h & 1] has landed
-                    if (h + 1 < 4) {
-                        tmem_ld_32x32(acc + (uint32_t)((h + 1) * 32), v[(h + 1) & 1]);
-                    } else {  // last TMEM read of this accumulator by this warp: release the region to the issuer now
-                        tcgen05_fence_before();
-                        __syncwarp();
-                        if (lane == 0) arrive_drained(acc_empty_at_leader + 8 * r);
+                        tmem_ld_wait();  // v[hh] has landed
+                        if (h + 1 < 4) {
+                            tmem_ld_32x32(acc + (uint32_t)((h + 1) * 32), v[hh ^ 1]);
+                        } else {  // last TMEM read of this accumulator by this warp: release the region to the issuer now
+                            tcgen05_fence_before();
+                            __syncwarp();
+                            if (lane == 0) arrive_drained(acc_empty_at_leader + 8 * r);
 #ifdef AMP_DISC_PROFILE
-                        e_t2 = clock64();
+                            e_t2 = clock64();
 #endif
-                    }
-                    const uint32_t(&cur)[32] = v[h & 1];
-#ifdef AMP_DISC_PROFILE
-                    if (p.prof_mode & 1) { ++store_it; continue; }
-#endif
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {  // 16-byte chunk j of this thread's 64-byte slab row
-                        __nv_bfloat162 p0, p1, p2, p3;
-                        if (p.fold_bias1) {
-                            // the accumulator already holds x W1^T + b1: round, then ReLU on the packed pair (rounding is
-                            // monotonic and keeps the sign, so max(round(x), 0) == round(max(x, 0))): 1 instruction per element
-                            const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.0f, 0.0f);
-                            p0 = __hmax2(__floats2bfloat162_rn(__uint_as_float(cur[8 * j + 0]), __uint_as_float(cur[8 * j + 1])), zero2);
-                            p1 = __hmax2(__floats2bfloat162_rn(__uint_as_float(cur[8 * j + 2]), __uint_as_float(cur[8 * j + 3])), zero2);
-                            p2 = __hmax2(__floats2bfloat162_rn(__uint_as_float(cur[8 * j + 4]), __uint_as_float(cur[8 * j + 5])), zero2);
-                            p3 = __hmax2(__floats2bfloat162_rn(__uint_as_float(cur[8 * j + 6]), __uint_as_float(cur[8 * j + 7])), zero2);
-                        } else {
-                            const float4 b0 = bb[2 * j], b1v = bb[2 * j + 1];
-                            p0 = __floats2bfloat162_rn(fmaxf(__uint_as_float(cur[8 * j + 0]) + b0.x, 0.0f),
-                                                       fmaxf(__uint_as_float(cur[8 * j + 1]) + b0.y, 0.0f));
-                            p1 = __floats2bfloat162_rn(fmaxf(__uint_as_float(cur[8 * j + 2]) + b0.z, 0.0f),
-                                                       fmaxf(__uint_as_float(cur[8 * j + 3]) + b0.w, 0.0f));
-                            p2 = __floats2bfloat162_rn(fmaxf(__uint_as_float(cur[8 * j + 4]) + b1v.x, 0.0f),
-                                                       fmaxf(__uint_as_float(cur[8 * j + 5]) + b1v.y, 0.0f));
-                            p3 = __floats2bfloat162_rn(fmaxf(__uint_as_float(cur[8 * j + 6]) + b1v.z, 0.0f),
-                                                       fmaxf(__uint_as_float(cur[8 * j + 7]) + b1v.w, 0.0f));
                         }
-                        // SWIZZLE_64B: 16-byte chunk index XOR address bits [7,9) = (row >> 1) & 3 (rows are 64 bytes)
-                        const int chunk = j ^ ((lane >> 1) & 3);
-                        st_shared_v4(slab + (uint32_t)(lane * 64 + chunk * 16), *reinterpret_cast<const uint32_t *>(&p0),
-                                     *reinterpret_cast<const uint32_t *>(&p1), *reinterpret_cast<const uint32_t *>(&p2),
-                                     *reinterpret_cast<const uint32_t *>(&p3));
+                        const uint32_t(&cur)[32] = v[hh];
+#ifdef AMP_DISC_PROFILE
+                        if (p.prof_mode & 1) { ++store_it; continue; }
+#endif
+                        // the accumulator already holds x W1^T + b1 (the bias rides in two padding columns): round, then ReLU
+                        // on the packed pair (rounding is monotonic and keeps the sign, so max(round(x), 0) == round(max(x, 0)))
+                        const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.0f, 0.0f);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {  // 16-byte chunk j of this thread's 64-byte slab row
+                            const __nv_bfloat162 p0 = __hmax2(__floats2bfloat162_rn(__uint_as_float(cur[8 * j + 0]), __uint_as_float(cur[8 * j + 1])), zero2);
+                            const __nv_bfloat162 p1 = __hmax2(__floats2bfloat162_rn(__uint_as_float(cur[8 * j + 2]), __uint_as_float(cur[8 * j + 3])), zero2);
+                            const __nv_bfloat162 p2 = __hmax2(__floats2bfloat162_rn(__uint_as_float(cur[8 * j + 4]), __uint_as_float(cur[8 * j + 5])), zero2);
+                            const __nv_bfloat162 p3 = __hmax2(__floats2bfloat162_rn(__uint_as_float(cur[8 * j + 6]), __uint_as_float(cur[8 * j + 7])), zero2);
+                            // SWIZZLE_64B: 16-byte chunk index XOR address bits [7,9) = (row >> 1) & 3 (rows are 64 bytes)
+                            const int chunk = j ^ ((lane >> 1) & 3);
+                            st_shared_v4(slab + (uint32_t)(lane * 64 + chunk * 16), *reinterpret_cast<const uint32_t *>(&p0),
+                                         *reinterpret_cast<const uint32_t *>(&p1), *reinterpret_cast<const uint32_t *>(&p2),
+                                         *reinterpret_cast<const uint32_t *>(&p3));
+                        }
+                        fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA (async proxy)
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d_hint(&tmap_h_store, slab, col, row0, h1_keep);  // the slot is overwritten in place: keep it in L2
+                            bulk_commit();
+                        }
+                        ++store_it;
                     }
-                    fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA (async proxy)
-                    __syncwarp();
-                    if (lane == 0) {
-                        tma_store_2d_hint(&tmap_h_store, slab, col, row0, h1_keep);  // the slot is overwritten in place: keep it in L2
-                        bulk_commit();
-                    }
-                    ++store_it;
                 }
 #ifdef AMP_DISC_PROFILE
                 e_wait1 += e_t1 - e_t0;
@@ -474,43 +627,50 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                 tcgen05_fence_after();
                 uint32_t v[2][32];
                 tmem_ld_32x32(acc, v[0]);
+#pragma unroll 1
+                for (int cp = 0; cp < 4; cp += 2) {
 #pragma unroll
-                for (int chunk = 0; chunk < 4; ++chunk) {
-                    const int col0 = n2 * BN + (int)col_base + chunk * 32;
-                    const float4 *bias4 = reinterpret_cast<const float4 *>(p.b2 + col0);
-                    const float4 *w4 = reinterpret_cast<const float4 *>(p.w3 + col0);
-                    float4 bb[8], ww[8];
-#ifdef AMP_DISC_PROFILE
-                    if (p.prof_mode & 2) {
+                    for (int cc = 0; cc < 2; ++cc) {
+                        const int chunk = cp + cc;
+                        const int col0 = n2 * BN + (int)col_base + chunk * 32;
+                        const float4 *bias4 = reinterpret_cast<const float4 *>(p.b2 + col0);
+                        const float4 *w4 = reinterpret_cast<const float4 *>(p.w3 + col0);
+                        float4 bb[4], ww[4];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) bb[j] = ww[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    } else
-#endif
-                    {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
+                        for (int j = 0; j < 4; ++j) {
                             bb[j] = __ldg(bias4 + j);
                             ww[j] = __ldg(w4 + j);
                         }
-                    }
-                    tmem_ld_wait();  // v[chunk & 1] has landed
-                    if (chunk + 1 < 4) {
-                        tmem_ld_32x32(acc + (uint32_t)((chunk + 1) * 32), v[(chunk + 1) & 1]);
-                    } else {  // last TMEM read: hand the region back before finishing the arithmetic
-                        tcgen05_fence_before();
-                        __syncwarp();
-                        if (lane == 0) arrive_drained(acc_empty_at_leader + 8 * r);
+                        tmem_ld_wait();  // v[cc] has landed
+                        if (chunk + 1 < 4) {
+                            tmem_ld_32x32(acc + (uint32_t)((chunk + 1) * 32), v[cc ^ 1]);
+                        } else {  // last TMEM read: hand the region back before finishing the arithmetic
+                            tcgen05_fence_before();
+                            __syncwarp();
+                            if (lane == 0) arrive_drained(acc_empty_at_leader + 8 * r);
 #ifdef AMP_DISC_PROFILE
-                        e_t2 = clock64();
+                            e_t2 = clock64();
 #endif
-                    }
-                    const uint32_t(&cur)[32] = v[chunk & 1];
+                        }
+                        const uint32_t(&cur)[32] = v[cc];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        dot[0] = fmaf(fmaxf(__uint_as_float(cur[4 * j + 0]) + bb[j].x, 0.0f), ww[j].x, dot[0]);
-                        dot[1] = fmaf(fmaxf(__uint_as_float(cur[4 * j + 1]) + bb[j].y, 0.0f), ww[j].y, dot[1]);
-                        dot[2] = fmaf(fmaxf(__uint_as_float(cur[4 * j + 2]) + bb[j].z, 0.0f), ww[j].z, dot[2]);
-                        dot[3] = fmaf(fmaxf(__uint_as_float(cur[4 * j + 3]) + bb[j].w, 0.0f), ww[j].w, dot[3]);
+                        for (int half = 0; half < 2; ++half) {  // 16 columns at a time: the second half's constants load under the first
+                            if (half == 1) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    bb[j] = __ldg(bias4 + 4 + j);
+                                    ww[j] = __ldg(w4 + 4 + j);
+                                }
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int e = 16 * half + 4 * j;
+                                dot[0] = fmaf(fmaxf(__uint_as_float(cur[e + 0]) + bb[j].x, 0.0f), ww[j].x, dot[0]);
+                                dot[1] = fmaf(fmaxf(__uint_as_float(cur[e + 1]) + bb[j].y, 0.0f), ww[j].y, dot[1]);
+                                dot[2] = fmaf(fmaxf(__uint_as_float(cur[e + 2]) + bb[j].z, 0.0f), ww[j].z, dot[2]);
+                                dot[3] = fmaf(fmaxf(__uint_as_float(cur[e + 3]) + bb[j].w, 0.0f), ww[j].w, dot[3]);
+                            }
+                        }
                     }
                 }
 #ifdef AMP_DISC_PROFILE
@@ -527,7 +687,7 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                     if (colhalf == 1) *slot = mine;
                     asm volatile("bar.sync %0, 64;" ::"r"(8 + quarter) : "memory");
                     if (colhalf == 0) {
-                        const int row = tile_of(ti) * BM + quarter * 32 + lane;
+                        const int64_t row = (int64_t)tile_of(ti) * BM + quarter * 32 + lane;
                         if (row < p.M) {
                             const float logit = (mine + *slot) + __ldg(p.b3);
                             if (p.logits) p.logits[row] = logit;
@@ -695,49 +855,33 @@ int scaler_stats_to_f32(const double *mean, const double *var, int n, float *mea
     return AMP_OK;
 }
 
-int normalise_cast_rows(const float *x, int64_t x_stride, int64_t rows, int in_features, int Kp, const float *mean_f,
-                        const float *denom_f, void *out_bf16, cudaStream_t st) {
-    if (rows <= 0) return AMP_OK;
-    const bool vec = (x_stride % 2 == 0) && ((reinterpret_cast<uintptr_t>(x) & 7u) == 0);
-    const int grid = (int)std::min<int64_t>((rows + 7) / 8, (int64_t)sm_count() * 8);
-    __nv_bfloat16 *out = static_cast<__nv_bfloat16 *>(out_bf16);
-    int rc = vec ? disc::launch_normalise_cast<true>(Kp / disc::BK, grid, st, x, x_stride, rows, in_features, mean_f, denom_f, out,
-                                                     nullptr, 0, nullptr)
-                 : disc::launch_normalise_cast<false>(Kp / disc::BK, grid, st, x, x_stride, rows, in_features, mean_f, denom_f, out,
-                                                      nullptr, 0, nullptr);
-    if (rc != AMP_OK) return rc;
-    AMP_CUDA_TRY(cudaGetLastError());
-    return AMP_OK;
-}
-
 }  // namespace amp
 
 struct amp_disc {
     int in_features, Kp, h1, h2;
-    int64_t chunk_rows;
-    int ws_ctas;  // persistent CTAs the h1 workspace was sized for
+    int ws_ctas;  // persistent CTAs the h1 / x_hat scratch slots were sized for
     int device;
     __nv_bfloat16 *W1, *W2;       // (h1, Kp), (h2, h1) bf16
     float *b1, *b2, *w3, *b3;     // fp32
     float *mean, *denom;          // fp32 [in_features]
-    __nv_bfloat16 *xhat[2], *hid; // workspaces 2 x (chunk_rows, Kp) (double buffer) and (ws_ctas * 2 * 128, h1)
-    cudaStream_t side;            // the scaler/cast of chunk i+1 runs here, under the fused kernel of chunk i
-    cudaEvent_t ev_start, ev_ready[2], ev_free[2];
+    __nv_bfloat16 *xs, *hid;      // per-CTA scratch slots, L2-resident: x_hat (ws_ctas * 2 * 128, Kp) and h1 (ws_ctas * 2 * 128, h1)
+    // Wide inputs (Kp > 256, e.g. K*A = 830): the in-kernel converter warps cannot keep enough bytes in flight for 3.3 KB
+    // rows (measured 0.35 ms vs 0.24 ms per 65 536 x 830 rows), so x_hat of a whole chunk is prepared by normalise_cast_kernel
+    // in `xs` (xs_rows x Kp) and the fused kernel streams it by row tile.  Narrow inputs: one launch, converter warps.
+    bool wide;
+    int64_t xs_rows;              // rows of `xs`: ws_ctas * 2 * 128 (narrow) or the chunk capacity (wide)
+    CUtensorMap tmap_x;           // x_hat: 128-row loads
     CUtensorMap tmap_w1, tmap_w2; // weights never move: encoded once
     CUtensorMap tmap_w1_half, tmap_w2_half; // 128-row boxes: each CTA of a pair stages its half of a 256-row weight block
-    CUtensorMap tmap_h_load, tmap_h_store;  // h1 workspace: 128-row loads, 32-row epilogue slab stores
-    long long *prof;                        // AMP_DISC_PROFILE builds: device counters (ws_ctas x 8)
-    bool use_pair;                          // CTA-pair (cta_group::2) kernel, opt-in with AMP_B200_DISC_PAIR=1
-    bool fold_bias1;                        // Kp - in_features >= 2: b1 rides in two padding columns of W1 (x_hat holds 1.0 there)
+    CUtensorMap tmap_h_load, tmap_h_store;  // h1 scratch: 128-row loads, 32-row epilogue slab stores
+    long long *prof;                        // AMP_DISC_PROFILE builds: device counters (ws_ctas x 16)
+    bool use_pair;                          // CTA-pair (cta_group::2) kernel (default; AMP_B200_DISC_PAIR=0 at create selects single)
+    int prof_mode;                          // AMP_DISC_PROFILE builds: AMP_DISC_PROF_MODE read once at create
     bool loaded;
 };
 
 using namespace amp;
 using namespace amp::disc;
-
-struct ChunkPlan;
-static ChunkPlan plan_chunks(const amp_disc *d, int64_t M);
-static int64_t chunk_count(const amp_disc *d, int64_t M);
 
 extern "C" {
 
@@ -748,7 +892,9 @@ int amp_disc_create(int32_t in_features, int32_t h1, int32_t h2, int64_t max_row
     AMP_REQUIRE(in_features >= 1 && h1 >= BN && h2 >= BN && h1 % BN == 0 && h2 % BN == 0,
                 "amp_disc_create: hidden sizes must be multiples of %d (got %d, %d), in_features >= 1 (got %d)", BN, h1, h2,
                 in_features);
-    AMP_REQUIRE(max_rows >= 1, "amp_disc_create: max_rows must be positive");
+    AMP_REQUIRE(in_features <= 1022, "amp_disc_create: discriminator input wider than 1022 columns is not supported (got %d)",
+                in_features);
+    AMP_REQUIRE(max_rows >= 1, "amp_disc_create: max_rows must be positive");  // a sizing hint only: nothing scales with it
     int dev = 0, major = 0;
     AMP_CUDA_TRY(cudaGetDevice(&dev));
     AMP_CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
@@ -759,23 +905,12 @@ int amp_disc_create(int32_t in_features, int32_t h1, int32_t h2, int64_t max_row
     std::memset(d, 0, sizeof(*d));
     d->device = dev;
     d->in_features = in_features;
-    d->Kp = (in_features + BK - 1) / BK * BK;
-    d->fold_bias1 = d->Kp - in_features >= 2 && !(getenv("AMP_B200_DISC_NO_FOLD") && getenv("AMP_B200_DISC_NO_FOLD")[0] == '1');
+    // b1 rides inside the layer-1 product: x_hat carries 1.0 in its first two padding columns and W1 carries b1 there as a
+    // bf16 head + tail, so Kp always leaves at least two padding columns
+    d->Kp = (in_features + 2 + BK - 1) / BK * BK;
     d->h1 = h1;
     d->h2 = h2;
-    // Rows per launch ("chunk").  Measured (tools/sweep_disc.py, 1 M rows): 2 / 4 / 8 / 16 / 32 tiles per CTA per launch give
-    // 1.83 / 1.63 / 1.51 / 1.46 / 1.43 ms -- every launch pays an un-overlapped layer-1 prologue and a layer-2 tail, while
-    // keeping x_hat L2-resident buys nothing (the fused kernel is not DRAM-bound).  So chunks are as large as a 256 MB x_hat
-    // buffer allows, but a big batch is still cut in two so the cast of the second half overlaps the first fused launch.
-    const int64_t wave_rows = (int64_t)sm_count() * BM;
-    const int64_t per_wave_bytes = wave_rows * d->Kp * 2;
-    int64_t tiles_per_cta = std::max<int64_t>(1, std::min<int64_t>(32, ((int64_t)256 << 20) / per_wave_bytes));
-    if (const char *t = getenv("AMP_B200_DISC_TILES_PER_CTA")) tiles_per_cta = std::max(1, atoi(t));  // tuning knob
-    const int64_t rows_padded = (max_rows + BM - 1) / BM * BM;
-    d->chunk_rows = std::min<int64_t>(rows_padded, wave_rows * tiles_per_cta);
-    if (rows_padded >= 4 * wave_rows && rows_padded <= 2 * d->chunk_rows)  // two balanced chunks instead of one (+ a sliver)
-        d->chunk_rows = ((rows_padded + 1) / 2 + wave_rows - 1) / wave_rows * wave_rows;
-    d->ws_ctas = sm_count();  // h1 workspace: two 128-row slots per persistent CTA, L2-resident
+    d->ws_ctas = sm_count();  // two 128-row slots of x_hat and of h1 per persistent CTA
     auto alloc = [&](void **p, size_t bytes) { return cudaMalloc(p, bytes); };
     cudaError_t e = cudaSuccess;
     if (e == cudaSuccess) e = alloc((void **)&d->W1, (size_t)h1 * d->Kp * 2);
@@ -786,15 +921,13 @@ int amp_disc_create(int32_t in_features, int32_t h1, int32_t h2, int64_t max_row
     if (e == cudaSuccess) e = alloc((void **)&d->b3, 4);
     if (e == cudaSuccess) e = alloc((void **)&d->mean, (size_t)in_features * 4);
     if (e == cudaSuccess) e = alloc((void **)&d->denom, (size_t)in_features * 4);
-    if (e == cudaSuccess) e = alloc((void **)&d->xhat[0], (size_t)d->chunk_rows * d->Kp * 2);
-    if (e == cudaSuccess && max_rows > d->chunk_rows) e = alloc((void **)&d->xhat[1], (size_t)d->chunk_rows * d->Kp * 2);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->side, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_start, cudaEventDisableTiming);
-    for (int i = 0; i < 2; ++i) {
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_ready[i], cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_free[i], cudaEventDisableTiming);
-    }
+    d->wide = d->Kp > 256;
+    d->xs_rows = (int64_t)d->ws_ctas * 2 * BM;
+    if (d->wide)  // one chunk = the caller's max_rows, capped at 512 MB of x_hat; larger batches are cut into chunks
+        d->xs_rows = std::max<int64_t>(BM, std::min<int64_t>((max_rows + BM - 1) / BM * BM, (((int64_t)512 << 20) / (d->Kp * 2)) / BM * BM));
+    if (e == cudaSuccess) e = alloc((void **)&d->xs, (size_t)d->xs_rows * d->Kp * 2);
     if (e == cudaSuccess) e = alloc((void **)&d->hid, (size_t)d->ws_ctas * 2 * BM * h1 * 2);
+    if (e == cudaSuccess) e = cudaMemset(d->xs, 0, (size_t)d->xs_rows * d->Kp * 2);
     if (e != cudaSuccess) {
         amp_disc_destroy(d);
         return cuda_fail(e, "cudaMalloc(amp_disc_create)");
@@ -803,6 +936,7 @@ int amp_disc_create(int32_t in_features, int32_t h1, int32_t h2, int64_t max_row
     if (rc == AMP_OK) rc = make_tmap(&d->tmap_w2, d->W2, h2, h1, h1, BN);
     if (rc == AMP_OK) rc = make_tmap(&d->tmap_w1_half, d->W1, h1, d->Kp, d->Kp, BN / 2);
     if (rc == AMP_OK) rc = make_tmap(&d->tmap_w2_half, d->W2, h2, h1, h1, BN / 2);
+    if (rc == AMP_OK) rc = make_tmap(&d->tmap_x, d->xs, d->xs_rows, d->Kp, d->Kp, BM);
     if (rc == AMP_OK) rc = make_tmap(&d->tmap_h_load, d->hid, (int64_t)d->ws_ctas * 2 * BM, h1, h1, BM);
     // epilogue slabs: 32 rows x 32 columns (64-byte rows, 64B swizzle)
     if (rc == AMP_OK) rc = make_tmap(&d->tmap_h_store, d->hid, (int64_t)d->ws_ctas * 2 * BM, h1, h1, 32, SLAB_COLS, CU_TENSOR_MAP_SWIZZLE_64B);
@@ -811,14 +945,27 @@ int amp_disc_create(int32_t in_features, int32_t h1, int32_t h2, int64_t max_row
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(disc_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_smem_bytes(true));
         if (e != cudaSuccess) rc = cuda_fail(e, "cudaFuncSetAttribute(disc_fused_kernel)");
-    #ifdef AMP_DISC_PROFILE
+#ifdef AMP_DISC_PROFILE
         if (cudaMalloc((void **)&d->prof, (size_t)d->ws_ctas * 16 * sizeof(long long)) != cudaSuccess) d->prof = nullptr;
+        if (const char *m = getenv("AMP_DISC_PROF_MODE")) d->prof_mode = atoi(m);
+        {  // timing experiments that skip the converter still feed the MMAs realistic operands (tensor-core power depends on data)
+            const size_t n = (size_t)d->xs_rows * d->Kp;
+            std::vector<uint16_t> h(n);
+            uint32_t st = 12345u;
+            for (size_t i = 0; i < n; ++i) {
+                st = st * 1664525u + 1013904223u;
+                h[i] = (uint16_t)(((st >> 16) & 0x807f) | (0x7e + ((st >> 8) & 1)) << 7);  // +-[0.5, 2) bf16
+            }
+            cudaMemcpy(d->xs, h.data(), n * 2, cudaMemcpyHostToDevice);
+        }
 #endif
-        // Measured on the 1 M-row bench (B200, sustained, sw_power_cap active): single-CTA 1.61 ms, CTA pair 1.68 ms.  The pair
-        // halves the weight bytes each SM ingests but every accumulator hand-off crosses the cluster twice; it is kept as
-        // an opt-in (AMP_B200_DISC_PAIR=1) and covered by the GPU tests.
+        // The CTA pair (cta_group::2) is the default: each SM stages only half of every weight block (a third less L2 -> SM
+        // traffic per row).  Measured, 1 M rows x 166: pair 1.35 ms, single CTA 1.49 ms; 65 536 x 830: 0.218 vs 0.232 ms.  (Round 1
+        // measured the pair slower -- its accumulator hand-off used mbarrier.arrive.release.cluster, which ptxas expands to
+        // MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR: see mbar_arrive_cluster.)  AMP_B200_DISC_PAIR=0 selects the single-CTA kernel;
+        // both are covered by the GPU tests.
         const char *pair = getenv("AMP_B200_DISC_PAIR");
-        d->use_pair = pair && pair[0] == '1';
+        d->use_pair = !(pair && pair[0] == '0');
     }
     if (rc != AMP_OK) {
         amp_disc_destroy(d);
@@ -830,29 +977,28 @@ int amp_disc_create(int32_t in_features, int32_t h1, int32_t h2, int64_t max_row
 
 int amp_disc_destroy(amp_disc_t *d) {
     if (!d) return AMP_OK;
-    void *ptrs[] = {d->W1, d->W2, d->b1, d->b2, d->w3, d->b3, d->mean, d->denom, d->xhat[0], d->xhat[1], d->hid};
+    void *ptrs[] = {d->W1, d->W2, d->b1, d->b2, d->w3, d->b3, d->mean, d->denom, d->xs, d->hid, d->prof};
     for (void *p : ptrs)
         if (p) cudaFree(p);
-    if (d->side) cudaStreamDestroy(d->side);
-    if (d->ev_start) cudaEventDestroy(d->ev_start);
-    for (int i = 0; i < 2; ++i) {
-        if (d->ev_ready[i]) cudaEventDestroy(d->ev_ready[i]);
-        if (d->ev_free[i]) cudaEventDestroy(d->ev_free[i]);
-    }
     delete d;
     return AMP_OK;
 }
 
-int64_t amp_disc_chunk_rows(const amp_disc_t *d) { return d ? d->chunk_rows : 0; }
+// rows one persistent wave covers (one 128-row tile per CTA)
+int64_t amp_disc_chunk_rows(const amp_disc_t *d) { return d ? (int64_t)d->ws_ctas * BM : 0; }
 
-int64_t amp_disc_launch_count(const amp_disc_t *d, int64_t M) { return (d && M > 0) ? 2 * chunk_count(d, M) : 0; }
+// narrow inputs (K*A <= 254): ONE launch whatever the batch; wide inputs: cast + fused kernel per chunk of xs_rows rows
+int64_t amp_disc_launch_count(const amp_disc_t *d, int64_t M) {
+    if (!d || M <= 0) return 0;
+    return d->wide ? 2 * ((M + d->xs_rows - 1) / d->xs_rows) : 1;
+}
 
 int amp_disc_load(amp_disc_t *d, const float *W1, const float *b1, const float *W2, const float *b2, const float *W3,
                   const float *b3, const double *running_mean, const double *running_variance, void *stream) {
     AMP_REQUIRE(d && W1 && b1 && W2 && b2 && W3 && b3 && running_mean && running_variance, "amp_disc_load: NULL argument");
     cudaStream_t st = as_stream(stream);
     const int blocks = sm_count() * 4;
-    cast_weight_kernel<<<blocks, 256, 0, st>>>(W1, d->h1, d->in_features, d->Kp, d->W1, d->fold_bias1 ? b1 : nullptr);
+    cast_weight_kernel<<<blocks, 256, 0, st>>>(W1, d->h1, d->in_features, d->Kp, d->W1, b1);
     cast_weight_kernel<<<blocks, 256, 0, st>>>(W2, d->h2, d->h1, d->h1, d->W2, nullptr);
     AMP_CUDA_TRY(cudaGetLastError());
     AMP_CUDA_TRY(cudaMemcpyAsync(d->b1, b1, (size_t)d->h1 * 4, cudaMemcpyDeviceToDevice, st));
@@ -868,32 +1014,8 @@ int amp_disc_load(amp_disc_t *d, const float *W1, const float *b1, const float *
 
 }  // extern "C"
 
-// Chunk plan of an M-row batch.  One chunk when M fits a workspace buffer, else equal big chunks; optionally a short LEAD-IN
-// chunk first (AMP_B200_DISC_LEAD_TILES row tiles per CTA): the scaler/cast of chunk c+1 hides under the fused kernel of
-// chunk c but the cast of chunk 0 has nothing to hide under.  Measured on the 1 M-row bench: 0 / 2 / 4 / 8 lead-in tiles ->
-// 1.396 / 1.469 / 1.415 / 1.401 ms -- the extra launch (prologue + tail) costs what the smaller first cast saves, so the
-// default is no lead-in.
-struct ChunkPlan {
-    int64_t n, lead, big;  // number of chunks, rows of the lead-in chunk (0 = none), rows of every following chunk
-    int64_t start(int64_t c) const { return c == 0 ? 0 : (lead ? lead + (c - 1) * big : c * big); }
-};
-static ChunkPlan plan_chunks(const amp_disc *d, int64_t M) {
-    ChunkPlan p{1, 0, d->chunk_rows};
-    if (M <= d->chunk_rows) return p;
-    const int64_t wave_rows = (int64_t)d->ws_ctas * BM;
-    int64_t lead_tiles = 0;
-    if (const char *t = getenv("AMP_B200_DISC_LEAD_TILES")) lead_tiles = std::max(0, atoi(t));  // tuning knob, 0 = no lead-in
-    p.lead = std::min<int64_t>(lead_tiles * wave_rows, d->chunk_rows / 4) / wave_rows * wave_rows;
-    const int64_t rest = M - p.lead;
-    const int64_t k = (rest + d->chunk_rows - 1) / d->chunk_rows;
-    p.big = std::min<int64_t>(d->chunk_rows, ((rest + k - 1) / k + wave_rows - 1) / wave_rows * wave_rows);
-    p.n = (p.lead ? 1 : 0) + (rest + p.big - 1) / p.big;
-    return p;
-}
-
-static int64_t chunk_count(const amp_disc *d, int64_t M) { return plan_chunks(d, M).n; }
-
-// x rows are taken in order (row_index == NULL) or gathered: row r of the batch = x[row_index[r]] with x holding `capacity` rows
+// x rows are taken in order (row_index == NULL) or gathered: row r of the batch = x[row_index[r]] with x holding `capacity` rows.
+// ONE launch: scaler + cast + both layers + reward; the grid is min(row tiles, SMs) persistent CTAs.
 static int style_reward_impl(amp_disc_t *d, const float *x, int64_t x_stride, const int64_t *row_index, int64_t capacity,
                              uint32_t *flags, int64_t M, float reward_scale, float *reward, float *logits, void *stream) {
     AMP_REQUIRE(d && M >= 0, "amp_disc_style_reward: bad handle or negative size");
@@ -902,59 +1024,45 @@ static int style_reward_impl(amp_disc_t *d, const float *x, int64_t x_stride, co
     AMP_REQUIRE(x && reward, "amp_disc_style_reward: NULL buffer");
     AMP_REQUIRE(x_stride >= d->in_features, "amp_disc_style_reward: x_stride %lld < in_features %d", (long long)x_stride,
                 d->in_features);
+    AMP_REQUIRE(M <= ((int64_t)1 << 31) - BM, "amp_disc_style_reward: %lld rows exceed the 2^31 row limit of one call", (long long)M);
     cudaStream_t st = as_stream(stream);
     const int sms = sm_count();
-    const ChunkPlan plan = plan_chunks(d, M);
-    const int64_t n_chunks = plan.n;
-    AMP_REQUIRE(n_chunks == 1 || d->xhat[1], "amp_disc_style_reward: %lld rows exceed the max_rows given to amp_disc_create",
-                (long long)M);
-    // With several chunks the scaler/cast of chunk c+1 runs on the handle's side stream underneath the fused kernel of
-    // chunk c (the fused kernel is operand-delivery bound and leaves HBM and most issue slots idle; the cast kernel uses no
-    // shared memory, so its CTAs co-reside with the persistent fused CTAs).  A single chunk stays on the caller's stream.
-    const bool overlap = n_chunks > 1;
-    auto issue_cast = [&](int64_t c) -> int {
-        const int b = (int)(c & 1);
-        const int64_t r0 = plan.start(c), rows = std::min<int64_t>(plan.start(c + 1), M) - r0;
-        cudaStream_t cs = overlap ? d->side : st;
-        if (overlap && c >= 2) AMP_CUDA_TRY(cudaStreamWaitEvent(cs, d->ev_free[b], 0));  // fused(c-2) is done with xhat[b]
+    const int64_t chunk = d->wide ? d->xs_rows : M;
+    for (int64_t r0 = 0; r0 < M; r0 += chunk) {
+        const int64_t rows = std::min(chunk, M - r0);
+        const int m_tiles = (int)((rows + BM - 1) / BM);
         const float *xc = row_index ? x : x + r0 * x_stride;
         const int64_t *ic = row_index ? row_index + r0 : nullptr;
         const bool vec = (x_stride % 2 == 0) && ((reinterpret_cast<uintptr_t>(xc) & 7u) == 0);
-        const int cast_grid = (int)std::min<int64_t>((rows + 7) / 8, (int64_t)sms * 8);
-        const int ones = d->fold_bias1 ? 2 : 0;
-        int rc = vec ? launch_normalise_cast<true>(d->Kp / BK, cast_grid, cs, xc, x_stride, rows, d->in_features, d->mean, d->denom,
-                                                   d->xhat[b], ic, capacity, flags, ones)
-                     : launch_normalise_cast<false>(d->Kp / BK, cast_grid, cs, xc, x_stride, rows, d->in_features, d->mean, d->denom,
-                                                    d->xhat[b], ic, capacity, flags, ones);
-        if (rc != AMP_OK) return rc;
-        AMP_CUDA_TRY(cudaGetLastError());
-        if (overlap) AMP_CUDA_TRY(cudaEventRecord(d->ev_ready[b], cs));
-        return AMP_OK;
-    };
-    if (overlap) {  // the side stream starts after everything already queued on the caller's stream (x may still be in flight)
-        AMP_CUDA_TRY(cudaEventRecord(d->ev_start, st));
-        AMP_CUDA_TRY(cudaStreamWaitEvent(d->side, d->ev_start, 0));
-    }
-    int rc = issue_cast(0);
-    if (rc != AMP_OK) return rc;
-    for (int64_t c = 0; c < n_chunks; ++c) {
-        const int b = (int)(c & 1);
-        const int64_t r0 = plan.start(c), rows = std::min<int64_t>(plan.start(c + 1), M) - r0;
-        if (c + 1 < n_chunks && (rc = issue_cast(c + 1)) != AMP_OK) return rc;
-        if (overlap) AMP_CUDA_TRY(cudaStreamWaitEvent(st, d->ev_ready[b], 0));
-        const int m_tiles = (int)((rows + BM - 1) / BM);
-        const int grid = std::min(m_tiles, std::min(sms, d->ws_ctas));
-        CUtensorMap tm_x;
-        rc = make_tmap(&tm_x, d->xhat[b], rows, d->Kp, d->Kp, BM);
-        if (rc != AMP_OK) return rc;
+        if (d->wide) {
+            const int cast_grid = (int)std::min<int64_t>((rows + 7) / 8, (int64_t)sms * 8);
+            int rc = vec ? launch_normalise_cast<true>(d->Kp / BK, cast_grid, st, xc, x_stride, rows, d->in_features, d->mean, d->denom,
+                                                       d->xs, ic, capacity, flags, 2)
+                         : launch_normalise_cast<false>(d->Kp / BK, cast_grid, st, xc, x_stride, rows, d->in_features, d->mean, d->denom,
+                                                        d->xs, ic, capacity, flags, 2);
+            if (rc != AMP_OK) return rc;
+            AMP_CUDA_TRY(cudaGetLastError());
+        }
         FusedParams fp{};
-        fp.M = (int)rows;
+        fp.M = rows;
+        fp.x = xc;
+        fp.x_stride = x_stride;
+        fp.row_index = ic;
+        fp.capacity = capacity;
+        fp.flags = flags;
+        fp.mean = d->mean;
+        fp.denom = d->denom;
+        fp.xs = d->xs;
+        fp.in_features = d->in_features;
+        fp.Kp = d->Kp;
+        fp.x_vec = vec ? 1 : 0;
+        fp.xhat_rows_in_order = d->wide ? 1 : 0;
+        // a row tile starts at a multiple of 128 * x_stride * 4 = 512 * x_stride bytes from x: 16-byte aligned when x is
+        fp.x_prefetch = (!row_index && (reinterpret_cast<uintptr_t>(xc) & 15u) == 0 && x_stride < 2 * (int64_t)d->in_features) ? 1 : 0;
         fp.kb1 = d->Kp / BK;
-        fp.fold_bias1 = d->fold_bias1 ? 1 : 0;
-        fp.ksteps1_last = (d->in_features + (d->fold_bias1 ? 2 : 0) - BK * (fp.kb1 - 1) + UMMA_K - 1) / UMMA_K;
+        fp.ksteps1_last = (d->in_features + 2 - BK * (fp.kb1 - 1) + UMMA_K - 1) / UMMA_K;
         fp.n1_tiles = d->h1 / BN;
         fp.n2_tiles = d->h2 / BN;
-        fp.b1 = d->b1;
         fp.b2 = d->b2;
         fp.w3 = d->w3;
         fp.b3 = d->b3;
@@ -962,9 +1070,7 @@ static int style_reward_impl(amp_disc_t *d, const float *x, int64_t x_stride, co
         fp.reward = reward + r0;
         fp.logits = logits ? logits + r0 : nullptr;
         fp.prof = d->prof;
-#ifdef AMP_DISC_PROFILE
-        if (const char *m = getenv("AMP_DISC_PROF_MODE")) fp.prof_mode = atoi(m);
-#endif
+        fp.prof_mode = d->prof_mode;
         if (d->use_pair && m_tiles >= 2) {
             // CTA pairs: an even grid of at most ws_ctas CTAs, launched as clusters of 2
             const int pair_blocks = (m_tiles + 1) / 2;
@@ -981,17 +1087,17 @@ static int style_reward_impl(amp_disc_t *d, const float *x, int64_t x_stride, co
             attr[0].val.clusterDim.z = 1;
             cfg.attrs = attr;
             cfg.numAttrs = 1;
-            AMP_CUDA_TRY(cudaLaunchKernelEx(&cfg, disc_fused_kernel<true>, tm_x, d->tmap_w1_half, d->tmap_h_load, d->tmap_h_store,
+            AMP_CUDA_TRY(cudaLaunchKernelEx(&cfg, disc_fused_kernel<true>, d->tmap_x, d->tmap_w1_half, d->tmap_h_load, d->tmap_h_store,
                                             d->tmap_w2_half, fp));
         } else {
-            disc_fused_kernel<false><<<grid, FUSED_THREADS, fused_smem_bytes(false), st>>>(tm_x, d->tmap_w1, d->tmap_h_load,
+            const int grid = std::min(m_tiles, std::min(sms, d->ws_ctas));
+            disc_fused_kernel<false><<<grid, FUSED_THREADS, fused_smem_bytes(false), st>>>(d->tmap_x, d->tmap_w1, d->tmap_h_load,
                                                                                            d->tmap_h_store, d->tmap_w2, fp);
         }
         AMP_CUDA_TRY(cudaGetLastError());
-        if (overlap) AMP_CUDA_TRY(cudaEventRecord(d->ev_free[b], st));
     }
 #ifdef AMP_DISC_PROFILE
-    if (d->prof) {  // developer build: dump the wait breakdown of the LAST chunk (synchronises!)
+    if (d->prof) {  // developer build: dump the wait breakdown of this launch (synchronises!)
         static long long host[1024 * 16];
         cudaStreamSynchronize(st);
         const int n = std::min(d->ws_ctas, 1024);
@@ -1013,7 +1119,7 @@ static int style_reward_impl(amp_disc_t *d, const float *x, int64_t x_stride, co
             for (int k = 0; k < 8; ++k) acc[k] += (double)host[i * 8 + k];
         }
         if (cnt)
-            fprintf(stderr, "[amp_disc profile] issuer CTAs=%d total=%.0f wait_full=%.0f wait_d1_empty=%.0f wait_d2_empty=%.0f | producer(all) wait_empty=%.0f wait_h1=%.0f (cycles, mean per CTA) | issuer wall %.1f us => SM clock %.0f MHz\n",
+            fprintf(stderr, "[amp_disc profile] issuer CTAs=%d total=%.0f wait_full=%.0f wait_d1_empty=%.0f wait_d2_empty=%.0f | producer(all) wait_empty=%.0f wait_h1+xhat=%.0f (cycles, mean per CTA) | issuer wall %.1f us => SM clock %.0f MHz\n",
                     cnt, acc[0] / cnt, acc[1] / cnt, acc[2] / cnt, acc[3] / cnt, acc[4] / n, acc[5] / n, acc[6] / cnt * 1e-3,
                     acc[0] / acc[6] * 1e3);
     }

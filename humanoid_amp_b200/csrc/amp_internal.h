@@ -53,12 +53,9 @@ struct LibView {
     uint32_t *flags;         // sticky error bits
 };
 
-// amp_disc.cu helpers shared with amp_disc_train.cu (all pointers device; no allocation):
+// amp_disc.cu helper shared with amp_disc_train.cu (all pointers device; no allocation):
 //   scaler_stats_to_f32   mean_f = (float)mean, denom_f = sqrt((float)var) + 1e-8 (skrl RunningStandardScaler, eval form)
-//   normalise_cast_rows   x (rows, in_features) fp32 -> clamp((x - mean_f) / denom_f, -5, 5) as bf16 (rows, Kp), zero padded
 int scaler_stats_to_f32(const double *mean, const double *var, int n, float *mean_f, float *denom_f, cudaStream_t st);
-int normalise_cast_rows(const float *x, int64_t x_stride, int64_t rows, int in_features, int Kp, const float *mean_f,
-                        const float *denom_f, void *out_bf16, cudaStream_t st);
 
 }  // namespace amp
 

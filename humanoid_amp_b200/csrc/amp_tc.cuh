@@ -108,8 +108,12 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t local_addr, uint32_t rank
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
     return r;
 }
+// The default (.release at CTA scope) form on a shared::cluster address is a bare SYNCS.ARRIVE; spelling out
+// .release.cluster makes ptxas emit MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in front of it (a GPU-scope fence that waits for every
+// outstanding store of the warp, thousands of cycles next to TMA stores).  The callers only hand TMEM regions back to the
+// MMA issuer (ordered by tcgen05.wait::ld + tcgen05.fence::before_thread_sync), no generic-proxy data is published.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release;" ::: "memory");

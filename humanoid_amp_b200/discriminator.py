@@ -31,10 +31,10 @@ class AmpDiscriminator:
         _lib.check(lib.amp_disc_create(self.in_features, self.hidden[0], self.hidden[1], int(max_rows), stream, C.byref(h)))
         self._h = h
         self._masters = None
-        self.chunk_rows = int(lib.amp_disc_chunk_rows(h))  # rows per internal chunk: 2 kernel launches each (cast + fused two-layer kernel)
+        self.chunk_rows = int(lib.amp_disc_chunk_rows(h))  # rows one persistent wave covers (148 CTAs x 128 rows)
 
     def launch_count(self, rows: int) -> int:
-        """Kernel launches one ``style_reward`` call over ``rows`` rows issues (two per internal chunk)."""
+        """Kernel launches one ``style_reward`` call over ``rows`` rows issues: ONE (scaler + cast + both layers + reward)."""
         return int(_lib.load().amp_disc_launch_count(self._h, int(rows)))
 
     def load(self, weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor], running_mean: torch.Tensor, running_variance: torch.Tensor) -> None:

@@ -234,9 +234,11 @@ AMP_API int amp_scaler_apply(const float *x, int64_t x_stride, int64_t M, int32_
  * h1, h2 must be multiples of 256 (reference: 1024, 512); in_features any value >= 1 (padded to 64 internally). */
 AMP_API int amp_disc_create(int32_t in_features, int32_t h1, int32_t h2, int64_t max_rows, void *stream, amp_disc_t **out);
 AMP_API int amp_disc_destroy(amp_disc_t *d);
-/* Rows processed per internal chunk (two kernel launches per chunk: scaler + cast, fused MLP); 0 for a NULL handle. */
+/* Rows one persistent wave covers (one 128-row tile per SM); 0 for a NULL handle.  max_rows of amp_disc_create is a hint
+ * only: the scratch (two 128-row x_hat and h1 slots per SM, L2-resident) does not scale with the batch. */
 AMP_API int64_t amp_disc_chunk_rows(const amp_disc_t *d);
-/* Kernel launches amp_disc_style_reward issues for a batch of M rows (two per chunk). */
+/* Kernel launches amp_disc_style_reward issues for a batch of M rows: 1 (scaler + bf16 cast + both layers + reward in one
+ * persistent tcgen05 kernel), 0 for M == 0. */
 AMP_API int64_t amp_disc_launch_count(const amp_disc_t *d, int64_t M);
 /* Refresh the staged bf16 weights / fp32 biases / scaler statistics from the fp32 masters the trainer owns
  * (device pointers; W row-major (out,in) as torch.nn.Linear stores them; mean/var are the scaler's float64 buffers). */

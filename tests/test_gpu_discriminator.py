@@ -52,17 +52,24 @@ def build(in_features, gain, seed=42, max_rows=65536):
     return disc, ora, inputs
 
 
-@pytest.mark.parametrize("in_features", [166, 830, 162])
+# 166 / 162 / 830: the shipped configurations; 83 = K = 1 (odd row pitch: 4-byte loads in the converter warps); 63, 64: the two
+# bias columns open a second K-block; 254 / 255: the widest in-kernel-converted input / the narrowest cast-kernel one
+@pytest.mark.parametrize("in_features", [166, 830, 162, 83, 63, 64, 254, 255])
 @pytest.mark.parametrize("gain", [1.0, 30.0])
 def test_style_reward_vs_oracle(in_features, gain):
     disc, ora, inputs = build(in_features, gain)
+    shipped = in_features in (166, 830, 162)
+    # The stated bar is relative to the logit scale of the batch.  For the shipped widths it is applied per batch exactly as
+    # stated; the extra widths (kernel-path coverage: odd pitch, padding edge cases, the converter / cast-kernel boundary) are
+    # random networks for which a 1-row batch defines no scale, so the scale is taken from the 4096-row batch.
+    span_dist = max(1.0, float(ora.logits(inputs(4096, 4096)).abs().max()))
     for M in (1, 127, 128, 129, 4096):
         x = inputs(M, M)
         reward, logits = disc.style_reward(x.cuda(), return_logits=True)
         assert reward.shape == (M, 1) and logits.shape == (M, 1)
         want_logits = ora.logits(x)
         want_reward = ora.style_reward(x)
-        span = max(1.0, float(want_logits.abs().max()))
+        span = max(1.0, float(want_logits.abs().max())) if shipped else span_dist
         dl = (logits.cpu() - want_logits).abs().max().item()
         dr = (reward.cpu() - want_reward).abs().max().item()
         assert dl <= 1e-2 * span, f"M={M}: |dlogit| {dl:.3e} > {1e-2 * span:.3e}"
@@ -93,7 +100,7 @@ def test_reward_expression_and_clamp():
 
 
 def test_multi_chunk_rows_and_row_independence():
-    """More rows than one L2-resident chunk (2 x 148 x 128 = 37888), with a strided input view (a memory slice)."""
+    """More rows than two persistent waves (2 x 148 x 128 = 37888), with a strided input view (a memory slice)."""
     disc, ora, inputs = build(166, 5.0, max_rows=100_000)
     M = 37888 + 128 + 5
     x = inputs(M, 3).cuda()
@@ -115,26 +122,38 @@ def test_multi_chunk_rows_and_row_independence():
     assert disc.style_reward(x[:0]).shape == (0, 1)
 
 
-def test_lead_in_chunk_plan_gives_the_same_bits(monkeypatch):
-    """The optional lead-in chunk (AMP_B200_DISC_LEAD_TILES, a tuning knob that is off by default) only changes how the batch
-    is cut into launches: rewards must be bit-identical and the launch count must follow the plan."""
+def test_one_launch_whatever_the_batch_and_many_tiles_per_cta():
+    """The scaler + cast run inside the fused kernel: a call is ONE launch for any batch size, and a CTA that walks many row
+    tiles (here 4 x 148 x 128 rows + a ragged tail: scratch slots and barriers wrap several times) gives the same bits as the
+    same rows evaluated in small independent calls."""
     import humanoid_amp_b200 as amp
     from humanoid_amp_b200.synthetic import skrl_style_discriminator_params
 
-    monkeypatch.setenv("AMP_B200_DISC_TILES_PER_CTA", "8")  # chunks of 8 row tiles per CTA
     W, b = skrl_style_discriminator_params(166, seed=4, logit_gain=3.0)
-    disc = amp.AmpDiscriminator(166, device="cuda:0", max_rows=700_000)
+    disc = amp.AmpDiscriminator(166, device="cuda:0", max_rows=1)  # max_rows is only a hint: nothing is sized by it
     disc.load(W, b, torch.zeros(166, dtype=torch.float64), torch.ones(166, dtype=torch.float64))
-    M = 4 * disc.chunk_rows
-    assert M <= 700_000
+    M = 4 * disc.chunk_rows + 77
     x = torch.randn(M, 166, device="cuda", generator=torch.Generator(device="cuda").manual_seed(0))
-    monkeypatch.setenv("AMP_B200_DISC_LEAD_TILES", "0")
-    plain, launches_plain = disc.style_reward(x), disc.launch_count(M)
-    monkeypatch.setenv("AMP_B200_DISC_LEAD_TILES", "2")
-    lead, launches_lead = disc.style_reward(x), disc.launch_count(M)
-    assert torch.equal(plain, lead)
-    assert launches_plain == 2 * 4 and launches_lead == 2 * 5  # four chunks; a 2-tile lead-in + four (smaller) chunks
-    assert disc.launch_count(100) == 2 and disc.launch_count(0) == 0
+    whole = disc.style_reward(x)
+    for lo in (0, 128 * 147, disc.chunk_rows - 5, 3 * disc.chunk_rows + 1000, M - 300):
+        assert torch.equal(disc.style_reward(x[lo : lo + 300]), whole[lo : lo + 300])
+    assert disc.launch_count(M) == 1 and disc.launch_count(100) == 1 and disc.launch_count(0) == 0
+
+
+def test_wide_input_chunks_and_gather_give_the_same_bits():
+    """K*A = 830 takes the cast-kernel path (x_hat of a chunk prepared by normalise_cast_kernel): a batch larger than the
+    chunk capacity (max_rows) is cut into chunks and gives the same bits as independent calls; the gathered form agrees."""
+    disc, ora, inputs = build(830, 5.0, max_rows=1000)  # chunk capacity 1024 rows
+    M = 3 * 1024 + 77
+    x = inputs(M, 11).cuda()
+    whole, logits = disc.style_reward(x, return_logits=True)
+    assert disc.launch_count(M) == 2 * 4 and disc.launch_count(1000) == 2
+    for lo in (0, 1000, 2048, M - 200):
+        assert torch.equal(disc.style_reward(x[lo : lo + 200]), whole[lo : lo + 200])
+    idx = torch.randperm(M, generator=torch.Generator().manual_seed(3))[:2500].cuda()
+    assert torch.equal(disc.style_reward_sampled(x, idx), whole[idx])
+    want = ora.logits(x[:512].cpu())
+    assert (logits[:512].cpu() - want).abs().max() <= 1e-2 * max(1.0, float(want.abs().max()))
 
 
 def test_weight_refresh_changes_result():
@@ -151,8 +170,7 @@ def test_weight_refresh_changes_result():
 
 
 def test_cuda_graph_capture_of_a_whole_step(tmp_path):
-    """A step (fused collect -> env-step history -> multi-chunk style reward, which forks onto the handle's side stream)
-    captured once with ``capture_step`` and replayed gives the same bits as eager launches, also after the inputs change."""
+    """A step (fused collect -> env-step history -> style reward over several row tiles per CTA) captured once with ``capture_step`` and replayed gives the same bits as eager launches, also after the inputs change."""
     import humanoid_amp_b200 as amp
     from humanoid_amp_b200.synthetic import skrl_style_discriminator_params, synthetic_sim_state, write_synthetic_clip
 
@@ -161,14 +179,8 @@ def test_cuda_graph_capture_of_a_whole_step(tmp_path):
     env = amp.AmpEnvPath(amp.AmpEnvCfg(motion_file=path, num_envs=n, num_amp_observations=K, robot=amp.G1), "cuda:0")
     width = K * 83
     W, b = skrl_style_discriminator_params(width, seed=1, logit_gain=3.0)
-    import os
-
-    os.environ["AMP_B200_DISC_TILES_PER_CTA"] = "1"  # force several chunks (148 x 128 rows each) at a small batch
-    try:
-        disc = amp.AmpDiscriminator(width, device="cuda:0", max_rows=16 * n)
-    finally:
-        del os.environ["AMP_B200_DISC_TILES_PER_CTA"]
-    assert disc.chunk_rows < 16 * n
+    disc = amp.AmpDiscriminator(width, device="cuda:0", max_rows=16 * n)
+    assert disc.chunk_rows < 16 * n  # several row tiles per persistent CTA
     disc.load(W, b, torch.zeros(width, dtype=torch.float64), torch.ones(width, dtype=torch.float64))
     g = torch.Generator(device="cuda").manual_seed(5)
     ids, times = env._motion_loader.sample_times_device(n, generator=g)
