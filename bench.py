@@ -732,7 +732,12 @@ JSON_OUT = sys.stdout  # the ONE JSON line goes here; everything else printed du
 
 def main():
     global JSON_OUT
-    JSON_OUT, sys.stdout = sys.stdout, sys.stderr
+    # stdout carries ONLY the JSON line: Python-level prints go to stderr, and so does everything native code writes to file
+    # descriptor 1 (NCCL prints its version banner there) -- the line itself is written to a duplicate of the original fd
+    sys.stdout.flush()
+    JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
