@@ -77,6 +77,17 @@ class EnvStepArgs(C.Structure):
     ]  # fmt: skip
 
 
+class DatasetDesc(C.Structure):
+    """``amp_dataset_desc_t`` of include/amp_b200.h."""
+
+    _fields_ = [
+        ("n_in", C.c_int32), ("n_cols", C.c_int32), ("n_out", C.c_int32), ("n_dofs", C.c_int32), ("n_bodies", C.c_int32), ("n_joints", C.c_int32),
+        ("rows", C.c_void_p), ("t_orig", C.c_void_p), ("t_new", C.c_void_p), ("lerp_lo", C.c_void_p), ("slerp_ind", C.c_void_p),
+        ("slerp_alpha", C.c_void_p), ("joint_parent", C.c_void_p), ("joint_qidx", C.c_void_p), ("joint_origin_xyz", C.c_void_p),
+        ("joint_origin_rot", C.c_void_p), ("joint_axis", C.c_void_p), ("body_joint", C.c_void_p),
+    ]  # fmt: skip
+
+
 _P, _I32, _I64, _F32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
 # name -> (restype, argtypes); mirrors include/amp_b200.h one to one (tests/test_abi.py checks the header against this)
@@ -117,6 +128,9 @@ SIGNATURES = {
     "amp_disc_train_destroy": (C.c_int, [_P]),
     "amp_disc_train_stage": (C.c_int, [_P, _I32, _P, _I64, _I64, _P, _P, _P]),
     "amp_disc_train_step": (C.c_int, [_P] * 7 + [_I64, _F32, _F32, _F32, _F32] + [_P] * 9),
+    "amp_dataset_scratch_bytes": (C.c_int64, [_I32, _I32, _I32]),
+    "amp_dataset_interp_fk": (C.c_int, [C.POINTER(DatasetDesc), _P, _P, _P, _P, _P, _I64, _P]),
+    "amp_dataset_velocities": (C.c_int, [_I32, _I32, _I32, C.c_double, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _P]),
     "amp_bucket_create": (C.c_int, [_I64, _I32, _I32, C.POINTER(_P)]),
     "amp_bucket_destroy": (C.c_int, [_P]),
     "amp_bucket_floats": (C.c_int64, [_P]),

@@ -35,6 +35,8 @@ SOURCES = {
     "amp_disc.cu": ["-DAMP_DISC_PROFILE"] if os.environ.get("AMP_DISC_PROFILE") == "1" else [],
     "amp_disc_train.cu": [],
     "amp_bucket.cu": [],
+    # the float32 steps of the dataset tool mirror numpy: no contraction into FMA
+    "amp_dataset.cu": ["-fmad=false"],
 }
 HEADERS = ["amp_internal.h", "amp_math.cuh", os.path.join(ROOT, "include", "amp_b200.h")]
 

@@ -309,6 +309,38 @@ AMP_API int amp_bucket_poll_status(amp_bucket_t *b, void *stream, uint32_t *stat
  * barrier B passed.  Synchronises the stream.  For tools/bench_allreduce.py. */
 AMP_API int amp_bucket_last_timing(amp_bucket_t *b, void *stream, uint64_t *stamps4);
 
+/* ---- offline dataset pipeline (reference motions/data_convert.py:161-379) ----------------------------- */
+/* CSV rows at 30 fps -> 2N-1 frames at 60 fps (scipy interp1d / Slerp semantics) -> forward kinematics over the URDF tree
+ * (Pinocchio forwardKinematics + updateFramePlacements, Eigen matrix -> quaternion) -> velocities.  All pointers device. */
+typedef struct amp_dataset_desc {
+    int32_t n_in, n_cols, n_out, n_dofs, n_bodies, n_joints;
+    const float *rows;          /* (n_in, n_cols): root xyz, root quat xyzw, n_dofs joint angles (data_convert.py:178-183) */
+    const double *t_orig;       /* [n_in]  np.linspace(0, (n_in-1)/30, n_in)            (:188) */
+    const double *t_new;        /* [n_out] np.linspace(0, (n_in-1)/30, 2 n_in - 1)      (:193) */
+    const int32_t *lerp_lo;     /* [n_out] lower knot of scipy interp1d: clip(searchsorted(t_orig, t_new), 1, n_in-1) - 1 */
+    const int32_t *slerp_ind;   /* [n_out] scipy Slerp: searchsorted(t_orig, t_new) - 1, 0 where t_new == t_orig[0] */
+    const double *slerp_alpha;  /* [n_out] (t_new - t_orig[ind]) / (t_orig[ind+1] - t_orig[ind]) */
+    const int32_t *joint_parent;    /* [n_joints] topological order; joint whose child link is this joint's parent link, -1 = root */
+    const int32_t *joint_qidx;      /* [n_joints] column of the joint-angle block driving the joint, -1 = fixed */
+    const double *joint_origin_xyz; /* (n_joints, 3) */
+    const double *joint_origin_rot; /* (n_joints, 9) row-major Rz(yaw) Ry(pitch) Rx(roll) of the URDF origin */
+    const double *joint_axis;       /* (n_joints, 3) unit axis */
+    const int32_t *body_joint;      /* [n_bodies] joint whose child link is the recorded body, -1 = the root link (data_convert.py:301-327) */
+} amp_dataset_desc_t;
+AMP_API int64_t amp_dataset_scratch_bytes(int32_t n_in, int32_t n_out, int32_t n_bodies);
+/* data_convert.py:196-215 (interpolation) + :331-347 (FK).  dof_positions f64 (n_out, n_dofs); body_positions f32 (n_out, B, 3);
+ * body_rotations f32 (n_out, B, 4) wxyz; root_pose f64 (n_out, 7) xyz + quat xyzw or NULL. */
+AMP_API int amp_dataset_interp_fk(const amp_dataset_desc_t *d, double *dof_positions, float *body_positions, float *body_rotations,
+                                  double *root_pose, void *scratch, int64_t scratch_bytes, void *stream);
+/* data_convert.py:290-297 (joint velocities), :349-355 (body linear velocities), :357-371 (body angular velocities); each is the
+ * raw difference followed by scipy gaussian_filter1d(sigma=1, axis=0) with reflect boundaries.  gauss_w host [5]: the kernel
+ * weights for offsets 0..4 as scipy computes them.  The angular velocity evaluates compute_angular_velocity (:87-108) in
+ * float64 on the float32 rotations (the reference's float32 evaluation is ill-conditioned, see csrc/amp_dataset.cu). */
+AMP_API int amp_dataset_velocities(int32_t n_out, int32_t n_dofs, int32_t n_bodies, double dt, const double *gauss_w,
+                                   const double *dof_positions, const float *body_positions, const float *body_rotations,
+                                   double *dof_velocities, float *body_linear_velocities, float *body_angular_velocities,
+                                   void *scratch, int64_t scratch_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

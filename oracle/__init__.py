@@ -9,6 +9,8 @@ reference's per-step AMP path so the CUDA kernels in ``humanoid_amp_b200`` can b
 * ``memory_oracle``  -- skrl ``RandomMemory`` ring write / ``sample_by_index`` (upstream skrl, PARITY UNPINNED)
 * ``disc_train_oracle`` -- skrl ``AMP._update`` discriminator LOSS block (BCE + logit regularisation + gradient penalty + weight decay)
                         evaluated by torch autograd, and the closed-form gradients the CUDA path implements (PARITY UNPINNED)
+* ``dataset_oracle`` -- the offline dataset tool ``motions/data_convert.py:161-379``: scipy interpolation, restated
+                        Pinocchio forward kinematics / Eigen quaternion conversion, velocity stages
 * ``disc_oracle``    -- skrl ``RunningStandardScaler`` (eval + train-mode statistics) + MLP + AMP style reward (upstream skrl >= 1.4.3,
                         ``agents/torch/amp/amp.py::_update``; configured by ``agents/skrl_g1_dance_amp_cfg.yaml:31-39, 80, 94-95``)
 
@@ -21,11 +23,18 @@ Parity pinning status
 * ``motion_oracle``: PINNED -- bit-identical to the live reference ``MotionLoader`` (imported by file path from
   ``/root/reference``) on all 8 shipped clips; see ``tests/golden/make_golden.py`` and ``tests/test_oracle_pins.py``.
   The committed fixtures under ``tests/golden/`` were produced by the live reference, not by this oracle.
-* ``env_oracle``: the reference env module imports ``isaaclab`` (absent) so it cannot be imported; the functions are
-  restated literally and pinned to the known answers recorded in SURVEY.md section 8c (obs row sums / slice for
-  G1_walk) which were produced with the live reference loader.  ``quat_apply`` is upstream Isaac Lab 2.2.0
-  (``isaaclab.utils.math.quat_apply``), not vendored: PARITY UNPINNED for that one function (closed-form rotation columns
-  agree to 1 ulp).
+* ``env_oracle``: PINNED ON THE REFERENCE'S OWN TEXT -- the env modules import ``isaaclab`` (absent) and cannot be imported,
+  so ``oracle/build_ref.py`` cuts the source of the methods on the path (``_get_observations``, ``_get_rewards``,
+  ``_reset_strategy_random``, ``collect_reference_motions``, ``compute_obs``, ``quaternion_to_tangent_and_normal``,
+  ``compute_rewards``, ``exp_reward_with_floor``) out of ``g1_amp_env.py`` / ``humanoid_amp_env.py`` unmodified and
+  ``oracle/ref_harness.py`` executes it on CPU torch; ``tests/golden/make_golden.py`` wrote every env fixture with that text and
+  ``env_oracle`` must reproduce them bit for bit (``tests/test_oracle_pins.py``).  Only ``quat_apply`` / ``quat_rotate_inverse``
+  (upstream Isaac Lab 2.2.0 ``isaaclab.utils.math``, not vendored) are injected restatements: PARITY UNPINNED for those two
+  functions, convention checked against scipy's ``Rotation``.
+* ``dataset_oracle``: PINNED -- ``motions/data_convert.py`` run UNMODIFIED (Pinocchio replaced by the restated forward
+  kinematics) wrote ``tests/golden/dataset/data_convert_output.npz``, which the oracle reproduces bit for bit; the restated FK is
+  pinned on ``motions/custom_motion.npz``, the reference's own output of that conversion made with the real Pinocchio (poses to
+  2 float32 ulp; ``tests/test_dataset_oracle.py``).
 * ``disc_oracle``: skrl is a third-party dependency that is neither vendored nor installed: PARITY UNPINNED; the oracle
   is a literal restatement of the upstream expression.
 """

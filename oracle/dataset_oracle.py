@@ -215,6 +215,38 @@ def compute_angular_velocity(q_prev, q_next, dt, eps=1e-8):
     return (angle / dt) * (q_rel[1:] / sin_half)
 
 
+def velocity_stages(dof_positions, body_positions, body_rotations, dt, exact_angular=False):
+    """data_convert.py:290-297, :349-371 on given positions / rotations: ``(dof_velocities, body_linear_velocities,
+    body_angular_velocities)``.  ``exact_angular``: the SAME angular-velocity expression evaluated in float64 on the float32
+    rotations (the rotations are widened first, so every helper above runs in float64) -- the value the reference's float32
+    evaluation scatters around: one ulp of the relative quaternion's w moves 2 acos(w) / dt by up to ~0.04 rad/s at 60 fps."""
+    from scipy.ndimage import gaussian_filter1d
+
+    N, B = body_positions.shape[:2]
+    dof_velocities = np.zeros_like(dof_positions)
+    dof_velocities[1:-1] = (dof_positions[2:] - dof_positions[:-2]) / (2 * dt)
+    dof_velocities[0] = (dof_positions[1] - dof_positions[0]) / dt
+    dof_velocities[-1] = (dof_positions[-1] - dof_positions[-2]) / dt
+    dof_velocities = gaussian_filter1d(dof_velocities, sigma=1, axis=0)
+    lin = np.zeros_like(body_positions)
+    lin[1:-1] = (body_positions[2:] - body_positions[:-2]) / (2 * dt)
+    lin[0] = (body_positions[1] - body_positions[0]) / dt
+    lin[-1] = (body_positions[-1] - body_positions[-2]) / dt
+    lin = gaussian_filter1d(lin, sigma=1, axis=0)
+    ang = np.zeros((N, B, 3), dtype=np.float32)
+    rot = body_rotations.astype(np.float64) if exact_angular else body_rotations
+    for j in range(B):
+        quats = rot[:, j, :]
+        angular_vels = np.zeros((N, 3), dtype=np.float32)
+        if N > 1:
+            angular_vels[0] = compute_angular_velocity(quats[0], quats[1], dt)
+            angular_vels[-1] = compute_angular_velocity(quats[-2], quats[-1], dt)
+        for k in range(1, N - 1):
+            angular_vels[k] = 0.5 * (compute_angular_velocity(quats[k - 1], quats[k], dt) + compute_angular_velocity(quats[k], quats[k + 1], dt))
+        ang[:, j, :] = gaussian_filter1d(angular_vels, sigma=1, axis=0)
+    return dof_velocities, lin, ang
+
+
 def convert(csv_rows: np.ndarray, tree: KinematicTree, joint_names: Sequence[str] = G1_JOINT_NAMES, body_names: Sequence[str] = G1_BODY_NAMES,
             fps: int = 60) -> Dict[str, np.ndarray]:
     """``main`` of data_convert.py (:161-379) on the already sliced CSV rows (``df.iloc[start:end].to_numpy(float32)``)."""
