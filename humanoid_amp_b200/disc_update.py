@@ -67,6 +67,13 @@ class AmpDiscriminatorUpdate:
         if scaler is not None:
             if scaler.size != self.in_features:
                 raise RuntimeError("scaler size does not match in_features")
+            if scaler.epsilon != 1e-8 or scaler.clip_threshold != 5.0:
+                # the staging kernel evaluates skrl's DEFAULT preprocessor (epsilon 1e-8, clip +-5, the reference's yaml sets
+                # neither): refuse anything else instead of normalising the batch differently from scaler() itself
+                raise RuntimeError(
+                    f"the staging kernel implements RunningStandardScaler(epsilon=1e-8, clip_threshold=5.0); got epsilon={scaler.epsilon}, "
+                    f"clip_threshold={scaler.clip_threshold} -- normalise with scaler(states) first and stage without a scaler"
+                )
             if train:
                 scaler.update(x)
             mean, var = scaler.running_mean, scaler.running_variance

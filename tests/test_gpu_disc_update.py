@@ -230,3 +230,8 @@ def test_errors():
     upd2 = amp.AmpDiscriminatorUpdate(166, (1024, 512), max_batch_rows=256, device=DEV)
     with pytest.raises(amp.AmpB200Error):
         upd2.stage(0, big)  # exceeds max_batch_rows
+    # a scaler with non-default settings is refused instead of being normalised with the defaults
+    odd = amp.RunningStandardScaler(166, epsilon=1e-3, clip_threshold=2.0, device=DEV)
+    upd3 = amp.AmpDiscriminatorUpdate(166, (1024, 512), max_batch_rows=256, device=DEV)
+    with pytest.raises(RuntimeError, match="epsilon"):
+        upd3.stage(0, agent.to(DEV), scaler=odd)
