@@ -139,7 +139,6 @@ struct FusedParams {
     int x_vec;                 // rows are 8-byte aligned: float2 loads
     int xhat_rows_in_order;    // wide inputs (Kp > 256): tmap_x covers a bf16 x_hat of the whole batch written by
                                // normalise_cast_kernel, the converter warps idle
-    int x_prefetch;            // rows in order, 16-byte aligned row tiles, pitch < 2 x in_features: bulk L2 prefetch of the next tile
     int kb1;        // K blocks of layer 1 (Kp / 64)
     int ksteps1_last;  // 16-wide K steps the LAST layer-1 block really needs: ceil((in_features + 2 - 64 (kb1 - 1)) / 16), 1..4
                        // (b1 travels inside the layer-1 product: two padding columns of x_hat hold 1.0, W1 holds b1 there)
@@ -309,10 +308,10 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                         AMP_PROF_ADD(w_h1);
                         asm volatile("fence.proxy.async.global;" ::: "memory");
                     }
-                    // the slot is re-read by the four N1 tiles of this row tile and then overwritten in place: keep it in L2
+                    // the slot is re-read by the four N1 tiles of this row tile (keep it in L2) and dead after the last one
 #pragma unroll 1
                     for (int kb = 0; kb < p.kb1; ++kb)
-                        load_pair(&tmap_x, kb * BK, slot_row0 + (ti & 1) * BM, keep, &tmap_w1, kb * BK, nt * BN);
+                        load_pair(&tmap_x, kb * BK, slot_row0 + (ti & 1) * BM, nt == p.n1_tiles - 1 ? stream : keep, &tmap_w1, kb * BK, nt * BN);
                     if (nt == p.n1_tiles - 1) {
                         free_slot = ti & 1;
                         free_at = loads_issued + STAGES;
@@ -326,7 +325,8 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                         AMP_PROF_ADD(w_h1);
                         asm volatile("fence.proxy.async.global;" ::: "memory");
                     }
-                    load_pair(&tmap_h_load, kb * BK, slot_row0 + (ti & 1) * BM, keep, &tmap_w2, kb * BK, n2 * BN);
+                    // h1 is dead after its last read (the second N2 tile): let L2 evict those lines before live ones
+                    load_pair(&tmap_h_load, kb * BK, slot_row0 + (ti & 1) * BM, n2 == p.n2_tiles - 1 ? stream : keep, &tmap_w2, kb * BK, n2 * BN);
                 });
 #ifdef AMP_DISC_PROFILE
             if (p.prof) {
@@ -430,17 +430,8 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             if (ti >= 2) mbar_wait(xfree + 8 * s, (uint32_t)(((ti >> 1) - 1) & 1));
             const int64_t row_base = (int64_t)tile_of(ti) * BM;
             __nv_bfloat16 *const dst = my_slots + (size_t)s * BM * p.Kp;
-            // pull the fp32 rows of the NEXT tile into L2 while this one is converted: the loads below are latency-bound
-            // (registers cap the bytes in flight), an L2 hit costs a third of a DRAM access
-            if (cw == 0 && lane == 0 && p.x_prefetch && ti + 1 < T) {
-                const int64_t next_base = (int64_t)tile_of(ti + 1) * BM;
-                const int64_t rows_next = min((int64_t)BM, p.M - next_base);
-                if (rows_next > 0) {
-                    const char *a = reinterpret_cast<const char *>(p.x + next_base * p.x_stride);
-                    const uint32_t bytes = (uint32_t)((rows_next * p.x_stride * 4) & ~(int64_t)15);
-                    if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(bytes) : "memory");
-                }
-            }
+            // (A bulk L2 prefetch of the next tile's fp32 rows was measured here: it shortens the converter's load latency but
+            // costs the fused kernel 3.4 % -- the extra L2 fills evict h1 / weight lines -- and the converter is not critical.)
 #ifdef AMP_DISC_PROFILE
             if (p.prof_mode & 4) {  // timing experiment: no conversion work at all (wrong results)
                 __syncwarp();
@@ -987,10 +978,12 @@ int amp_disc_destroy(amp_disc_t *d) {
 // rows one persistent wave covers (one 128-row tile per CTA)
 int64_t amp_disc_chunk_rows(const amp_disc_t *d) { return d ? (int64_t)d->ws_ctas * BM : 0; }
 
-// narrow inputs (K*A <= 254): ONE launch whatever the batch; wide inputs: cast + fused kernel per chunk of xs_rows rows
+// narrow inputs (K*A <= 254): ONE launch for batches beyond two persistent waves, cast + fused kernel below that (nothing
+// to hide the conversion under); wide inputs: cast + fused kernel per chunk of xs_rows rows
 int64_t amp_disc_launch_count(const amp_disc_t *d, int64_t M) {
     if (!d || M <= 0) return 0;
-    return d->wide ? 2 * ((M + d->xs_rows - 1) / d->xs_rows) : 1;
+    if (d->wide) return 2 * ((M + d->xs_rows - 1) / d->xs_rows);
+    return M <= d->xs_rows ? 2 : 1;
 }
 
 int amp_disc_load(amp_disc_t *d, const float *W1, const float *b1, const float *W2, const float *b2, const float *W3,
@@ -1034,7 +1027,11 @@ static int style_reward_impl(amp_disc_t *d, const float *x, int64_t x_stride, co
         const float *xc = row_index ? x : x + r0 * x_stride;
         const int64_t *ic = row_index ? row_index + r0 : nullptr;
         const bool vec = (x_stride % 2 == 0) && ((reinterpret_cast<uintptr_t>(xc) & 7u) == 0);
-        if (d->wide) {
+        // Batches of at most two row tiles per SM (37 888 rows) have no earlier tile to convert under: the converter warps of a
+        // CTA would run 9 dependent load rounds before its first MMA (measured 4096 x 166: 58 us fused against 39-45 us with
+        // the cast kernel at full-chip parallelism), so they take the cast-kernel path; the scratch holds exactly that many rows.
+        const bool external = d->wide || rows <= d->xs_rows;
+        if (external) {
             const int cast_grid = (int)std::min<int64_t>((rows + 7) / 8, (int64_t)sms * 8);
             int rc = vec ? launch_normalise_cast<true>(d->Kp / BK, cast_grid, st, xc, x_stride, rows, d->in_features, d->mean, d->denom,
                                                        d->xs, ic, capacity, flags, 2)
@@ -1056,9 +1053,7 @@ static int style_reward_impl(amp_disc_t *d, const float *x, int64_t x_stride, co
         fp.in_features = d->in_features;
         fp.Kp = d->Kp;
         fp.x_vec = vec ? 1 : 0;
-        fp.xhat_rows_in_order = d->wide ? 1 : 0;
-        // a row tile starts at a multiple of 128 * x_stride * 4 = 512 * x_stride bytes from x: 16-byte aligned when x is
-        fp.x_prefetch = (!row_index && (reinterpret_cast<uintptr_t>(xc) & 15u) == 0 && x_stride < 2 * (int64_t)d->in_features) ? 1 : 0;
+        fp.xhat_rows_in_order = external ? 1 : 0;
         fp.kb1 = d->Kp / BK;
         fp.ksteps1_last = (d->in_features + 2 - BK * (fp.kb1 - 1) + UMMA_K - 1) / UMMA_K;
         fp.n1_tiles = d->h1 / BN;
@@ -1071,7 +1066,9 @@ static int style_reward_impl(amp_disc_t *d, const float *x, int64_t x_stride, co
         fp.logits = logits ? logits + r0 : nullptr;
         fp.prof = d->prof;
         fp.prof_mode = d->prof_mode;
-        if (d->use_pair && m_tiles >= 2) {
+        // CTA pairs once there is more than one row tile per SM; below that single CTAs spread the tiles over twice as many
+        // independent pipelines (4096 rows: 45 us single, 47-51 us pair)
+        if (d->use_pair && m_tiles > sms) {
             // CTA pairs: an even grid of at most ws_ctas CTAs, launched as clusters of 2
             const int pair_blocks = (m_tiles + 1) / 2;
             const int clusters = std::min(pair_blocks, std::min(sms, d->ws_ctas) / 2);
