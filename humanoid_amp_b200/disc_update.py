@@ -135,4 +135,7 @@ class AmpDiscriminatorUpdate:
                 self._h = None
 
     def __del__(self):
-        self.close()
+        try:
+            self.close()
+        except Exception:  # interpreter shutdown: module globals may already be gone; the driver reclaims the handle
+            pass

@@ -104,7 +104,10 @@ class AmpDiscriminator:
                 self._h = None
 
     def __del__(self):
-        self.close()
+        try:
+            self.close()
+        except Exception:  # interpreter shutdown: module globals may already be gone; the driver reclaims the handle
+            pass
 
 
 def style_reward_from_logits(logits: torch.Tensor, reward_scale: float = 2.0) -> torch.Tensor:

@@ -113,7 +113,10 @@ class GradientBucket:
                 self._h = None
 
     def __del__(self):
-        self.close()
+        try:
+            self.close()
+        except Exception:  # interpreter shutdown: module globals may already be gone; the driver reclaims the handle
+            pass
 
 
 def reduce_parameters(parameter_groups: Iterable[Sequence[torch.nn.Parameter]], group=None, flat: torch.Tensor | None = None,
