@@ -848,6 +848,9 @@ int scaler_stats_to_f32(const double *mean, const double *var, int n, float *mea
 
 }  // namespace amp
 
+// Batches of at most this many row tiles per SM take the cast-kernel path (see style_reward_impl)
+constexpr int kCastPathWaves = 8;
+
 struct amp_disc {
     int in_features, Kp, h1, h2;
     int ws_ctas;  // persistent CTAs the h1 / x_hat scratch slots were sized for
@@ -860,7 +863,7 @@ struct amp_disc {
     // rows (measured 0.35 ms vs 0.24 ms per 65 536 x 830 rows), so x_hat of a whole chunk is prepared by normalise_cast_kernel
     // in `xs` (xs_rows x Kp) and the fused kernel streams it by row tile.  Narrow inputs: one launch, converter warps.
     bool wide;
-    int64_t xs_rows;              // rows of `xs`: ws_ctas * 2 * 128 (narrow) or the chunk capacity (wide)
+    int64_t xs_rows;              // rows of `xs`: ws_ctas * kCastPathWaves * 128 (narrow) or the chunk capacity (wide)
     CUtensorMap tmap_x;           // x_hat: 128-row loads
     CUtensorMap tmap_w1, tmap_w2; // weights never move: encoded once
     CUtensorMap tmap_w1_half, tmap_w2_half; // 128-row boxes: each CTA of a pair stages its half of a 256-row weight block
@@ -913,7 +916,9 @@ int amp_disc_create(int32_t in_features, int32_t h1, int32_t h2, int64_t max_row
     if (e == cudaSuccess) e = alloc((void **)&d->mean, (size_t)in_features * 4);
     if (e == cudaSuccess) e = alloc((void **)&d->denom, (size_t)in_features * 4);
     d->wide = d->Kp > 256;
-    d->xs_rows = (int64_t)d->ws_ctas * 2 * BM;
+    // narrow inputs: the in-kernel converter needs two 128-row slots per CTA; the same buffer, sized for eight persistent waves
+    // (151 552 rows, 58 MB at K*A = 166), is the x_hat of a whole batch on the cast-kernel path below the crossover
+    d->xs_rows = (int64_t)d->ws_ctas * kCastPathWaves * BM;
     if (d->wide)  // one chunk = the caller's max_rows, capped at 512 MB of x_hat; larger batches are cut into chunks
         d->xs_rows = std::max<int64_t>(BM, std::min<int64_t>((max_rows + BM - 1) / BM * BM, (((int64_t)512 << 20) / (d->Kp * 2)) / BM * BM));
     if (e == cudaSuccess) e = alloc((void **)&d->xs, (size_t)d->xs_rows * d->Kp * 2);
@@ -978,8 +983,8 @@ int amp_disc_destroy(amp_disc_t *d) {
 // rows one persistent wave covers (one 128-row tile per CTA)
 int64_t amp_disc_chunk_rows(const amp_disc_t *d) { return d ? (int64_t)d->ws_ctas * BM : 0; }
 
-// narrow inputs (K*A <= 254): ONE launch for batches beyond two persistent waves, cast + fused kernel below that (nothing
-// to hide the conversion under); wide inputs: cast + fused kernel per chunk of xs_rows rows
+// narrow inputs (K*A <= 254): ONE launch for batches beyond eight persistent waves, cast + fused kernel below that (too
+// little to hide the first tile's conversion under); wide inputs: cast + fused kernel per chunk of xs_rows rows
 int64_t amp_disc_launch_count(const amp_disc_t *d, int64_t M) {
     if (!d || M <= 0) return 0;
     if (d->wide) return 2 * ((M + d->xs_rows - 1) / d->xs_rows);
@@ -1027,9 +1032,10 @@ static int style_reward_impl(amp_disc_t *d, const float *x, int64_t x_stride, co
         const float *xc = row_index ? x : x + r0 * x_stride;
         const int64_t *ic = row_index ? row_index + r0 : nullptr;
         const bool vec = (x_stride % 2 == 0) && ((reinterpret_cast<uintptr_t>(xc) & 7u) == 0);
-        // Batches of at most two row tiles per SM (37 888 rows) have no earlier tile to convert under: the converter warps of a
-        // CTA would run 9 dependent load rounds before its first MMA (measured 4096 x 166: 58 us fused against 39-45 us with
-        // the cast kernel at full-chip parallelism), so they take the cast-kernel path; the scratch holds exactly that many rows.
+        // Small and medium batches have little to hide the first tile's conversion under: the converter warps of a CTA run 9
+        // dependent load rounds (~17 us at 65 536 rows) before its first MMA.  Measured cast path vs in-kernel conversion, x 166:
+        // 4096 rows 39 vs 58 us, 65 536 rows 111 vs 125 us, 131 072 rows 177 vs 182 us, 262 144 rows equal, 1 M rows 1.29 vs 1.25 ms
+        // (and no 384 MB workspace).  Crossover = eight row tiles per SM; the scratch holds exactly that many rows.
         const bool external = d->wide || rows <= d->xs_rows;
         if (external) {
             const int cast_grid = (int)std::min<int64_t>((rows + 7) / 8, (int64_t)sms * 8);
@@ -1066,6 +1072,9 @@ static int style_reward_impl(amp_disc_t *d, const float *x, int64_t x_stride, co
         fp.logits = logits ? logits + r0 : nullptr;
         fp.prof = d->prof;
         fp.prof_mode = d->prof_mode;
+#ifdef AMP_DISC_PROFILE
+        if (d->prof) cudaMemsetAsync(d->prof, 0, (size_t)d->ws_ctas * 16 * sizeof(long long), st);  // CTAs outside this grid read 0
+#endif
         // CTA pairs once there is more than one row tile per SM; below that single CTAs spread the tiles over twice as many
         // independent pipelines (4096 rows: 45 us single, 47-51 us pair)
         if (d->use_pair && m_tiles > sms) {
@@ -1103,7 +1112,9 @@ static int style_reward_impl(amp_disc_t *d, const float *x, int64_t x_stride, co
             double ea[2][8] = {{0}};
             for (int i = 0; i < n; ++i)
                 for (int k = 0; k < 8; ++k) ea[d->use_pair ? (i & 1) : 0][k] += (double)host[n * 8 + i * 8 + k];
-            const double div = d->use_pair ? n / 2.0 : (double)n;
+            int ran = 0;
+            for (int i = 0; i < n; ++i) ran += (host[n * 8 + i * 8 + 1] + host[n * 8 + i * 8 + 4]) > 0;
+            const double div = std::max(1.0, d->use_pair ? ran / 2.0 : (double)ran);
             for (int rk = 0; rk < (d->use_pair ? 2 : 1); ++rk)
                 fprintf(stderr, "[amp_disc profile] epilogue rank %d: D1 wait=%.0f drain=%.0f post=%.0f slab_wait=%.0f | D2 wait=%.0f drain=%.0f post=%.0f\n", rk,
                         ea[rk][0] / div, ea[rk][1] / div, ea[rk][2] / div, ea[rk][6] / div, ea[rk][3] / div, ea[rk][4] / div, ea[rk][5] / div);

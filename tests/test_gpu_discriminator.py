@@ -124,7 +124,7 @@ def test_multi_chunk_rows_and_row_independence():
 
 def test_one_launch_for_large_batches_and_many_tiles_per_cta():
     """The scaler + cast run inside the fused kernel: a call is ONE launch for a large batch, and a CTA that walks many row
-    tiles (here 4 x 148 x 128 rows + a ragged tail: scratch slots and barriers wrap several times) gives the same bits as the
+    tiles (here 9 x 148 x 128 rows + a ragged tail: scratch slots and barriers wrap several times) gives the same bits as the
     same rows evaluated in small independent calls."""
     import humanoid_amp_b200 as amp
     from humanoid_amp_b200.synthetic import skrl_style_discriminator_params
@@ -132,14 +132,17 @@ def test_one_launch_for_large_batches_and_many_tiles_per_cta():
     W, b = skrl_style_discriminator_params(166, seed=4, logit_gain=3.0)
     disc = amp.AmpDiscriminator(166, device="cuda:0", max_rows=1)  # max_rows is only a hint: nothing is sized by it
     disc.load(W, b, torch.zeros(166, dtype=torch.float64), torch.ones(166, dtype=torch.float64))
-    M = 4 * disc.chunk_rows + 77
+    M = 9 * disc.chunk_rows + 77
     x = torch.randn(M, 166, device="cuda", generator=torch.Generator(device="cuda").manual_seed(0))
     whole = disc.style_reward(x)
-    for lo in (0, 128 * 147, disc.chunk_rows - 5, 3 * disc.chunk_rows + 1000, M - 300):
+    for lo in (0, 128 * 147, disc.chunk_rows - 5, 7 * disc.chunk_rows + 1000, M - 300):
         assert torch.equal(disc.style_reward(x[lo : lo + 300]), whole[lo : lo + 300])
-    # one launch beyond two persistent waves; cast + fused kernel below (nothing to hide the in-kernel conversion under)
-    assert disc.launch_count(M) == 1 and disc.launch_count(2 * disc.chunk_rows + 1) == 1
-    assert disc.launch_count(2 * disc.chunk_rows) == 2 and disc.launch_count(100) == 2 and disc.launch_count(0) == 0
+    # one launch beyond eight persistent waves; cast + fused kernel below (too little to hide the in-kernel conversion under)
+    assert disc.launch_count(M) == 1 and disc.launch_count(8 * disc.chunk_rows + 1) == 1
+    assert disc.launch_count(8 * disc.chunk_rows) == 2 and disc.launch_count(100) == 2 and disc.launch_count(0) == 0
+    # the two paths give the same bits (same scaler arithmetic, same K order per row)
+    mid = 8 * disc.chunk_rows
+    assert torch.equal(disc.style_reward(x[:mid]), whole[:mid])
 
 
 def test_wide_input_chunks_and_gather_give_the_same_bits():
