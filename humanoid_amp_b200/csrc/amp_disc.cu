@@ -1025,7 +1025,11 @@ static int style_reward_impl(amp_disc_t *d, const float *x, int64_t x_stride, co
     AMP_REQUIRE(M <= ((int64_t)1 << 31) - BM, "amp_disc_style_reward: %lld rows exceed the 2^31 row limit of one call", (long long)M);
     cudaStream_t st = as_stream(stream);
     const int sms = sm_count();
-    const int64_t chunk = d->wide ? d->xs_rows : M;
+    // Gathered batches (row_index) always take the cast-kernel path, in chunks of the scratch: random 664-byte rows out of a
+    // multi-GB memory are pure DRAM latency, which six converter warps per SM cannot cover (measured 1 M sampled rows x 166:
+    // 1.99 ms in-kernel against 1.43 ms with the gather done by the cast kernel at full-chip parallelism)
+    const bool always_cast = d->wide || row_index != nullptr;
+    const int64_t chunk = always_cast ? d->xs_rows : M;
     for (int64_t r0 = 0; r0 < M; r0 += chunk) {
         const int64_t rows = std::min(chunk, M - r0);
         const int m_tiles = (int)((rows + BM - 1) / BM);
@@ -1036,7 +1040,7 @@ static int style_reward_impl(amp_disc_t *d, const float *x, int64_t x_stride, co
         // dependent load rounds (~17 us at 65 536 rows) before its first MMA.  Measured cast path vs in-kernel conversion, x 166:
         // 4096 rows 39 vs 58 us, 65 536 rows 111 vs 125 us, 131 072 rows 177 vs 182 us, 262 144 rows equal, 1 M rows 1.29 vs 1.25 ms
         // (and no 384 MB workspace).  Crossover = eight row tiles per SM; the scratch holds exactly that many rows.
-        const bool external = d->wide || rows <= d->xs_rows;
+        const bool external = always_cast || rows <= d->xs_rows;
         if (external) {
             const int cast_grid = (int)std::min<int64_t>((rows + 7) / 8, (int64_t)sms * 8);
             int rc = vec ? launch_normalise_cast<true>(d->Kp / BK, cast_grid, st, xc, x_stride, rows, d->in_features, d->mean, d->denom,

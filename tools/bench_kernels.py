@@ -114,6 +114,58 @@ def main():
         term = torch.zeros(n, dtype=torch.bool, device=DEV)
         ms = timed(lambda: env.get_rewards(term, acts, state[0], lim, acc, state[1], state[4], state[3]))
         row("task_reward_kernel", ms, n * ((29 * 6 + 9) * 4 + 1 + 4), note=f"G1 N={n}, velocity tracking on")
+        # the three per-step kernels in ONE launch (amp_env_step): every simulator tensor read once
+        K = cfg.num_amp_observations
+        rin = dict(reset_terminated=term, actions=acts, soft_joint_pos_limits=lim, joint_acc=acc)
+        ms_three = ms_both + ms
+        ms = timed(lambda: env.step_observations(*state, out=out, reward_inputs=rin))
+        step_bytes = n * (((2 * 29 + 25) + (K - 1) * 83 + K * 83) * 4) + nbytes + n * ((29 * 4 + 9) * 4 + 1 + 4)
+        row("env_step_kernel (obs_step + actor_obs + task_reward fused)", ms, step_bytes,
+            note=f"G1 N={n} K={K} n_actor={n_actor}; the three separate launches take {ms_three:.4f} ms")
+        del env, state, out
+
+    # ---- the per-step env path at the reference's real scale (4096 envs): one fused launch vs three, graph replay, cold L2 ------
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
+
+    def timed_graph(fn, reps=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        g = amp.capture_step(fn, DEV)
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            g.replay()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.median(ts))
+
+    for n, K, n_actor in ((4096, 2, 2), (4096, 10, 2)):
+        ld = loaders["G1_dance"]
+        cfg = amp.AmpEnvCfg(motion_file="", num_envs=n, num_amp_observations=K, robot=amp.G1, num_actor_observations=n_actor, rew_track_vel=1.0,
+                            rew_termination=-1.0, rew_action_l2=-0.1, rew_joint_pos_limits=-10.0, rew_joint_acc_l2=-1e-6, rew_joint_vel_l2=-1e-3)
+        env = amp.AmpEnvPath(cfg, DEV, motion_loader=ld)
+        state = synthetic_sim_state(n, amp.G1, DEV, seed=6)
+        out = torch.empty((n, cfg.observation_space), device=DEV)
+        g = torch.Generator(device="cuda").manual_seed(1)
+        acts, acc = torch.randn(n, 29, device=DEV, generator=g), torch.randn(n, 29, device=DEV, generator=g)
+        lim = torch.randn(n, 29, 2, device=DEV, generator=g)
+        term = torch.zeros(n, dtype=torch.uint8, device=DEV)
+        rin = dict(reset_terminated=term, actions=acts, soft_joint_pos_limits=lim, joint_acc=acc)
+
+        def three():
+            env.get_observations(*state, out=out)
+            env.get_rewards(term, acts, state[0], lim, acc, state[1], state[4], state[3])
+
+        ms3 = timed_graph(three)
+        ms1 = timed_graph(lambda: env.step_observations(*state, out=out, reward_inputs=rin))
+        P = cfg.hist_frame_size
+        nbytes = n * (((2 * 29 + 25) + (K - 1) * 83 + K * 83) * 4 + (71 + 29 + 2 + max(n_actor - 2, 0) * P) * 4 + ((n_actor - 1) * P + cfg.observation_space) * 4 + (29 * 4 + 9) * 4 + 5)
+        row("env step at 4096 envs: ONE launch (amp_env_step), graph replay, L2 flushed", ms1, nbytes, note=f"G1 N={n} K={K} n_actor={n_actor}")
+        row("env step at 4096 envs: three launches (obs_step + actor_obs + task_reward), graph replay, L2 flushed", ms3, nbytes, note=f"G1 N={n} K={K} n_actor={n_actor}")
         del env, state, out
 
     # ---- compute_obs free function ---------------------------------------------------------------------------------------
