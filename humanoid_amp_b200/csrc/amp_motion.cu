@@ -757,14 +757,14 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// one env, whole warp: the per-joint sums are lane-strided partial sums combined with a fixed shuffle tree, lane 0 finishes
-__device__ __forceinline__ void task_reward_env(const RewardScales &sc, int64_t i, int lane, const uint8_t *__restrict__ terminated,
-                                                const float *__restrict__ actions, int act, const float *__restrict__ joint_pos,
-                                                const float *__restrict__ limits, const float *__restrict__ joint_acc,
-                                                const float *__restrict__ joint_vel, int D, const float *__restrict__ body_lin,
-                                                const float *__restrict__ body_quat, int Bsim, int ref,
-                                                const float *__restrict__ command, float *__restrict__ total,
-                                                float *__restrict__ terms, float *__restrict__ track_err) {
+// the per-joint sums of one env (whole warp): lane-strided partial sums combined with a fixed shuffle tree.  Loads only --
+// the fused env-step kernel issues them at the top of an env's trip, together with the observation loads.
+struct RewardSums {
+    float act, lim, acc, vel;
+};
+__device__ __forceinline__ RewardSums task_reward_sums(int64_t i, int lane, const float *__restrict__ actions, int act,
+                                                       const float *__restrict__ joint_pos, const float *__restrict__ limits,
+                                                       const float *__restrict__ joint_acc, const float *__restrict__ joint_vel, int D) {
     float s_act = 0.0f, s_lim = 0.0f, s_acc = 0.0f, s_vel = 0.0f;
     for (int j = lane; j < act; j += 32) {
         const float a = __ldg(actions + i * act + j);
@@ -778,10 +778,38 @@ __device__ __forceinline__ void task_reward_env(const RewardScales &sc, int64_t 
         s_acc += a * a;
         s_vel += w * w;
     }
-    s_act = warp_sum(s_act);
-    s_lim = warp_sum(s_lim);
-    s_acc = warp_sum(s_acc);
-    s_vel = warp_sum(s_vel);
+    RewardSums r;
+    r.act = warp_sum(s_act);
+    r.lim = warp_sum(s_lim);
+    r.acc = warp_sum(s_acc);
+    r.vel = warp_sum(s_vel);
+    return r;
+}
+
+__device__ __forceinline__ void task_reward_finish(const RewardScales &sc, const RewardSums &sums, int64_t i, int lane,
+                                                   const uint8_t *__restrict__ terminated, const float *__restrict__ body_lin,
+                                                   const float *__restrict__ body_quat, int Bsim, int ref,
+                                                   const float *__restrict__ command, float *__restrict__ total,
+                                                   float *__restrict__ terms, float *__restrict__ track_err);
+
+// one env, whole warp: sums, then lane 0 finishes
+__device__ __forceinline__ void task_reward_env(const RewardScales &sc, int64_t i, int lane, const uint8_t *__restrict__ terminated,
+                                                const float *__restrict__ actions, int act, const float *__restrict__ joint_pos,
+                                                const float *__restrict__ limits, const float *__restrict__ joint_acc,
+                                                const float *__restrict__ joint_vel, int D, const float *__restrict__ body_lin,
+                                                const float *__restrict__ body_quat, int Bsim, int ref,
+                                                const float *__restrict__ command, float *__restrict__ total,
+                                                float *__restrict__ terms, float *__restrict__ track_err) {
+    const RewardSums sums = task_reward_sums(i, lane, actions, act, joint_pos, limits, joint_acc, joint_vel, D);
+    task_reward_finish(sc, sums, i, lane, terminated, body_lin, body_quat, Bsim, ref, command, total, terms, track_err);
+}
+
+__device__ __forceinline__ void task_reward_finish(const RewardScales &sc, const RewardSums &sums, int64_t i, int lane,
+                                                   const uint8_t *__restrict__ terminated, const float *__restrict__ body_lin,
+                                                   const float *__restrict__ body_quat, int Bsim, int ref,
+                                                   const float *__restrict__ command, float *__restrict__ total,
+                                                   float *__restrict__ terms, float *__restrict__ track_err) {
+    const float s_act = sums.act, s_lim = sums.lim, s_acc = sums.acc, s_vel = sums.vel;
     if (lane == 0) {
         const float r_term = sc.termination * (terminated[i] ? 1.0f : 0.0f);
         const float r_act = sc.action_l2 * s_act, r_lim = sc.joint_pos_limits * s_lim;
@@ -854,7 +882,7 @@ struct EnvStepParams {
 };
 
 template <int NSLOT>
-__global__ void __launch_bounds__(256, 2) env_step_kernel(const __grid_constant__ EnvStepParams p) {
+__global__ void __launch_bounds__(256, NSLOT <= 3 ? 3 : 2) env_step_kernel(const __grid_constant__ EnvStepParams p) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -891,6 +919,13 @@ __global__ void __launch_bounds__(256, 2) env_step_kernel(const __grid_constant_
 
     for (int64_t i = warp; i < p.N; i += nwarps) {
         // ---- all simulator-state loads of this env, then the history loads, before the first store ------------------
+        // (the kernel's pointers may alias as far as the compiler knows, so nothing below a store is hoisted for us: the reward's
+        // loads and the first slot of last_actions | command are issued here by hand, one DRAM round trip for the whole env)
+        RewardSums sums{};
+        if (p.total) sums = task_reward_sums(i, lane, p.actions, p.act, p.joint_pos, p.limits, p.joint_acc, p.joint_vel, D);
+        float extra0 = 0.0f;  // column base + lane of the actor observation
+        if (p.actor_obs && lane < p.act + p.cmd)
+            extra0 = lane < p.act ? __ldg(p.last_actions + i * p.act + lane) : __ldg(p.command + i * p.cmd + (lane - p.act));
         const float4 q = __ldg(reinterpret_cast<const float4 *>(p.body_quat) + i * Bsim + ref);
         float val[NSLOT], minus[NSLOT];
 #pragma unroll
@@ -947,7 +982,7 @@ __global__ void __launch_bounds__(256, 2) env_step_kernel(const __grid_constant_
             }
             for (int e = lane; e < p.act + p.cmd; e += 32) {
                 const bool is_act = e < p.act;
-                const float v = is_act ? __ldg(p.last_actions + i * p.act + e) : __ldg(p.command + i * p.cmd + (e - p.act));
+                const float v = e == lane ? extra0 : (is_act ? __ldg(p.last_actions + i * p.act + e) : __ldg(p.command + i * p.cmd + (e - p.act)));
                 arow[base + e] = v;
                 if (p.n_hist > 0) {
                     if (is_act && p.inc_act) history_column(base + e, v);
@@ -961,8 +996,7 @@ __global__ void __launch_bounds__(256, 2) env_step_kernel(const __grid_constant_
         }
         // ---- task reward on the same state ----------------------------------------------------------------------------
         if (p.total)
-            task_reward_env(p.sc, i, lane, p.terminated, p.actions, p.act, p.joint_pos, p.limits, p.joint_acc, p.joint_vel, D, p.body_lin,
-                            p.body_quat, Bsim, ref, p.command, p.total, p.terms, p.track_err);
+            task_reward_finish(p.sc, sums, i, lane, p.terminated, p.body_lin, p.body_quat, Bsim, ref, p.command, p.total, p.terms, p.track_err);
     }
 }
 
