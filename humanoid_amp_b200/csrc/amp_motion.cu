@@ -328,10 +328,18 @@ struct __align__(16) FrameMeta {
 };
 static_assert(sizeof(FrameMeta) == 64, "FrameMeta must stay one 64-byte record");
 
+// Table reads.  The shared-memory variant addresses the table with explicit 32-bit shared-space addresses: through a generic
+// pointer nvcc 12.9 rebuilds the shared window base (S2R SR_CgaCtaId + MOV + LEA) in front of every group of loads -- ncu
+// showed those S2R among the most-stalled instructions of the row loop.
 template <bool SMEM_TABLE>
 __device__ __forceinline__ float table_ld(const float *p) {
-    if constexpr (SMEM_TABLE) return *p;  // generic load from a shared-memory address: LDS
-    else return __ldg(p);
+    if constexpr (SMEM_TABLE) {
+        float v;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"((uint32_t)(uintptr_t)p));
+        return v;
+    } else {
+        return __ldg(p);
+    }
 }
 
 #ifdef AMP_COLLECT_PROFILE
@@ -356,7 +364,9 @@ collect_reference_kernel(LibView v, const double *__restrict__ cur_times, const 
         float4 *dst = reinterpret_cast<float4 *>(collect_smem);
         const float4 *src = reinterpret_cast<const float4 *>(v.packed);
         for (int i = threadIdx.x; i < quads; i += blockDim.x) dst[i] = __ldg(src + i);
-        tab = reinterpret_cast<const float *>(collect_smem);
+        // NOT a dereferenceable pointer: the 32-bit shared-space address of the table, carried in a pointer-typed variable so
+        // that both variants share the offset arithmetic below (table_ld<true> reads it with ld.shared)
+        tab = reinterpret_cast<const float *>((uintptr_t)__cvta_generic_to_shared(collect_smem));
         // the last row may be over-read by 32*NSLOT - R floats (values discarded): keep that slack inside the allocation
         meta_base = collect_smem + (size_t)quads * 16 + 512;
         __syncthreads();
