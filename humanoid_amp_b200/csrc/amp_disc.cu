@@ -10,11 +10,12 @@
 //   logit  = h2 . w3 + b3                 fp32, folded into the TMEM read-out of layer 2 (one thread owns one row)
 //   reward = -log(max(1 - 1/(1+exp(-logit)), 1e-4)) * scale
 //
-// Structure: see disc_fused_kernel below -- ONE persistent launch per call (one CTA per SM, 448 threads, warp-specialised:
-// TMA producer, single-thread tcgen05.mma issuer, two sets of four epilogue warps, four scaler/cast warps).  The scaler and
-// the bf16 cast run INSIDE the kernel: the cast warps read the fp32 rows of the CTA's next row tile straight from the
-// caller's buffer (or gather them through row_index), normalise, round to bf16 and park the tile in a per-CTA, L2-resident
-// scratch slot that the TMA producer then streams into the operand ring.  No x_hat workspace in HBM, no second kernel.
+// Structure: see disc_fused_kernel below -- a persistent kernel (one CTA per SM, 512 threads, warp-specialised: TMA producer,
+// single-thread tcgen05.mma issuer, eight read-out warps, six scaler/cast warps).  For large batches of narrow rows the scaler
+// and the bf16 cast run INSIDE the kernel: the cast warps read the fp32 rows of the CTA's next row tile straight from the
+// caller's buffer, normalise, round to bf16 and park the tile in a per-CTA, L2-resident scratch slot that the TMA producer
+// then streams into the operand ring -- ONE launch, no x_hat workspace.  Wide rows (K*A = 830), batches of at most eight row
+// tiles per SM and gathered batches run normalise_cast_kernel first (style_reward_impl explains each with its measurement).
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -128,11 +129,9 @@ __device__ __forceinline__ void walk_schedule(int T, int n1_tiles, int units, G1
 struct FusedParams {
     int64_t M;      // rows of this call
     // scaler + cast stage (converter warps): source rows, statistics, the CTA-private bf16 scratch slots
-    const float *x;            // (rows, in_features) fp32, row pitch x_stride floats
+    const float *x;            // (rows, in_features) fp32, row pitch x_stride floats (gathered batches never get here: they
+                               // take the cast-kernel path, see style_reward_impl)
     int64_t x_stride;
-    const int64_t *row_index;  // NULL: row r of the batch is x[r]; else x[row_index[r]] with x holding `capacity` rows
-    int64_t capacity;
-    uint32_t *flags;           // bit 1 raised by an out-of-range row_index (may be NULL)
     const float *mean, *denom; // fp32 [in_features]: (float)running_mean, sqrt((float)running_variance) + 1e-8
     __nv_bfloat16 *xs;         // (gridDim.x * 2 * 128, Kp) bf16: two x_hat row-tile slots per CTA, L2-resident
     int in_features, Kp;
@@ -450,15 +449,7 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                 if (!in0 && c < p.in_features + 2) { mu.x = -1.0f; rc.x = 1.0f; }
                 if (!in1 && c + 1 < p.in_features + 2) { mu.y = -1.0f; rc.y = 1.0f; }
                 auto source_row = [&](int64_t grow) -> const float * {  // first float of this lane's pair in batch row grow
-                    int64_t sr = grow;
-                    if (p.row_index) {
-                        sr = __ldg(p.row_index + grow);
-                        if (sr < 0 || sr >= p.capacity) {
-                            if (lane == 0 && p.flags) atomicOr(p.flags, 2u);
-                            sr = 0;
-                        }
-                    }
-                    return p.x + sr * p.x_stride + c;
+                    return p.x + grow * p.x_stride + c;
                 };
                 auto emit = [&](int r, float2 x, bool live) {
                     const float a = fminf(fmaxf(__fmul_rn(__fsub_rn(x.x, mu.x), rc.x), -5.0f), 5.0f);
@@ -1054,9 +1045,6 @@ static int style_reward_impl(amp_disc_t *d, const float *x, int64_t x_stride, co
         fp.M = rows;
         fp.x = xc;
         fp.x_stride = x_stride;
-        fp.row_index = ic;
-        fp.capacity = capacity;
-        fp.flags = flags;
         fp.mean = d->mean;
         fp.denom = d->denom;
         fp.xs = d->xs;
