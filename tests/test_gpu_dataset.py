@@ -99,3 +99,27 @@ def test_argument_checks():
         dataset.convert_rows(np.zeros((4, 30), dtype=np.float32), tree, device="cuda:0")
     with pytest.raises(AmpB200Error):
         dataset.convert_rows(np.zeros((4, 36), dtype=np.float32), tree, device="cpu")
+
+
+def test_command_line_writes_a_clip_the_motion_loader_reads(tmp_path):
+    """``python -m humanoid_amp_b200.dataset`` keeps the reference tool's command line (data_convert.py:133-158) and writes the
+    same ``.npz`` layout: the file loads into the product ``MotionLoader`` and into the oracle loader with identical tensors."""
+    import humanoid_amp_b200 as amp
+    from humanoid_amp_b200 import dataset
+    from oracle import OracleMotionLoader
+
+    out = str(tmp_path / "clip.npz")
+    dataset.main(["--csv", CSV, "--urdf", URDF, "--meshes", str(tmp_path), "--output", out, "--start", "10", "--end", "90"])
+    d = np.load(out)
+    assert set(d.files) == {"fps", "dof_names", "body_names", "dof_positions", "dof_velocities", "body_positions", "body_rotations",
+                            "body_linear_velocities", "body_angular_velocities"}  # fmt: skip
+    assert d["dof_positions"].shape == (159, 29) and d["body_rotations"].shape == (159, 25, 4) and int(d["fps"]) == 60
+    assert d["dof_positions"].dtype == np.float64 and d["body_positions"].dtype == np.float32
+    loader = amp.MotionLoader(out, "cuda:0")
+    ora = OracleMotionLoader([out])
+    assert loader.num_frames == ora.num_frames == 159 and loader.dof_names == list(ora.dof_names)
+    assert torch.equal(loader.body_positions.cpu(), ora.body_positions) and torch.equal(loader.dof_positions.cpu(), ora.dof_positions)
+    # the G1 env path runs on the converted clip (pelvis reference body, the four key bodies are among the 25 recorded links)
+    env = amp.AmpEnvPath(amp.AmpEnvCfg(motion_file=out, num_envs=8, num_amp_observations=2, robot=amp.G1), "cuda:0", motion_loader=loader)
+    rows = env.collect_reference_motions(64)
+    assert rows.shape == (64, 2 * 83) and bool(torch.isfinite(rows).all())
