@@ -214,3 +214,21 @@ def test_cuda_graph_capture_of_a_whole_step(tmp_path):
         graph.replay()
         torch.cuda.synchronize()
         assert torch.equal(obs, want[0]) and torch.equal(env.amp_observation_buffer, want[1]) and torch.equal(reward, want[2])
+
+
+def test_random_batch_sizes_all_paths_agree_bitwise_and_are_deterministic():
+    """Stress of the converter / producer / issuer hand-offs: batches of random size take the in-kernel conversion (above eight
+    row tiles per SM) or the cast-kernel path; the same rows evaluated in pieces (always the cast path) must give the same bits,
+    and repeated calls must be bit-identical (no race shows up as run-to-run noise)."""
+    disc, _, inputs = build(166, 5.0)
+    rng = np.random.default_rng(7)
+    x = inputs(420_000, 5).cuda()
+    whole = disc.style_reward(x)
+    for _ in range(3):
+        assert torch.equal(disc.style_reward(x), whole)
+    for M in [int(v) for v in rng.integers(1, 420_000, 12)] + [151_552, 151_553, 151_680]:
+        lo = int(rng.integers(0, 420_000 - M + 1))
+        got = disc.style_reward(x[lo : lo + M])
+        assert torch.equal(got, whole[lo : lo + M]), (M, lo)
+    pieces = torch.cat([disc.style_reward(x[i : i + 100_000]) for i in range(0, 420_000, 100_000)])
+    assert torch.equal(pieces, whole)
