@@ -148,6 +148,7 @@ struct FusedParams {
     float *reward;  // [M]
     float *logits;  // [M] or NULL
     long long *prof;  // AMP_DISC_PROFILE builds only: per-CTA cycle counters of the producer / issuer waits, else NULL
+    int prof_ctas;    // AMP_DISC_PROFILE builds only: CTAs the counter buffer is laid out for (issuer block, then read-out block)
     int prof_mode;    // AMP_DISC_PROFILE builds only: bit 0 = skip the h1 staging + TMA store (timing experiment, wrong results)
 };
 
@@ -186,6 +187,10 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef AMP_DISC_PROFILE
+    unsigned long long ns_entry = 0;
+    if (threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_entry));
+#endif
     const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
     const bool leader = rank == 0;
     const int num_m_tiles = (int)((p.M + BM - 1) / BM);
@@ -235,6 +240,15 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+#ifdef AMP_DISC_PROFILE
+    if (threadIdx.x == 0 && p.prof) {
+        unsigned long long ns;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+        long long *e = p.prof + (size_t)p.prof_ctas * 8 + blockIdx.x * 8;
+        e[7] = (long long)(ns - ns_entry);  // entry -> setup done (barrier init, TMEM alloc, first sync)
+        p.prof[blockIdx.x * 8 + 7] = (long long)ns_entry;
+    }
+#endif
     const bool is_epilogue_warp = warp >= EPI_WARP0 && warp < EPI_WARP0 + NUM_EPI_THREADS / 32;
     // accumulator-drained barriers live in the leader CTA; the epilogue threads of both CTAs arrive there
     const uint32_t acc_empty_at_leader = PAIR ? mapa_rank(acc_empty, 0) : acc_empty;  // + 8 * region
@@ -681,7 +695,7 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             });
 #ifdef AMP_DISC_PROFILE
         if (p.prof && ew == 0 && lane == 0) {
-            long long *e = p.prof + (size_t)gridDim.x * 8 + blockIdx.x * 8;
+            long long *e = p.prof + (size_t)p.prof_ctas * 8 + blockIdx.x * 8;
             e[0] = e_wait1; e[1] = e_drain1; e[2] = e_post1; e[3] = e_wait2; e[4] = e_drain2; e[5] = e_post2; e[6] = e_slab;
         }
 #endif
@@ -689,6 +703,13 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 
     tcgen05_fence_before();
     if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
+#ifdef AMP_DISC_PROFILE
+    if (threadIdx.x == 0 && p.prof) {
+        unsigned long long ns;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+        p.prof[blockIdx.x * 8 + 7] = (long long)ns - p.prof[blockIdx.x * 8 + 7];  // entry -> all roles done
+    }
+#endif
     if (warp == 1) {
         tcgen05_fence_after();
         if constexpr (PAIR)
@@ -1064,6 +1085,7 @@ static int style_reward_impl(amp_disc_t *d, const float *x, int64_t x_stride, co
         fp.logits = logits ? logits + r0 : nullptr;
         fp.prof = d->prof;
         fp.prof_mode = d->prof_mode;
+        fp.prof_ctas = d->ws_ctas;
 #ifdef AMP_DISC_PROFILE
         if (d->prof) cudaMemsetAsync(d->prof, 0, (size_t)d->ws_ctas * 16 * sizeof(long long), st);  // CTAs outside this grid read 0
 #endif
@@ -1119,6 +1141,14 @@ static int style_reward_impl(amp_disc_t *d, const float *x, int64_t x_stride, co
             for (int k = 0; k < 8; ++k) acc[k] += (double)host[i * 8 + k];
         }
         if (cnt)
+            fprintf(stderr, "[amp_disc profile] CTA wall: entry->setup done %.2f us, entry->all roles done %.2f us (mean over CTAs that ran)\n",
+                    [&] { double a = 0; int c = 0; for (int i = 0; i < n; ++i) if (host[i * 8 + 0] > 0) { a += (double)host[n * 8 + i * 8 + 7]; ++c; } return c ? a / c * 1e-3 : 0.0; }(),
+                    [&] { double a = 0; int c = 0; for (int i = 0; i < n; ++i) if (host[i * 8 + 0] > 0) { a += (double)host[i * 8 + 7]; ++c; } return c ? a / c * 1e-3 : 0.0; }());
+            {
+                double mn = 1e30, mx = 0; long long e0 = 0x7fffffffffffffffLL, e1 = 0;
+                for (int i = 0; i < n; ++i) if (host[i * 8 + 0] > 0) { mn = std::min(mn, (double)host[i * 8 + 7]); mx = std::max(mx, (double)host[i * 8 + 7]); }
+                fprintf(stderr, "[amp_disc profile] CTA wall min %.2f us max %.2f us\n", mn * 1e-3, mx * 1e-3);
+            }
             fprintf(stderr, "[amp_disc profile] issuer CTAs=%d total=%.0f wait_full=%.0f wait_d1_empty=%.0f wait_d2_empty=%.0f | producer(all) wait_empty=%.0f wait_h1+xhat=%.0f (cycles, mean per CTA) | issuer wall %.1f us => SM clock %.0f MHz\n",
                     cnt, acc[0] / cnt, acc[1] / cnt, acc[2] / cnt, acc[3] / cnt, acc[4] / n, acc[5] / n, acc[6] / cnt * 1e-3,
                     acc[0] / acc[6] * 1e3);
