@@ -719,6 +719,397 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     }
 }
 
+// =====================================================================================================================
+// Small batches (at most one row tile per two SMs, e.g. the 4096 environments of the reference configs): ONE launch, a cluster
+// of two CTAs per 128-row tile.  With one tile per CTA nothing overlaps -- the fused kernel above spends its time in a serial
+// chain of 172 MMAs (16 us) behind a separate cast launch.  Here the chain is split over the pair and the cast is folded in:
+//
+//   both CTAs    all warps: scaler + bf16 cast of the tile straight into shared memory in the UMMA operand layout (resident
+//                A operand of layer 1; the two CTAs convert the same rows, L2 serves the second one)
+//   CTA r        layer 1, N tiles 2r and 2r+1 (22 MMAs)  ->  ReLU -> bf16 -> TMA store into the tile's h1 scratch rows
+//   cluster barrier (h1 complete in L2)
+//   CTA r        layer 2, N tile r (64 MMAs), h1 by TMA
+//   CTA 0        relu(acc + b2) . w3 over ITS 256 columns, the four partial sums of every thread go to the same thread of CTA 1
+//   cluster barrier
+//   CTA 1        continues the SAME accumulation chains with its columns, combines the two column halves, emits logit + reward
+//
+// Every arithmetic step and its order is the one of disc_fused_kernel (same x_hat, same MMAs per accumulator, the layer-3 dot is
+// the fused kernel's per-thread chain handed from CTA 0 to CTA 1), so results are bit-identical with the large-batch paths.
+// 320 threads: warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2..9 read-out (as above).
+// =====================================================================================================================
+constexpr int SMALL_THREADS = 320;
+constexpr int SMALL_STAGES = 3;
+constexpr int SMALL_STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;  // 48 KiB
+constexpr int SMALL_STAGING_BYTES = 8 * STORE_SLAB_BYTES;        // one 32 x 32 slab per read-out warp
+__host__ __device__ constexpr int small_smem_bytes(int kb1) {
+    return kb1 * A_STAGE_BYTES + SMALL_STAGES * SMALL_STAGE_BYTES + SMALL_STAGING_BYTES + 256 /*barriers*/ + 4096 /*chain hand-off*/ +
+           1024 /*partial dots*/ + 1024 /*alignment slack*/;
+}
+
+struct SmallParams {
+    int64_t M;
+    const float *x;
+    int64_t x_stride;
+    const int64_t *row_index;  // NULL or gathered rows (x holds `capacity` rows)
+    int64_t capacity;
+    uint32_t *flags;
+    const float *mean, *denom;
+    int in_features, kb1, ksteps1_last, x_vec;
+    int n1_tiles, n2_tiles;  // 4, 2 (the kernel requires h1 = 1024, h2 = 512: two N tiles of each layer per CTA / one per CTA)
+    const float *b2, *w3, *b3;
+    float scale;
+    float *reward, *logits;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SMALL_THREADS, 1)
+disc_small_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_constant__ CUtensorMap tmap_h_load,
+                  const __grid_constant__ CUtensorMap tmap_h_store, const __grid_constant__ CUtensorMap tmap_w2, SmallParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t smem_a1 = base;                                    // kb1 K-blocks of the resident x_hat tile
+    const uint32_t ring = smem_a1 + p.kb1 * A_STAGE_BYTES;            // stage: A 16 KiB | B 32 KiB
+    const uint32_t staging = ring + SMALL_STAGES * SMALL_STAGE_BYTES;
+    const uint32_t bars = staging + SMALL_STAGING_BYTES;
+    const uint32_t full_bar = bars, empty_bar = bars + 8 * SMALL_STAGES;
+    const uint32_t acc_full = bars + 64, acc_empty = bars + 80;        // 2 x 8 B each (TMEM regions 0 / 1)
+    const uint32_t tmem_slot = bars + 96;
+    const uint32_t chain_smem = bars + 256;                            // 256 threads x 4 floats from CTA 0
+    const uint32_t part_smem = chain_smem + 4096;                      // 4 x 32 floats
+    uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    float *chain_in = reinterpret_cast<float *>(smem_raw + (chain_smem - smem_u32(smem_raw)));
+    float *part = reinterpret_cast<float *>(smem_raw + (part_smem - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int tile = (int)blockIdx.x >> 1;
+    const int64_t row_base = (int64_t)tile * BM;
+    const int h1_row0 = tile * BM;  // this tile's rows in the h1 scratch
+    const int kb2 = 4 * p.n1_tiles;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w1) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_h_load) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_h_store) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w2) : "memory");
+        for (int i = 0; i < SMALL_STAGES; ++i) {
+            mbar_init(full_bar + 8 * i, 1);
+            mbar_init(empty_bar + 8 * i, 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(acc_full + 8 * i, 1);
+            mbar_init(acc_empty + 8 * i, NUM_EPI_THREADS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+
+    // ---- scaler + bf16 cast of the tile, straight into the 128B-swizzled K-major operand layout (all ten warps) -----------
+    // row r of K-block kb at kb * 16 KiB + r * 128 B, 16-byte chunk index XOR (r & 7); lane l owns the column pair (2l, 2l+1)
+    // of every K-block.  All K-blocks of seven rows are in flight per warp (the tile is converted in two load rounds: every
+    // round is a DRAM round trip on the critical path of a kernel that is nothing but latency).
+    {
+        constexpr int RIF = 7, KB = 3;  // small_ok: kb1 <= 3
+        float2 mu[KB], rc[KB];
+        bool in0[KB], in1[KB];
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+            const int c = 2 * (lane + 32 * kb);
+            in0[kb] = kb < p.kb1 && c < p.in_features;
+            in1[kb] = kb < p.kb1 && c + 1 < p.in_features;
+            mu[kb] = make_float2(in0[kb] ? __ldg(p.mean + c) : 0.0f, in1[kb] ? __ldg(p.mean + c + 1) : 0.0f);
+            rc[kb] = make_float2(in0[kb] ? __frcp_rn(__ldg(p.denom + c)) : 0.0f, in1[kb] ? __frcp_rn(__ldg(p.denom + c + 1)) : 0.0f);
+            if (!in0[kb] && c < p.in_features + 2) { mu[kb].x = -1.0f; rc[kb].x = 1.0f; }  // bias columns: (0 - (-1)) * 1 = 1
+            if (!in1[kb] && c + 1 < p.in_features + 2) { mu[kb].y = -1.0f; rc[kb].y = 1.0f; }
+        }
+#pragma unroll 1
+        for (int r0 = warp; r0 < BM; r0 += (SMALL_THREADS / 32) * RIF) {
+            float2 v[RIF][KB];
+#pragma unroll
+            for (int q = 0; q < RIF; ++q) {
+                const int r = r0 + q * (SMALL_THREADS / 32);
+                const int64_t grow = row_base + r;
+                const bool live = r < BM && grow < p.M;
+                int64_t sr = grow;
+                if (live && p.row_index) {
+                    sr = __ldg(p.row_index + grow);
+                    if (sr < 0 || sr >= p.capacity) {
+                        if (lane == 0 && p.flags) atomicOr(p.flags, 2u);
+                        sr = 0;
+                    }
+                }
+                const float *xr = p.x + sr * p.x_stride + 2 * lane;
+#pragma unroll
+                for (int kb = 0; kb < KB; ++kb) {
+                    v[q][kb] = make_float2(0.0f, 0.0f);
+                    if (live && in0[kb]) {
+                        if (p.x_vec && in1[kb]) {
+                            v[q][kb] = __ldcs(reinterpret_cast<const float2 *>(xr + 64 * kb));
+                        } else {
+                            v[q][kb].x = __ldcs(xr + 64 * kb);
+                            if (in1[kb]) v[q][kb].y = __ldcs(xr + 64 * kb + 1);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < RIF; ++q) {
+                const int r = r0 + q * (SMALL_THREADS / 32);
+                if (r >= BM) continue;
+                const bool live = row_base + r < p.M;
+#pragma unroll
+                for (int kb = 0; kb < KB; ++kb) {
+                    if (kb >= p.kb1) continue;
+                    const float a = fminf(fmaxf(__fmul_rn(__fsub_rn(v[q][kb].x, mu[kb].x), rc[kb].x), -5.0f), 5.0f);
+                    const float b = fminf(fmaxf(__fmul_rn(__fsub_rn(v[q][kb].y, mu[kb].y), rc[kb].y), -5.0f), 5.0f);
+                    const __nv_bfloat162 o = live ? __floats2bfloat162_rn(a, b) : __floats2bfloat162_rn(0.0f, 0.0f);
+                    const uint32_t addr = smem_a1 + (uint32_t)(kb * A_STAGE_BYTES + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4) + ((lane & 3) << 2));
+                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(*reinterpret_cast<const uint32_t *>(&o)) : "memory");
+                }
+            }
+        }
+        fence_proxy_async_smem();  // generic-proxy shared writes -> visible to the tensor core (async proxy)
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();  // barriers initialised in both CTAs, TMEM allocated, x_hat in place
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ================= TMA producer ==================================================================================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint64_t keep = l2_policy_evict_last(), stream = l2_policy_evict_first();
+            auto acquire = [&]() {
+                mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+                return full_bar + 8 * stage;
+            };
+            auto advance = [&]() {
+                if (++stage == SMALL_STAGES) { stage = 0; phase ^= 1; }
+            };
+            for (int j = 0; j < 2; ++j) {  // layer 1: only the weight block moves, x_hat is resident
+                const int nt = 2 * (int)rank + j;
+                for (int kb = 0; kb < p.kb1; ++kb) {
+                    const uint32_t fb = acquire();
+                    mbar_arrive_expect_tx(fb, (uint32_t)B_STAGE_BYTES);
+                    tma_load_2d_hint(ring + stage * SMALL_STAGE_BYTES + A_STAGE_BYTES, &tmap_w1, kb * BK, nt * BN, fb, keep);
+                    advance();
+                }
+            }
+            // layer 2, N tile `rank`: the weight blocks of the first stages do not depend on h1 and are requested before the
+            // cluster barrier; the h1 blocks follow once both CTAs have stored their halves
+            int b_issued = 0;
+            int b_stage[SMALL_STAGES];
+            uint32_t b_full[SMALL_STAGES];
+            for (; b_issued < SMALL_STAGES && b_issued < kb2; ++b_issued) {
+                const uint32_t fb = acquire();
+                mbar_arrive_expect_tx(fb, (uint32_t)SMALL_STAGE_BYTES);
+                tma_load_2d_hint(ring + stage * SMALL_STAGE_BYTES + A_STAGE_BYTES, &tmap_w2, b_issued * BK, (int)rank * BN, fb, keep);
+                b_stage[b_issued] = stage;
+                b_full[b_issued] = fb;
+                advance();
+            }
+            cluster_sync_all();  // #1: h1 of the tile is complete (both CTAs' TMA stores have been waited for)
+            asm volatile("fence.proxy.async.global;" ::: "memory");
+            for (int kb = 0; kb < b_issued; ++kb)
+                tma_load_2d_hint(ring + b_stage[kb] * SMALL_STAGE_BYTES, &tmap_h_load, kb * BK, h1_row0, b_full[kb], rank == 1 ? stream : keep);
+            for (int kb = b_issued; kb < kb2; ++kb) {
+                const uint32_t fb = acquire();
+                mbar_arrive_expect_tx(fb, (uint32_t)SMALL_STAGE_BYTES);
+                tma_load_2d_hint(ring + stage * SMALL_STAGE_BYTES, &tmap_h_load, kb * BK, h1_row0, fb, stream);
+                tma_load_2d_hint(ring + stage * SMALL_STAGE_BYTES + A_STAGE_BYTES, &tmap_w2, kb * BK, (int)rank * BN, fb, keep);
+                advance();
+            }
+            cluster_sync_all();  // #2
+        } else {  // the idle lanes only take part in the two cluster barriers (they must not wait for lane 0 in between)
+            cluster_sync_all();  // #1
+            cluster_sync_all();  // #2
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =====================================================================================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            auto advance = [&]() {
+                if (++stage == SMALL_STAGES) { stage = 0; phase ^= 1; }
+            };
+            for (int j = 0; j < 2; ++j) {  // layer 1 into TMEM region j
+                for (int kb = 0; kb < p.kb1; ++kb) {
+                    mbar_wait(full_bar + 8 * stage, phase);
+                    tcgen05_fence_after();
+                    const uint64_t a0 = make_kmajor_sw128_desc(smem_a1 + kb * A_STAGE_BYTES);
+                    const uint64_t b0 = make_kmajor_sw128_desc(ring + stage * SMALL_STAGE_BYTES + A_STAGE_BYTES);
+                    const int ksteps = kb == p.kb1 - 1 ? p.ksteps1_last : BK / UMMA_K;
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        if (k >= ksteps) break;
+                        umma_bf16(tmem_base + j * ACC_COLS, a0 + 2 * k, b0 + 2 * k, kInstrDesc, (uint32_t)(kb != 0 || k != 0));
+                    }
+                    umma_commit(empty_bar + 8 * stage);
+                    advance();
+                }
+                umma_commit(acc_full + 8 * j);
+            }
+            cluster_sync_all();  // #1 (the layer-2 operands below only arrive after it)
+            mbar_wait(acc_empty, 0u);  // layer-1 tile 0 has been read out of region 0
+            tcgen05_fence_after();
+            for (int kb = 0; kb < kb2; ++kb) {  // layer 2 into region 0
+                mbar_wait(full_bar + 8 * stage, phase);
+                tcgen05_fence_after();
+                const uint64_t a0 = make_kmajor_sw128_desc(ring + stage * SMALL_STAGE_BYTES);
+                const uint64_t b0 = make_kmajor_sw128_desc(ring + stage * SMALL_STAGE_BYTES + A_STAGE_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16(tmem_base, a0 + 2 * k, b0 + 2 * k, kInstrDesc, (uint32_t)(kb != 0 || k != 0));
+                umma_commit(empty_bar + 8 * stage);
+                advance();
+            }
+            umma_commit(acc_full);  // second completion of region 0's barrier: parity 1
+            cluster_sync_all();  // #2
+        } else {
+            cluster_sync_all();  // #1
+            cluster_sync_all();  // #2
+        }
+    } else {
+        // ================= read-out warps 2..9 (quarter = TMEM lane quarter, colhalf = column half of the accumulator) ========
+        const int ew = warp - 2;
+        const int quarter = warp & 3;
+        const int colhalf = ew >> 2;
+        const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+        const uint32_t col_base = (uint32_t)(colhalf * (BN / 2));
+        const uint64_t h1_keep = l2_policy_evict_last();
+        const uint32_t slab = staging + (uint32_t)(ew * STORE_SLAB_BYTES);
+        for (int j = 0; j < 2; ++j) {  // ---- D1: ReLU -> bf16 -> slab -> TMA store into the h1 scratch (as in the fused kernel) ----
+            const int nt = 2 * (int)rank + j;
+            const uint32_t acc = tmem_base + lane_base + j * ACC_COLS + col_base;
+            mbar_wait(acc_full + 8 * j, 0u);
+            tcgen05_fence_after();
+            uint32_t v[2][32];
+            tmem_ld_32x32(acc, v[0]);
+#pragma unroll 1
+            for (int hp = 0; hp < 4; hp += 2) {
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int h = hp + hh;
+                    const int col = nt * BN + (int)col_base + h * 32;
+                    if (lane == 0) bulk_wait_read<0>();  // the previous store has drained the slab
+                    __syncwarp();
+                    tmem_ld_wait();
+                    if (h + 1 < 4) {
+                        tmem_ld_32x32(acc + (uint32_t)((h + 1) * 32), v[hh ^ 1]);
+                    } else {
+                        tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(acc_empty + 8 * j);
+                    }
+                    const uint32_t(&cur)[32] = v[hh];
+                    const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.0f, 0.0f);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const __nv_bfloat162 p0 = __hmax2(__floats2bfloat162_rn(__uint_as_float(cur[8 * q + 0]), __uint_as_float(cur[8 * q + 1])), zero2);
+                        const __nv_bfloat162 p1 = __hmax2(__floats2bfloat162_rn(__uint_as_float(cur[8 * q + 2]), __uint_as_float(cur[8 * q + 3])), zero2);
+                        const __nv_bfloat162 p2 = __hmax2(__floats2bfloat162_rn(__uint_as_float(cur[8 * q + 4]), __uint_as_float(cur[8 * q + 5])), zero2);
+                        const __nv_bfloat162 p3 = __hmax2(__floats2bfloat162_rn(__uint_as_float(cur[8 * q + 6]), __uint_as_float(cur[8 * q + 7])), zero2);
+                        const int chunk = q ^ ((lane >> 1) & 3);  // SWIZZLE_64B
+                        st_shared_v4(slab + (uint32_t)(lane * 64 + chunk * 16), *reinterpret_cast<const uint32_t *>(&p0),
+                                     *reinterpret_cast<const uint32_t *>(&p1), *reinterpret_cast<const uint32_t *>(&p2),
+                                     *reinterpret_cast<const uint32_t *>(&p3));
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d_hint(&tmap_h_store, slab, col, h1_row0 + quarter * 32, h1_keep);
+                        bulk_commit();
+                    }
+                }
+            }
+        }
+        if (lane == 0) bulk_wait_all();  // this warp's part of h1 is in L2
+        __syncwarp();
+        cluster_sync_all();  // #1
+        // ---- D2: this CTA's 256 columns of h2 (N tile `rank`), the fused kernel's per-thread chain -----------------------------
+        float dot[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        const int slot4 = (ew * 32 + lane) * 4;
+        auto chain_step = [&]() {
+            const uint32_t acc = tmem_base + lane_base + col_base;
+            mbar_wait(acc_full, 1u);
+            tcgen05_fence_after();
+            uint32_t v[2][32];
+            tmem_ld_32x32(acc, v[0]);
+#pragma unroll 1
+            for (int cp = 0; cp < 4; cp += 2) {
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int chunk = cp + cc;
+                    const int col0 = (int)rank * BN + (int)col_base + chunk * 32;
+                    const float4 *bias4 = reinterpret_cast<const float4 *>(p.b2 + col0);
+                    const float4 *w4 = reinterpret_cast<const float4 *>(p.w3 + col0);
+                    float4 bb[4], ww[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        bb[q] = __ldg(bias4 + q);
+                        ww[q] = __ldg(w4 + q);
+                    }
+                    tmem_ld_wait();
+                    if (chunk + 1 < 4) tmem_ld_32x32(acc + (uint32_t)((chunk + 1) * 32), v[cc ^ 1]);
+                    const uint32_t(&cur)[32] = v[cc];
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        if (half == 1) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                bb[q] = __ldg(bias4 + 4 + q);
+                                ww[q] = __ldg(w4 + 4 + q);
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int e = 16 * half + 4 * q;
+                            dot[0] = fmaf(fmaxf(__uint_as_float(cur[e + 0]) + bb[q].x, 0.0f), ww[q].x, dot[0]);
+                            dot[1] = fmaf(fmaxf(__uint_as_float(cur[e + 1]) + bb[q].y, 0.0f), ww[q].y, dot[1]);
+                            dot[2] = fmaf(fmaxf(__uint_as_float(cur[e + 2]) + bb[q].z, 0.0f), ww[q].z, dot[2]);
+                            dot[3] = fmaf(fmaxf(__uint_as_float(cur[e + 3]) + bb[q].w, 0.0f), ww[q].w, dot[3]);
+                        }
+                    }
+                }
+            }
+        };
+        if (rank == 0) {
+            chain_step();
+            // hand the four running sums to the same thread of CTA 1 (its shared memory, through the cluster window)
+            const uint32_t remote = mapa_rank(chain_smem + (uint32_t)slot4 * 4u, 1);
+            asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(remote), "f"(dot[0]), "f"(dot[1]), "f"(dot[2]), "f"(dot[3]) : "memory");
+            cluster_sync_all();  // #2 (release: the stores above are visible to CTA 1 after its wait)
+        } else {
+            cluster_sync_all();  // #2
+            const float4 in = *reinterpret_cast<const float4 *>(chain_in + slot4);
+            dot[0] = in.x; dot[1] = in.y; dot[2] = in.z; dot[3] = in.w;
+            chain_step();
+            const float mine = (dot[0] + dot[1]) + (dot[2] + dot[3]);
+            float *slot = part + quarter * 32 + lane;
+            if (colhalf == 1) *slot = mine;
+            asm volatile("bar.sync %0, 64;" ::"r"(8 + quarter) : "memory");
+            if (colhalf == 0) {
+                const int64_t row = row_base + quarter * 32 + lane;
+                if (row < p.M) {
+                    const float logit = (mine + *slot) + __ldg(p.b3);
+                    if (p.logits) p.logits[row] = logit;
+                    p.reward[row] = style_reward(logit, p.scale);
+                }
+            }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
 // ---- RunningStandardScaler (eval) + bf16 cast: x (M, in) fp32 -> x_hat (M, Kp) bf16, zero padded -----------------------
 // One warp per row; lane l owns the column pairs (2(l + 32 j), +1), j < NB = Kp / 64, of EVERY row it visits, so the
 // scaler statistics of its columns live in registers and a row costs NB 8-byte loads and NB 4-byte stores per lane, all
@@ -881,6 +1272,7 @@ struct amp_disc {
     CUtensorMap tmap_w1_half, tmap_w2_half; // 128-row boxes: each CTA of a pair stages its half of a 256-row weight block
     CUtensorMap tmap_h_load, tmap_h_store;  // h1 scratch: 128-row loads, 32-row epilogue slab stores
     long long *prof;                        // AMP_DISC_PROFILE builds: device counters (ws_ctas x 16)
+    bool small_ok;                          // the two-CTA-per-tile kernel applies (1024-512 hidden sizes, K*A <= 190)
     bool use_pair;                          // CTA-pair (cta_group::2) kernel (default; AMP_B200_DISC_PAIR=0 at create selects single)
     int prof_mode;                          // AMP_DISC_PROFILE builds: AMP_DISC_PROF_MODE read once at create
     bool loaded;
@@ -949,6 +1341,12 @@ int amp_disc_create(int32_t in_features, int32_t h1, int32_t h2, int64_t max_row
     // epilogue slabs: 32 rows x 32 columns (64-byte rows, 64B swizzle)
     if (rc == AMP_OK) rc = make_tmap(&d->tmap_h_store, d->hid, (int64_t)d->ws_ctas * 2 * BM, h1, h1, 32, SLAB_COLS, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc == AMP_OK) {
+        const char *small_env = getenv("AMP_B200_DISC_SMALL");  // 0 disables the small-batch kernel (tests compare the paths)
+        d->small_ok = h1 == 4 * BN && h2 == 2 * BN && d->Kp / BK <= 3 && !(small_env && small_env[0] == '0');
+        if (d->small_ok) {
+            e = cudaFuncSetAttribute(disc_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem_bytes(d->Kp / BK));
+            if (e != cudaSuccess) rc = cuda_fail(e, "cudaFuncSetAttribute(disc_small_kernel)");
+        }
         e = cudaFuncSetAttribute(disc_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_smem_bytes(false));
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(disc_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_smem_bytes(true));
@@ -1000,6 +1398,7 @@ int64_t amp_disc_chunk_rows(const amp_disc_t *d) { return d ? (int64_t)d->ws_cta
 int64_t amp_disc_launch_count(const amp_disc_t *d, int64_t M) {
     if (!d || M <= 0) return 0;
     if (d->wide) return 2 * ((M + d->xs_rows - 1) / d->xs_rows);
+    if (d->small_ok && (M + BM - 1) / BM <= sm_count() / 2) return 1;  // the two-CTA-per-tile kernel
     return M <= d->xs_rows ? 2 : 1;
 }
 
@@ -1037,6 +1436,35 @@ static int style_reward_impl(amp_disc_t *d, const float *x, int64_t x_stride, co
     AMP_REQUIRE(M <= ((int64_t)1 << 31) - BM, "amp_disc_style_reward: %lld rows exceed the 2^31 row limit of one call", (long long)M);
     cudaStream_t st = as_stream(stream);
     const int sms = sm_count();
+    // Small batches (at most one row tile per two SMs): ONE launch of the two-CTA-per-tile kernel, cast folded in
+    if (d->small_ok && (M + BM - 1) / BM <= sms / 2) {
+        SmallParams sp{};
+        sp.M = M;
+        sp.x = x;
+        sp.x_stride = x_stride;
+        sp.row_index = row_index;
+        sp.capacity = capacity;
+        sp.flags = flags;
+        sp.mean = d->mean;
+        sp.denom = d->denom;
+        sp.in_features = d->in_features;
+        sp.kb1 = d->Kp / BK;
+        sp.ksteps1_last = (d->in_features + 2 - BK * (sp.kb1 - 1) + UMMA_K - 1) / UMMA_K;
+        sp.x_vec = ((x_stride % 2 == 0) && ((reinterpret_cast<uintptr_t>(x) & 7u) == 0)) ? 1 : 0;
+        sp.n1_tiles = d->h1 / BN;
+        sp.n2_tiles = d->h2 / BN;
+        sp.b2 = d->b2;
+        sp.w3 = d->w3;
+        sp.b3 = d->b3;
+        sp.scale = reward_scale;
+        sp.reward = reward;
+        sp.logits = logits;
+        const int m_tiles = (int)((M + BM - 1) / BM);
+        disc_small_kernel<<<2 * m_tiles, SMALL_THREADS, small_smem_bytes(sp.kb1), st>>>(d->tmap_w1, d->tmap_h_load, d->tmap_h_store,
+                                                                                        d->tmap_w2, sp);
+        AMP_CUDA_TRY(cudaGetLastError());
+        return AMP_OK;
+    }
     // Gathered batches (row_index) always take the cast-kernel path, in chunks of the scratch: random 664-byte rows out of a
     // multi-GB memory are pure DRAM latency, which six converter warps per SM cannot cover (measured 1 M sampled rows x 166:
     // 1.99 ms in-kernel against 1.43 ms with the gather done by the cast kernel at full-chip parallelism)

@@ -237,8 +237,9 @@ AMP_API int amp_disc_destroy(amp_disc_t *d);
 /* Rows one persistent wave covers (one 128-row tile per SM); 0 for a NULL handle.  max_rows of amp_disc_create is a hint
  * only: the scratch (two 128-row x_hat and h1 slots per SM, L2-resident) does not scale with the batch. */
 AMP_API int64_t amp_disc_chunk_rows(const amp_disc_t *d);
-/* Kernel launches amp_disc_style_reward issues for a batch of M rows: 1 (scaler + bf16 cast + both layers + reward in one
- * persistent tcgen05 kernel), 0 for M == 0. */
+/* Kernel launches amp_disc_style_reward issues for a batch of M rows (0 for M == 0): 1 for at most 9472 rows (two-CTA-per-tile
+ * kernel) and for more than eight row tiles per SM (persistent kernel with in-kernel scaler + cast), else 2 (cast kernel + fused
+ * kernel; per chunk of max_rows rows for inputs wider than 254 columns). */
 AMP_API int64_t amp_disc_launch_count(const amp_disc_t *d, int64_t M);
 /* Refresh the staged bf16 weights / fp32 biases / scaler statistics from the fp32 masters the trainer owns
  * (device pointers; W row-major (out,in) as torch.nn.Linear stores them; mean/var are the scaler's float64 buffers). */

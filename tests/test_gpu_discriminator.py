@@ -139,7 +139,8 @@ def test_one_launch_for_large_batches_and_many_tiles_per_cta():
         assert torch.equal(disc.style_reward(x[lo : lo + 300]), whole[lo : lo + 300])
     # one launch beyond eight persistent waves; cast + fused kernel below (too little to hide the in-kernel conversion under)
     assert disc.launch_count(M) == 1 and disc.launch_count(8 * disc.chunk_rows + 1) == 1
-    assert disc.launch_count(8 * disc.chunk_rows) == 2 and disc.launch_count(100) == 2 and disc.launch_count(0) == 0
+    assert disc.launch_count(8 * disc.chunk_rows) == 2 and disc.launch_count(disc.chunk_rows) == 2 and disc.launch_count(0) == 0
+    assert disc.launch_count(100) == 1 and disc.launch_count(disc.chunk_rows // 2) == 1  # the two-CTA-per-tile kernel
     # the two paths give the same bits (same scaler arithmetic, same K order per row)
     mid = 8 * disc.chunk_rows
     assert torch.equal(disc.style_reward(x[:mid]), whole[:mid])
@@ -232,3 +233,30 @@ def test_random_batch_sizes_all_paths_agree_bitwise_and_are_deterministic():
         assert torch.equal(got, whole[lo : lo + M]), (M, lo)
     pieces = torch.cat([disc.style_reward(x[i : i + 100_000]) for i in range(0, 420_000, 100_000)])
     assert torch.equal(pieces, whole)
+
+
+@pytest.mark.parametrize("in_features", [166, 162, 83, 63])
+def test_small_batch_cluster_kernel_is_bit_identical_to_the_other_paths(in_features, monkeypatch):
+    """Batches of at most one row tile per two SMs run ONE launch of the two-CTA-per-tile kernel (cast folded in, layer-1 / layer-2
+    N tiles split over the pair, the layer-3 accumulation chain handed from CTA 0 to CTA 1 through distributed shared memory).
+    Same bits as the cast-kernel + fused-kernel path (AMP_B200_DISC_SMALL=0), also for gathered rows, ragged tiles and a strided view."""
+    import humanoid_amp_b200 as amp
+
+    disc, ora, inputs = build(in_features, 5.0)
+    monkeypatch.setenv("AMP_B200_DISC_SMALL", "0")
+    ref = amp.AmpDiscriminator(in_features, device="cuda:0", max_rows=65536)
+    ref.load(ora.weights, ora.biases, ora.running_mean, ora.running_variance)
+    x = inputs(9472, 21).cuda()
+    for M in (1, 127, 128, 129, 4096, 9472):
+        assert disc.launch_count(M) == 1 and ref.launch_count(M) == 2
+        got, got_logits = disc.style_reward(x[:M], return_logits=True)
+        want, want_logits = ref.style_reward(x[:M], return_logits=True)
+        assert torch.equal(got, want) and torch.equal(got_logits, want_logits), M
+    assert disc.launch_count(9473) == 2  # one tile more: back on the cast + fused path
+    idx = torch.randint(0, 9472, (5000,), device="cuda", generator=torch.Generator(device="cuda").manual_seed(2))
+    assert torch.equal(disc.style_reward_sampled(x, idx), ref.style_reward(x)[idx])
+    wide = torch.zeros(3000, in_features + 7, device="cuda")
+    wide[:, :in_features] = x[:3000]
+    assert torch.equal(disc.style_reward(wide[:, :in_features]), ref.style_reward(x[:3000]))
+    want = ora.logits(x[:4096].cpu())
+    assert (disc.style_reward(x[:4096], return_logits=True)[1].cpu() - want).abs().max() <= 1e-2 * max(1.0, float(want.abs().max()))
