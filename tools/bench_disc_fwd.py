@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--pair", action="store_true", help="(default) CTA-pair kernel")
     ap.add_argument("--single", action="store_true", help="single-CTA kernel")
     ap.add_argument("--graph", action="store_true", help="replay each call as a CUDA graph (small batches)")
+    ap.add_argument("--warm", action="store_true", help="do NOT flush L2 between calls of a small batch (weights / rows stay resident)")
     args = ap.parse_args()
     os.environ["AMP_B200_DISC_PAIR"] = "0" if args.single else "1"
     args.pair = not args.single
@@ -45,7 +46,7 @@ def main():
             for _ in range(args.warmup):
                 call()
             torch.cuda.synchronize()
-            small = M * inf * 4 < (64 << 20)
+            small = M * inf * 4 < (64 << 20) and not args.warm
             g = amp.capture_step(call, dev) if args.graph else None
             evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.iters)]
             for a, c in evs:
