@@ -466,8 +466,8 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                     return p.x + grow * p.x_stride + c;
                 };
                 auto emit = [&](int r, float2 x, bool live) {
-                    const float a = fminf(fmaxf(__fmul_rn(__fsub_rn(x.x, mu.x), rc.x), -5.0f), 5.0f);
-                    const float b = fminf(fmaxf(__fmul_rn(__fsub_rn(x.y, mu.y), rc.y), -5.0f), 5.0f);
+                    const float a = clamp_nan(__fmul_rn(__fsub_rn(x.x, mu.x), rc.x), -5.0f, 5.0f);
+                    const float b = clamp_nan(__fmul_rn(__fsub_rn(x.y, mu.y), rc.y), -5.0f, 5.0f);
                     reinterpret_cast<__nv_bfloat162 *>(dst + (size_t)r * p.Kp)[lane + 32 * kb] =
                         live ? __floats2bfloat162_rn(a, b) : __floats2bfloat162_rn(0.0f, 0.0f);
                 };
@@ -573,14 +573,15 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                         if (p.prof_mode & 1) { ++store_it; continue; }
 #endif
                         // the accumulator already holds x W1^T + b1 (the bias rides in two padding columns): round, then ReLU
-                        // on the packed pair (rounding is monotonic and keeps the sign, so max(round(x), 0) == round(max(x, 0)))
+                        // on the packed pair (rounding is monotonic and keeps the sign, so max(round(x), 0) == round(max(x, 0)));
+                        // the NaN-propagating max: torch's relu(NaN) is NaN
                         const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.0f, 0.0f);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {  // 16-byte chunk j of this thread's 64-byte slab row
-                            const __nv_bfloat162 p0 = __hmax2(__floats2bfloat162_rn(__uint_as_float(cur[8 * j + 0]), __uint_as_float(cur[8 * j + 1])), zero2);
-                            const __nv_bfloat162 p1 = __hmax2(__floats2bfloat162_rn(__uint_as_float(cur[8 * j + 2]), __uint_as_float(cur[8 * j + 3])), zero2);
-                            const __nv_bfloat162 p2 = __hmax2(__floats2bfloat162_rn(__uint_as_float(cur[8 * j + 4]), __uint_as_float(cur[8 * j + 5])), zero2);
-                            const __nv_bfloat162 p3 = __hmax2(__floats2bfloat162_rn(__uint_as_float(cur[8 * j + 6]), __uint_as_float(cur[8 * j + 7])), zero2);
+                            const __nv_bfloat162 p0 = __hmax2_nan(__floats2bfloat162_rn(__uint_as_float(cur[8 * j + 0]), __uint_as_float(cur[8 * j + 1])), zero2);
+                            const __nv_bfloat162 p1 = __hmax2_nan(__floats2bfloat162_rn(__uint_as_float(cur[8 * j + 2]), __uint_as_float(cur[8 * j + 3])), zero2);
+                            const __nv_bfloat162 p2 = __hmax2_nan(__floats2bfloat162_rn(__uint_as_float(cur[8 * j + 4]), __uint_as_float(cur[8 * j + 5])), zero2);
+                            const __nv_bfloat162 p3 = __hmax2_nan(__floats2bfloat162_rn(__uint_as_float(cur[8 * j + 6]), __uint_as_float(cur[8 * j + 7])), zero2);
                             // SWIZZLE_64B: 16-byte chunk index XOR address bits [7,9) = (row >> 1) & 3 (rows are 64 bytes)
                             const int chunk = j ^ ((lane >> 1) & 3);
                             st_shared_v4(slab + (uint32_t)(lane * 64 + chunk * 16), *reinterpret_cast<const uint32_t *>(&p0),
@@ -661,10 +662,10 @@ disc_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 const int e = 16 * half + 4 * j;
-                                dot[0] = fmaf(fmaxf(__uint_as_float(cur[e + 0]) + bb[j].x, 0.0f), ww[j].x, dot[0]);
-                                dot[1] = fmaf(fmaxf(__uint_as_float(cur[e + 1]) + bb[j].y, 0.0f), ww[j].y, dot[1]);
-                                dot[2] = fmaf(fmaxf(__uint_as_float(cur[e + 2]) + bb[j].z, 0.0f), ww[j].z, dot[2]);
-                                dot[3] = fmaf(fmaxf(__uint_as_float(cur[e + 3]) + bb[j].w, 0.0f), ww[j].w, dot[3]);
+                                dot[0] = fmaf(max_nan(__uint_as_float(cur[e + 0]) + bb[j].x, 0.0f), ww[j].x, dot[0]);
+                                dot[1] = fmaf(max_nan(__uint_as_float(cur[e + 1]) + bb[j].y, 0.0f), ww[j].y, dot[1]);
+                                dot[2] = fmaf(max_nan(__uint_as_float(cur[e + 2]) + bb[j].z, 0.0f), ww[j].z, dot[2]);
+                                dot[3] = fmaf(max_nan(__uint_as_float(cur[e + 3]) + bb[j].w, 0.0f), ww[j].w, dot[3]);
                             }
                         }
                     }
@@ -862,8 +863,8 @@ disc_small_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_cons
 #pragma unroll
                 for (int kb = 0; kb < KB; ++kb) {
                     if (kb >= p.kb1) continue;
-                    const float a = fminf(fmaxf(__fmul_rn(__fsub_rn(v[q][kb].x, mu[kb].x), rc[kb].x), -5.0f), 5.0f);
-                    const float b = fminf(fmaxf(__fmul_rn(__fsub_rn(v[q][kb].y, mu[kb].y), rc[kb].y), -5.0f), 5.0f);
+                    const float a = clamp_nan(__fmul_rn(__fsub_rn(v[q][kb].x, mu[kb].x), rc[kb].x), -5.0f, 5.0f);
+                    const float b = clamp_nan(__fmul_rn(__fsub_rn(v[q][kb].y, mu[kb].y), rc[kb].y), -5.0f, 5.0f);
                     const __nv_bfloat162 o = live ? __floats2bfloat162_rn(a, b) : __floats2bfloat162_rn(0.0f, 0.0f);
                     const uint32_t addr = smem_a1 + (uint32_t)(kb * A_STAGE_BYTES + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4) + ((lane & 3) << 2));
                     asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(*reinterpret_cast<const uint32_t *>(&o)) : "memory");
@@ -1008,10 +1009,10 @@ disc_small_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_cons
                     const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.0f, 0.0f);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const __nv_bfloat162 p0 = __hmax2(__floats2bfloat162_rn(__uint_as_float(cur[8 * q + 0]), __uint_as_float(cur[8 * q + 1])), zero2);
-                        const __nv_bfloat162 p1 = __hmax2(__floats2bfloat162_rn(__uint_as_float(cur[8 * q + 2]), __uint_as_float(cur[8 * q + 3])), zero2);
-                        const __nv_bfloat162 p2 = __hmax2(__floats2bfloat162_rn(__uint_as_float(cur[8 * q + 4]), __uint_as_float(cur[8 * q + 5])), zero2);
-                        const __nv_bfloat162 p3 = __hmax2(__floats2bfloat162_rn(__uint_as_float(cur[8 * q + 6]), __uint_as_float(cur[8 * q + 7])), zero2);
+                        const __nv_bfloat162 p0 = __hmax2_nan(__floats2bfloat162_rn(__uint_as_float(cur[8 * q + 0]), __uint_as_float(cur[8 * q + 1])), zero2);
+                        const __nv_bfloat162 p1 = __hmax2_nan(__floats2bfloat162_rn(__uint_as_float(cur[8 * q + 2]), __uint_as_float(cur[8 * q + 3])), zero2);
+                        const __nv_bfloat162 p2 = __hmax2_nan(__floats2bfloat162_rn(__uint_as_float(cur[8 * q + 4]), __uint_as_float(cur[8 * q + 5])), zero2);
+                        const __nv_bfloat162 p3 = __hmax2_nan(__floats2bfloat162_rn(__uint_as_float(cur[8 * q + 6]), __uint_as_float(cur[8 * q + 7])), zero2);
                         const int chunk = q ^ ((lane >> 1) & 3);  // SWIZZLE_64B
                         st_shared_v4(slab + (uint32_t)(lane * 64 + chunk * 16), *reinterpret_cast<const uint32_t *>(&p0),
                                      *reinterpret_cast<const uint32_t *>(&p1), *reinterpret_cast<const uint32_t *>(&p2),
@@ -1067,10 +1068,10 @@ disc_small_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_cons
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             const int e = 16 * half + 4 * q;
-                            dot[0] = fmaf(fmaxf(__uint_as_float(cur[e + 0]) + bb[q].x, 0.0f), ww[q].x, dot[0]);
-                            dot[1] = fmaf(fmaxf(__uint_as_float(cur[e + 1]) + bb[q].y, 0.0f), ww[q].y, dot[1]);
-                            dot[2] = fmaf(fmaxf(__uint_as_float(cur[e + 2]) + bb[q].z, 0.0f), ww[q].z, dot[2]);
-                            dot[3] = fmaf(fmaxf(__uint_as_float(cur[e + 3]) + bb[q].w, 0.0f), ww[q].w, dot[3]);
+                            dot[0] = fmaf(max_nan(__uint_as_float(cur[e + 0]) + bb[q].x, 0.0f), ww[q].x, dot[0]);
+                            dot[1] = fmaf(max_nan(__uint_as_float(cur[e + 1]) + bb[q].y, 0.0f), ww[q].y, dot[1]);
+                            dot[2] = fmaf(max_nan(__uint_as_float(cur[e + 2]) + bb[q].z, 0.0f), ww[q].z, dot[2]);
+                            dot[3] = fmaf(max_nan(__uint_as_float(cur[e + 3]) + bb[q].w, 0.0f), ww[q].w, dot[3]);
                         }
                     }
                 }
@@ -1167,8 +1168,8 @@ __global__ void __launch_bounds__(256) normalise_cast_kernel(const float *__rest
         __nv_bfloat162 *orow = reinterpret_cast<__nv_bfloat162 *>(out + r * Kp);
 #pragma unroll
         for (int j = 0; j < NB; ++j) {
-            const float a = fminf(fmaxf(__fmul_rn(__fsub_rn(v[j].x, mu[j].x), rc[j].x), -5.0f), 5.0f);
-            const float b = fminf(fmaxf(__fmul_rn(__fsub_rn(v[j].y, mu[j].y), rc[j].y), -5.0f), 5.0f);
+            const float a = clamp_nan(__fmul_rn(__fsub_rn(v[j].x, mu[j].x), rc[j].x), -5.0f, 5.0f);
+            const float b = clamp_nan(__fmul_rn(__fsub_rn(v[j].y, mu[j].y), rc[j].y), -5.0f, 5.0f);
             orow[lane + 32 * j] = __floats2bfloat162_rn(a, b);
         }
     };

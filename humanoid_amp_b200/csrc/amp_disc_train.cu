@@ -43,6 +43,7 @@
 #include <new>
 
 #include "amp_internal.h"
+#include "amp_math.cuh"
 #include "amp_tc.cuh"
 
 namespace amp {
@@ -280,8 +281,8 @@ train_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const float4 b = __ldg(bias4 + j);
-                            const float h0 = fmaxf(__uint_as_float(cur[4 * j]) + b.x, 0.0f), h1 = fmaxf(__uint_as_float(cur[4 * j + 1]) + b.y, 0.0f);
-                            const float h2 = fmaxf(__uint_as_float(cur[4 * j + 2]) + b.z, 0.0f), h3 = fmaxf(__uint_as_float(cur[4 * j + 3]) + b.w, 0.0f);
+                            const float h0 = max_nan(__uint_as_float(cur[4 * j]) + b.x, 0.0f), h1 = max_nan(__uint_as_float(cur[4 * j + 1]) + b.y, 0.0f);
+                            const float h2 = max_nan(__uint_as_float(cur[4 * j + 2]) + b.z, 0.0f), h3 = max_nan(__uint_as_float(cur[4 * j + 3]) + b.w, 0.0f);
                             o[2 * j] = pack_bf16(h0, h1);
                             o[2 * j + 1] = pack_bf16(h2, h3);
                             if (with_dot) {
@@ -394,7 +395,7 @@ constexpr int REPL = 8;
 // scalar accumulators at the head of the fp32 workspace (zeroed at the start of every step)
 enum Acc { ACC_BCE_CAT = 0, ACC_BCE_MOTION, ACC_W3_SQ, ACC_GP_SQ, ACC_W_SQ, ACC_GB3, ACC_COUNT = 8 };
 
-__device__ __forceinline__ float softplus_f(float x) { return fmaxf(x, 0.0f) + log1pf(__expf(-fabsf(x))); }
+__device__ __forceinline__ float softplus_f(float x) { return max_nan(x, 0.0f) + log1pf(__expf(-fabsf(x))); }
 
 // After the second layer: logits, BCE terms, dL/dd, and everything that hangs off it row by row.
 //   A block takes 32 rows: the a2 tile (32 x h2 bf16) is read ONCE into shared memory; phase A: one lane per row ->
@@ -518,8 +519,8 @@ __global__ void __launch_bounds__(256) stage_cast_kernel(const float *__restrict
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             if (rb + u >= r1) break;
-            const float v0 = live[0] ? fminf(fmaxf(__fmul_rn(__fsub_rn(x0[u], mu[0]), rc[0]), -5.0f), 5.0f) : pad0;
-            const float v1 = live[1] ? fminf(fmaxf(__fmul_rn(__fsub_rn(x1[u], mu[1]), rc[1]), -5.0f), 5.0f) : pad1;
+            const float v0 = live[0] ? clamp_nan(__fmul_rn(__fsub_rn(x0[u], mu[0]), rc[0]), -5.0f, 5.0f) : pad0;
+            const float v1 = live[1] ? clamp_nan(__fmul_rn(__fsub_rn(x1[u], mu[1]), rc[1]), -5.0f, 5.0f) : pad1;
             *reinterpret_cast<uint32_t *>(out + (long long)(rb + u) * Kp + c) = pack_bf16(v0, v1);
         }
     }

@@ -172,11 +172,25 @@ __device__ __forceinline__ void tangent_normal(float4 q, float tn[6]) {
     tn[5] = __fadd_rn(1.0f, __fsub_rn(-x2, y2));
 }
 
+// ---- torch.clamp(x, lo, hi) / torch.maximum(x, c): NaN propagates (fminf / fmaxf would return the bound) -------------------
+// (max.NaN / min.NaN are single FMNMX instructions)
+__device__ __forceinline__ float max_nan(float x, float c) {
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(c));
+    return r;
+}
+__device__ __forceinline__ float min_nan(float x, float c) {
+    float r;
+    asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(c));
+    return r;
+}
+__device__ __forceinline__ float clamp_nan(float x, float lo, float hi) { return min_nan(max_nan(x, lo), hi); }
+
 // ---- skrl AMP style reward : -log(max(1 - 1/(1+exp(-d)), 1e-4)) * scale ------------------------------------------------
 __device__ __forceinline__ float style_reward(float logit, float scale) {
     const float e = expf(-logit);
     const float p = __fsub_rn(1.0f, __fdiv_rn(1.0f, __fadd_rn(1.0f, e)));
-    return __fmul_rn(-logf(fmaxf(p, 0.0001f)), scale);
+    return __fmul_rn(-logf(max_nan(p, 0.0001f)), scale);  // torch.maximum: a NaN logit gives a NaN reward, as in the reference
 }
 
 }  // namespace amp

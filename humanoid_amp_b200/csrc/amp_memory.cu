@@ -5,6 +5,7 @@
 #include <cmath>
 
 #include "amp_internal.h"
+#include "amp_math.cuh"
 
 namespace amp {
 
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(256) scaler_apply_kernel(const float *__restri
                 if (r0 + j >= M) continue;
                 float *f = reinterpret_cast<float *>(&v[j]);
 #pragma unroll
-                for (int e = 0; e < VEC; ++e) f[e] = fminf(fmaxf(__fdiv_rn(__fsub_rn(f[e], mf[e]), df[e]), -clip), clip);
+                for (int e = 0; e < VEC; ++e) f[e] = clamp_nan(__fdiv_rn(__fsub_rn(f[e], mf[e]), df[e]), -clip, clip);
                 __stcs(reinterpret_cast<V *>(out + (r0 + j) * out_stride) + c, v[j]);
             }
         }

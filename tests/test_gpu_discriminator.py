@@ -260,3 +260,26 @@ def test_small_batch_cluster_kernel_is_bit_identical_to_the_other_paths(in_featu
     assert torch.equal(disc.style_reward(wide[:, :in_features]), ref.style_reward(x[:3000]))
     want = ora.logits(x[:4096].cpu())
     assert (disc.style_reward(x[:4096], return_logits=True)[1].cpu() - want).abs().max() <= 1e-2 * max(1.0, float(want.abs().max()))
+
+
+@pytest.mark.parametrize("M", [300, 40_000, 200_000])
+def test_nan_rows_propagate_like_torch_and_do_not_touch_their_neighbours(M):
+    """torch.clamp and torch.maximum propagate NaN: a NaN in an AMP row gives a NaN logit and a NaN reward in the reference.
+    Same here on every path (small-batch kernel, cast + fused kernel, in-kernel conversion), and the other rows keep their bits."""
+    from humanoid_amp_b200 import style_reward_from_logits
+
+    disc, ora, inputs = build(166, 5.0)
+    x = inputs(M, 9).cuda()
+    clean, clean_logits = disc.style_reward(x, return_logits=True)
+    bad = sorted({0, 1, M // 2, M - 1})
+    x2 = x.clone()
+    for i, r in enumerate(bad):
+        x2[r, (37 * i) % 166] = float("nan")
+    got, logits = disc.style_reward(x2, return_logits=True)
+    mask = torch.zeros(M, dtype=torch.bool, device="cuda")
+    mask[bad] = True
+    assert bool(torch.isnan(got[mask]).all()) and bool(torch.isnan(logits[mask]).all())
+    assert torch.equal(got[~mask], clean[~mask]) and torch.equal(logits[~mask], clean_logits[~mask])
+    want = ora.style_reward(x2[:300].cpu())
+    assert torch.equal(torch.isnan(want.view(-1)), torch.isnan(got[:300].cpu().view(-1)))
+    assert bool(torch.isnan(style_reward_from_logits(torch.tensor([float("nan"), 0.0], device="cuda"), 2.0)[0]))
