@@ -123,3 +123,47 @@ def test_command_line_writes_a_clip_the_motion_loader_reads(tmp_path):
     env = amp.AmpEnvPath(amp.AmpEnvCfg(motion_file=out, num_envs=8, num_amp_observations=2, robot=amp.G1), "cuda:0", motion_loader=loader)
     rows = env.collect_reference_motions(64)
     assert rows.shape == (64, 2 * 83) and bool(torch.isfinite(rows).all())
+
+
+def test_random_urdf_tree_with_oblique_axes_and_rotated_origins(tmp_path):
+    """The shipped G1 URDF only has axis-aligned joints and two rotated origins.  A random tree (oblique unit axes, rpy origins,
+    fixed and continuous joints, branches) exercises the general Rodrigues / rpy paths of the kernel against the oracle."""
+    from humanoid_amp_b200 import dataset
+    from oracle import dataset_oracle as do
+
+    rng = np.random.default_rng(11)
+    n_rev, links, lines = 9, ["base"], ['<?xml version="1.0"?>', '<robot name="rnd">', '  <link name="base"/>']
+    joint_names, bodies = [], ["base"]
+    for j in range(14):
+        parent = links[int(rng.integers(0, len(links)))]
+        child = f"l{j}"
+        kind = "fixed" if j % 3 == 2 else ("continuous" if j % 5 == 0 else "revolute")
+        xyz = " ".join(f"{v:.4f}" for v in rng.uniform(-0.3, 0.3, 3))
+        rpy = " ".join(f"{v:.4f}" for v in rng.uniform(-1.5, 1.5, 3))
+        axis = rng.normal(size=3)
+        lines += [f'  <link name="{child}"/>', f'  <joint name="j{j}" type="{kind}">', f'    <origin xyz="{xyz}" rpy="{rpy}"/>',
+                  f'    <parent link="{parent}"/>', f'    <child link="{child}"/>']  # fmt: skip
+        if kind != "fixed":
+            lines.append(f'    <axis xyz="{axis[0]:.5f} {axis[1]:.5f} {axis[2]:.5f}"/>')  # NOT normalised: both sides normalise
+            joint_names.append(f"j{j}")
+        lines.append("  </joint>")
+        links.append(child)
+        bodies.append(child)
+    lines.append("</robot>")
+    urdf = tmp_path / "rnd.urdf"
+    urdf.write_text("\n".join(lines))
+    D = len(joint_names)
+    assert D >= n_rev - 2
+    n_in = 60
+    t = np.linspace(0, 2, n_in)
+    rows = np.zeros((n_in, 7 + D))
+    rows[:, 0:3] = rng.normal(size=(1, 3)) + 0.3 * np.sin(t)[:, None]
+    q = rng.normal(size=(n_in, 4)) * 0.05 + np.array([0.3, -0.5, 0.2, 0.8])
+    rows[:, 3:7] = q / np.linalg.norm(q, axis=1, keepdims=True)
+    rows[:, 7:] = 1.5 * np.sin(t[:, None] * rng.uniform(0.5, 3, D)[None, :] + rng.uniform(0, 6, D)[None, :])
+    rows = rows.astype(np.float32)
+    got = dataset.convert_rows(rows, dataset.UrdfTree(str(urdf), joint_names), body_names=bodies, joint_names=joint_names, device="cuda:0")
+    want = do.convert(rows, do.load_urdf_tree(str(urdf), joint_names), joint_names=joint_names, body_names=bodies)
+    assert np.array_equal(got["dof_positions"], want["dof_positions"])
+    assert close32(got["body_positions"], want["body_positions"]) and close32(got["body_rotations"], want["body_rotations"])
+    assert np.abs(got["body_linear_velocities"] - want["body_linear_velocities"]).max() <= 2e-5
