@@ -813,18 +813,17 @@ disc_small_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_cons
     // round is a DRAM round trip on the critical path of a kernel that is nothing but latency).
     {
         constexpr int RIF = 7, KB = 3;  // small_ok: kb1 <= 3
-        float2 mu[KB], rc[KB];
-        bool in0[KB], in1[KB];
+        float2 mu[KB], rc[KB];  // rc holds the denominators until the first round of row loads is in flight (issue is in order:
+        bool in0[KB], in1[KB];  // taking the reciprocals here would hold the row loads back by one DRAM round trip)
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb) {
             const int c = 2 * (lane + 32 * kb);
             in0[kb] = kb < p.kb1 && c < p.in_features;
             in1[kb] = kb < p.kb1 && c + 1 < p.in_features;
             mu[kb] = make_float2(in0[kb] ? __ldg(p.mean + c) : 0.0f, in1[kb] ? __ldg(p.mean + c + 1) : 0.0f);
-            rc[kb] = make_float2(in0[kb] ? __frcp_rn(__ldg(p.denom + c)) : 0.0f, in1[kb] ? __frcp_rn(__ldg(p.denom + c + 1)) : 0.0f);
-            if (!in0[kb] && c < p.in_features + 2) { mu[kb].x = -1.0f; rc[kb].x = 1.0f; }  // bias columns: (0 - (-1)) * 1 = 1
-            if (!in1[kb] && c + 1 < p.in_features + 2) { mu[kb].y = -1.0f; rc[kb].y = 1.0f; }
+            rc[kb] = make_float2(in0[kb] ? __ldg(p.denom + c) : 0.0f, in1[kb] ? __ldg(p.denom + c + 1) : 0.0f);
         }
+        bool have_rcp = false;
 #pragma unroll 1
         for (int r0 = warp; r0 < BM; r0 += (SMALL_THREADS / 32) * RIF) {
             float2 v[RIF][KB];
@@ -855,6 +854,16 @@ disc_small_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_cons
                     }
                 }
             }
+            if (!have_rcp) {
+                have_rcp = true;
+#pragma unroll
+                for (int kb = 0; kb < KB; ++kb) {
+                    const int c = 2 * (lane + 32 * kb);
+                    rc[kb] = make_float2(in0[kb] ? __frcp_rn(rc[kb].x) : 0.0f, in1[kb] ? __frcp_rn(rc[kb].y) : 0.0f);
+                    if (!in0[kb] && c < p.in_features + 2) { mu[kb].x = -1.0f; rc[kb].x = 1.0f; }  // bias columns: (0 - (-1)) * 1 = 1
+                    if (!in1[kb] && c + 1 < p.in_features + 2) { mu[kb].y = -1.0f; rc[kb].y = 1.0f; }
+                }
+            }
 #pragma unroll
             for (int q = 0; q < RIF; ++q) {
                 const int r = r0 + q * (SMALL_THREADS / 32);
@@ -874,7 +883,7 @@ disc_small_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_cons
         fence_proxy_async_smem();  // generic-proxy shared writes -> visible to the tensor core (async proxy)
     }
     tcgen05_fence_before();
-    cluster_sync_all();  // barriers initialised in both CTAs, TMEM allocated, x_hat in place
+    __syncthreads();  // barriers initialised, TMEM allocated, x_hat in place (the peer is first touched after cluster barrier #1)
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
