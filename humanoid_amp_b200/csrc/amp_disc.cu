@@ -1354,7 +1354,9 @@ int amp_disc_create(int32_t in_features, int32_t h1, int32_t h2, int64_t max_row
         const char *small_env = getenv("AMP_B200_DISC_SMALL");  // 0 disables the small-batch kernel (tests compare the paths)
         d->small_ok = h1 == 4 * BN && h2 == 2 * BN && d->Kp / BK <= 3 && !(small_env && small_env[0] == '0');
         if (d->small_ok) {
-            e = cudaFuncSetAttribute(disc_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem_bytes(d->Kp / BK));
+            // the attribute belongs to the function, not to the handle: always the largest footprint (kb1 = 3), or a later handle
+            // with a narrower input would lower the limit under an earlier one
+            e = cudaFuncSetAttribute(disc_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem_bytes(3));
             if (e != cudaSuccess) rc = cuda_fail(e, "cudaFuncSetAttribute(disc_small_kernel)");
         }
         e = cudaFuncSetAttribute(disc_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_smem_bytes(false));

@@ -283,3 +283,17 @@ def test_nan_rows_propagate_like_torch_and_do_not_touch_their_neighbours(M):
     want = ora.style_reward(x2[:300].cpu())
     assert torch.equal(torch.isnan(want.view(-1)), torch.isnan(got[:300].cpu().view(-1)))
     assert bool(torch.isnan(style_reward_from_logits(torch.tensor([float("nan"), 0.0], device="cuda"), 2.0)[0]))
+
+
+def test_handles_of_different_widths_coexist():
+    """Function attributes (dynamic shared-memory limits) are per kernel, not per handle: creating a narrow discriminator after a
+    wider one must not break the wider one's small-batch launches."""
+    wide, ora_w, inputs_w = build(166, 3.0)   # three K-blocks
+    narrow, ora_n, inputs_n = build(40, 3.0)  # one K-block, created later
+    xw, xn = inputs_w(2000, 1).cuda(), inputs_n(2000, 2).cuda()
+    for _ in range(2):
+        lw = wide.style_reward(xw, return_logits=True)[1].cpu()
+        ln = narrow.style_reward(xn, return_logits=True)[1].cpu()
+    want_w, want_n = ora_w.logits(xw.cpu()), ora_n.logits(xn.cpu())
+    assert (lw - want_w).abs().max() <= 1e-2 * max(1.0, float(want_w.abs().max()))
+    assert (ln - want_n).abs().max() <= 1e-2 * max(1.0, float(want_n.abs().max()))
