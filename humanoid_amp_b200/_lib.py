@@ -128,6 +128,7 @@ SIGNATURES = {
     "amp_disc_train_destroy": (C.c_int, [_P]),
     "amp_disc_train_stage": (C.c_int, [_P, _I32, _P, _I64, _I64, _P, _P, _P]),
     "amp_disc_train_step": (C.c_int, [_P] * 7 + [_I64, _F32, _F32, _F32, _F32] + [_P] * 9),
+    "amp_disc_train_step_exchange": (C.c_int, [_P] * 7 + [_I64, _F32, _F32, _F32, _F32] + [_P] * 10),
     "amp_dataset_scratch_bytes": (C.c_int64, [_I32, _I32, _I32]),
     "amp_dataset_interp_fk": (C.c_int, [C.POINTER(DatasetDesc), _P, _P, _P, _P, _P, _I64, _P]),
     "amp_dataset_velocities": (C.c_int, [_I32, _I32, _I32, C.c_double, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _P]),

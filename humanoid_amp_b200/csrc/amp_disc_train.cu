@@ -42,6 +42,7 @@
 #include <cstring>
 #include <new>
 
+#include "amp_bucket.cuh"
 #include "amp_internal.h"
 #include "amp_math.cuh"
 #include "amp_tc.cuh"
@@ -623,6 +624,234 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinalizeParams p) {
     }
 }
 
+// ---- finalize + gradient exchange in ONE kernel (second half) ------------------------------------
+// With more than one rank the six gradient tensors live side by side in the rank's gradient bucket (amp_bucket.cu) and what the
+// optimiser needs is their MEAN over the ranks (skrl Model.reduce_parameters, enabled by the reference at train.py:53-58,
+// 184-196).  finalize_kernel followed by the all-reduce kernel writes the local gradients to the bucket, reads them back and
+// pulls every peer's copy over NVLink (a round trip per load).  This kernel is the reduce-scatter / all-gather pair with the
+// split-K reduction as its first stage:
+//
+//   push       every rank evaluates quad q of its local gradients (the arithmetic of finalize_kernel, same order) and STORES it
+//              straight into the staging area of the rank that owns q (peer stores, fire and forget) -- the local bucket is not
+//              written, nothing is read back
+//   barrier A  "all my pushes are out" (last CTA of the rank -> one flag per peer); wait for every rank's flag
+//   reduce     the owner adds the W staged copies of its slice (local loads, fixed rank order -> the same bits on every rank,
+//              and the same bits as finalize + all-reduce), scales by 1/W and stores the result into every rank's bucket
+//   barrier B  as in the all-reduce kernels: the stream continues only when every peer's stores have been announced
+//
+// The quads of the exchanged range map to (tensor, element) through `seg`: the six tensors may sit in any order inside the
+// range as long as each starts on a quad (only the one-element dL/db3 is ragged, so it must come last).  All CTAs of the grid
+// must be resident at once (every CTA waits for flags that the peers' LAST CTAs send): the host sizes the grid from the
+// occupancy calculator.
+struct ExchangeParams {
+    bucket::Peers peers;
+    int rank, world;
+    long long hull;        // float offset of the exchanged range inside the bucket (multiple of 4)
+    long long count;       // floats in the range (all six tensors)
+    long long stage;       // float offset of the staging area from the bucket base
+    long long seg[6];      // range-relative float offset of gW1, gb1, gW2, gb2, gW3, gb3
+    bucket::Control *ctl;
+    volatile uint32_t *host_status;
+    long long spin_limit;
+    unsigned long long *timing;
+};
+
+// quad `i4 / 4` of the local gradients; i4 = range-relative float index of its first element (a multiple of 4)
+__device__ __forceinline__ float4 gradient_quad(const FinalizeParams &p, const ExchangeParams &x, long long i4) {
+    const long long n1 = (long long)p.h1 * p.in_features, n2 = (long long)p.h2 * p.h1;
+    const long long s1 = (long long)p.h1 * p.Kp, s2 = n2;
+    const float cw = 2.0f * p.loss_scale * p.c_wd;
+    float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    long long e = i4 - x.seg[0];
+    if (e >= 0 && e < n1) {  // dL/dW1: split-K slices (h1, Kp) -> torch layout (h1, in_features); a quad may cross a row end
+        int r = (int)e / p.in_features, c = (int)e - r * p.in_features;  // n1 <= 2048 * 1024: 32-bit arithmetic
+        if ((p.in_features & 1) == 0) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float2 g = make_float2(0.0f, 0.0f);
+                for (int s = 0; s < p.splits1; ++s) {
+                    const float2 t = *reinterpret_cast<const float2 *>(p.slices1 + s * s1 + (long long)r * p.Kp + c);
+                    g.x += t.x; g.y += t.y;
+                }
+                const float2 w = *reinterpret_cast<const float2 *>(p.W1 + e + 2 * h);
+                v[2 * h] = fmaf(cw, w.x, g.x);
+                v[2 * h + 1] = fmaf(cw, w.y, g.y);
+                c += 2;
+                if (c >= p.in_features) { c = 0; ++r; }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float g = 0.0f;
+                for (int s = 0; s < p.splits1; ++s) g += p.slices1[s * s1 + (long long)r * p.Kp + c];
+                v[j] = fmaf(cw, p.W1[e + j], g);
+                if (++c >= p.in_features) { c = 0; ++r; }
+            }
+        }
+        return make_float4(v[0], v[1], v[2], v[3]);
+    }
+    e = i4 - x.seg[2];
+    if (e >= 0 && e < n2) {  // dL/dW2
+        float4 g = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        for (int s = 0; s < p.splits2; ++s) {
+            const float4 t = *reinterpret_cast<const float4 *>(p.slices2 + s * s2 + e);
+            g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+        }
+        const float4 w = *reinterpret_cast<const float4 *>(p.W2 + e);
+        return make_float4(fmaf(cw, w.x, g.x), fmaf(cw, w.y, g.y), fmaf(cw, w.z, g.z), fmaf(cw, w.w, g.w));
+    }
+    e = i4 - x.seg[1];
+    if (e >= 0 && e < p.h1) {  // dL/db1
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float g = 0.0f;
+            if (p.Kp > p.in_features) {
+                for (int s = 0; s < p.splits1; ++s) g += p.slices1[s * s1 + (e + j) * p.Kp + p.in_features];
+            } else {
+#pragma unroll
+                for (int k = 0; k < REPL; ++k) g += p.ws_gb1[k * p.h1 + e + j];
+            }
+            v[j] = g;
+        }
+        return make_float4(v[0], v[1], v[2], v[3]);
+    }
+    e = i4 - x.seg[3];
+    if (e >= 0 && e < p.h2) {  // dL/db2
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float g = 0.0f;
+#pragma unroll
+            for (int k = 0; k < REPL; ++k) g += p.ws_gb2[k * p.h2 + e + j];
+            v[j] = g;
+        }
+        return make_float4(v[0], v[1], v[2], v[3]);
+    }
+    e = i4 - x.seg[4];
+    if (e >= 0 && e < p.h2) {  // dL/dw3
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float g = 0.0f;
+#pragma unroll
+            for (int k = 0; k < REPL; ++k) g += p.ws_gw3[k * p.h2 + e + j];
+            v[j] = fmaf(cw + 2.0f * p.loss_scale * p.c_reg, p.w3[e + j], g);
+        }
+        return make_float4(v[0], v[1], v[2], v[3]);
+    }
+    return make_float4(p.acc[ACC_GB3], 0.0f, 0.0f, 0.0f);  // dL/db3 (the ragged last quad)
+}
+
+template <int MAXW>
+__global__ void __launch_bounds__(256) finalize_exchange_kernel(FinalizeParams p, ExchangeParams x) {
+    using namespace amp::bucket;
+    __shared__ bool ok, last;
+    __shared__ uint32_t s_epoch;
+    const int rank = x.rank, world = x.world;
+    uint32_t *local_flags = x.peers.flags[rank];
+    unsigned long long t_start = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+    // the epoch is device state advanced by the last CTA of every call on this bucket (graph replays stay in step)
+    if (threadIdx.x == 0) s_epoch = *reinterpret_cast<volatile uint32_t *>(&x.ctl->epoch) + 1;
+    __syncthreads();
+    const uint32_t epoch = s_epoch;
+    const long long quads = (x.count + 3) / 4, per = (quads + world - 1) / world;
+    const long long stride = (long long)gridDim.x * blockDim.x, tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    // ---- push: local gradients -> the owners' staging (slot `rank` of the owner's W slots of `per` quads) ----
+    // No barrier in front: the peers stopped reading their staging before they passed barrier B of the previous call, and this
+    // rank passed that barrier before its stream reached this launch.
+    for (long long q = tid; q < quads; q += stride) {
+        const int owner = (int)q / (int)per;  // the range is a few million floats: 32-bit arithmetic
+        const float4 g = gradient_quad(p, x, 4 * q);
+        st_peer(reinterpret_cast<float4 *>(x.peers.data[owner] + x.stage) + (long long)rank * per + (q - owner * per), g);
+    }
+    if (tid == 0 && p.terms) {  // the loss terms are local (skrl logs them per rank)
+        const float bce_cat = p.acc[ACC_BCE_CAT] / (2.0f * (float)p.B), bce_motion = p.acc[ACC_BCE_MOTION] / (float)p.B;
+        const float reg = p.acc[ACC_W3_SQ], gp = p.acc[ACC_GP_SQ] / (float)p.B, wd = p.acc[ACC_W_SQ] + p.acc[ACC_W3_SQ];
+        p.terms[0] = bce_cat; p.terms[1] = bce_motion; p.terms[2] = reg; p.terms[3] = gp; p.terms[4] = wd;
+        p.terms[5] = p.loss_scale * (0.5f * (bce_cat + bce_motion) + p.c_reg * reg + p.c_gp * gp + p.c_wd * wd);
+    }
+    // ---- barrier A: the last CTA to finish its pushes announces; every CTA waits for all ranks ----
+    // ONE system-scope fence per CTA, by the thread that then signals: the CTA barrier orders every thread's stores before it and
+    // the fence is cumulative (the cooperative-groups grid barrier is built the same way).  A fence per thread -- 32 warps per SM
+    // each draining the SM's peer stores -- cost more than the exchange itself.
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        last = atomicAdd(&x.ctl->pushed, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last) {
+        if (threadIdx.x == 0) x.ctl->pushed = 0;  // every CTA has passed the counter
+        if (threadIdx.x < world) {
+            __threadfence_system();
+            st_release_sys(x.peers.flags[threadIdx.x] + rank, epoch);
+        }
+    }
+    float *bucket_local = x.peers.data[rank];
+    if (threadIdx.x == 0) {
+        ok = wait_all(local_flags, world, epoch, x.spin_limit);
+        if (!ok && blockIdx.x == 0) report_failure(x.ctl, x.host_status, 1u, bucket_local, x.hull, x.count);
+    }
+    __syncthreads();
+    if (ok && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t_a;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_a));
+        x.timing[0] = t_start;
+        x.timing[1] = t_a;
+    }
+    // ---- reduce the own slice (local loads) and publish the mean to every rank's bucket ----
+    const long long q0 = (long long)rank * per, q1 = min(quads, q0 + per);
+    const float inv = 1.0f / (float)world;
+    const float4 *staged = reinterpret_cast<const float4 *>(bucket_local + x.stage);
+    for (long long q = q0 + tid; ok && q < q1; q += stride) {
+        float4 v[MAXW];
+#pragma unroll
+        for (int r = 0; r < MAXW; ++r)
+            if (r < world) v[r] = ld_peer(staged + (long long)r * per + (q - q0));  // .cg: written by the peers, never in this L1
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < MAXW; ++r)  // fixed rank order, starting from zero: the all-reduce kernels' sum
+            if (r < world) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }
+        acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+        const int valid = (int)min(4LL, x.count - 4 * q);  // < 4 only in the ragged last quad: its other floats are not ours
+#pragma unroll
+        for (int r = 0; r < MAXW; ++r) {
+            if (r < world) {
+                float *dst = x.peers.data[r] + x.hull + 4 * q;
+                if (valid == 4) {
+                    st_peer(reinterpret_cast<float4 *>(dst), acc);
+                } else {
+                    const float a[4] = {acc.x, acc.y, acc.z, acc.w};
+                    for (int j = 0; j < valid; ++j) asm volatile("st.global.cg.f32 [%0], %1;" ::"l"(dst + j), "f"(a[j]) : "memory");
+                }
+            }
+        }
+    }
+    // ---- barrier B (amp_bucket.cu) ----
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        last = atomicAdd(&x.ctl->arrivals, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    if (threadIdx.x == 0) {
+        x.ctl->arrivals = 0;
+        x.ctl->epoch = epoch + 1;
+    }
+    if (threadIdx.x < world) {
+        __threadfence_system();
+        st_release_sys(x.peers.flags[threadIdx.x] + rank, epoch + 1);
+    }
+    if (threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        x.timing[2] = t;
+        if (ok && !wait_all(local_flags, world, epoch + 1, x.spin_limit)) report_failure(x.ctl, x.host_status, 2u, bucket_local, x.hull, x.count);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        x.timing[3] = t;
+    }
+}
+
 __global__ void sumsq_kernel(const float *__restrict__ x, int n, float *__restrict__ out) {
     float s = 0.0f;
     for (int i = threadIdx.x; i < n; i += blockDim.x) s = fmaf(x[i], x[i], s);
@@ -735,7 +964,9 @@ int amp_disc_train_create(int32_t in_features, int32_t h1, int32_t h2, int64_t m
         }
     }
     if ((size_t)32 * h2 * 2 > 48 * 1024) {  // head_kernel keeps a 32-row tile of a2 in shared memory
-        cudaError_t e = cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * h2 * 2);
+        // per function, not per handle: always the limit of the widest head create accepts (h2 = 2048), so that a narrower
+        // handle created later cannot lower it under a wider one
+        cudaError_t e = cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 2048 * 2);
         if (e != cudaSuccess) {
             amp_disc_train_destroy(t);
             return cuda_fail(e, "cudaFuncSetAttribute(head_kernel)");
@@ -762,11 +993,57 @@ int amp_disc_train_stage(amp_disc_train_t *t, int32_t source, const float *x, in
     return AMP_OK;
 }
 
-int amp_disc_train_step(amp_disc_train_t *t, const float *W1, const float *b1, const float *W2, const float *b2, const float *W3,
-                        const float *b3, int64_t batch_rows, float loss_scale, float logit_regularization_scale,
-                        float gradient_penalty_scale, float weight_decay_scale, float *gW1, float *gb1, float *gW2, float *gb2,
-                        float *gW3, float *gb3, float *terms, float *logits, void *stream) {
+}  // extern "C"
+
+// the exchanged range of a fused step: the six gradient tensors must tile one contiguous, quad-aligned range of the bucket
+static int plan_exchange(amp_disc_train_t *t, amp_bucket_t *bk, float *const g[6], ExchangeParams *x) {
+    const long long n[6] = {(long long)t->h1 * t->in_features, t->h1, (long long)t->h2 * t->h1, t->h2, t->h2, 1};
+    long long off[6];
+    int order[6] = {0, 1, 2, 3, 4, 5};
+    for (int k = 0; k < 6; ++k) {
+        off[k] = g[k] - bk->data;
+        AMP_REQUIRE(g[k] >= bk->data && off[k] + n[k] <= bk->floats, "amp_disc_train_step_exchange: gradient tensor %d is not inside the bucket", k);
+    }
+    std::sort(order, order + 6, [&](int a, int c) { return off[a] < off[c]; });
+    AMP_REQUIRE(off[order[0]] % 4 == 0, "amp_disc_train_step_exchange: the gradient range must start on a 16-byte boundary of the bucket");
+    for (int k = 0; k + 1 < 6; ++k)
+        AMP_REQUIRE(off[order[k]] + n[order[k]] == off[order[k + 1]],
+                    "amp_disc_train_step_exchange: the six gradient tensors must lie side by side in the bucket (dL/db3, the one ragged "
+                    "tensor, last)");
+    AMP_REQUIRE(order[5] == 5, "amp_disc_train_step_exchange: dL/db3 must be the last tensor of the range");
+    x->hull = off[order[0]];
+    x->count = off[5] + 1 - x->hull;
+    AMP_REQUIRE(x->count < (1LL << 31), "amp_disc_train_step_exchange: gradient range of %lld floats is too long (32-bit index arithmetic)", x->count);
+    for (int k = 0; k < 6; ++k) x->seg[k] = off[k] - x->hull;
+    const long long quads = (x->count + 3) / 4, per = (quads + bk->world - 1) / bk->world;
+    AMP_REQUIRE(bk->world == 1 || per * 4 * bk->world <= bk->stage_floats, "amp_disc_train_step_exchange: staging area too small");  // sized from the bucket
+    x->peers = bk->peers;
+    x->rank = bk->rank;
+    x->world = bk->world;
+    x->stage = bk->floats;
+    x->ctl = reinterpret_cast<bucket::Control *>(bk->flags + bucket::kMaxWorld);
+    x->host_status = bk->host_status_dev;
+    x->spin_limit = bk->spin_limit;
+    x->timing = bk->timing;
+    return AMP_OK;
+}
+
+static int train_step_impl(amp_disc_train_t *t, const float *W1, const float *b1, const float *W2, const float *b2, const float *W3,
+                           const float *b3, int64_t batch_rows, float loss_scale, float logit_regularization_scale,
+                           float gradient_penalty_scale, float weight_decay_scale, float *gW1, float *gb1, float *gW2, float *gb2,
+                           float *gW3, float *gb3, float *terms, float *logits, amp_bucket_t *bucket, void *stream) {
     AMP_REQUIRE(t && W1 && b1 && W2 && b2 && W3 && b3 && gW1 && gb1 && gW2 && gb2 && gW3 && gb3, "amp_disc_train_step: NULL argument");
+    ExchangeParams ex{};
+    const bool exchange = bucket && bucket->world > 1;
+    if (bucket) {  // the placement rules hold for a world of one too (same call, same errors on every world size)
+        AMP_REQUIRE(bucket->connected, "amp_disc_train_step_exchange: amp_bucket_connect has not been called");
+        AMP_REQUIRE(bucket->world <= 8, "amp_disc_train_step_exchange: at most 8 ranks (got %d)", bucket->world);
+        if (const uint32_t failed = *bucket->host_status)
+            return fail(AMP_ECUDA, "amp_disc_train_step_exchange: an earlier exchange on this bucket timed out waiting for a peer (status bits 0x%x)",
+                        failed & 0x7fffffffu);
+        float *const g6[6] = {gW1, gb1, gW2, gb2, gW3, gb3};
+        if (int rc = plan_exchange(t, bucket, g6, &ex)) return rc;
+    }
     AMP_REQUIRE(batch_rows >= 1 && batch_rows <= t->max_batch, "amp_disc_train_step: batch_rows %lld outside [1, %lld]",
                 (long long)batch_rows, (long long)t->max_batch);
     for (int i = 0; i < 3; ++i)
@@ -876,10 +1153,44 @@ int amp_disc_train_step(amp_disc_train_t *t, const float *W1, const float *b1, c
     f.in_features = t->in_features; f.Kp = Kp; f.h1 = h1; f.h2 = h2; f.B = B; f.acc = acc; f.ws_gw3 = ws_gw3; f.ws_gb2 = ws_gb2;
     f.ws_gb1 = ws_gb1; f.loss_scale = loss_scale; f.c_reg = logit_regularization_scale; f.c_gp = gradient_penalty_scale;
     f.c_wd = weight_decay_scale; f.gW1 = gW1; f.gb1 = gb1; f.gW2 = gW2; f.gb2 = gb2; f.gW3 = gW3; f.gb3 = gb3; f.terms = terms;
-    finalize_kernel<<<sm_count() * 4, 256, 0, st>>>(f);
+    if (exchange) {
+        // every CTA waits for flags the peers send from their LAST CTA: the whole grid has to be resident
+        auto launch = [&](auto kern) -> int {
+            int per_sm = 0;
+            AMP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));
+            AMP_REQUIRE(per_sm >= 1, "amp_disc_train_step_exchange: the exchange kernel does not fit on an SM");
+            const long long quads = (ex.count + 3) / 4;
+            const int grid = (int)std::max<long long>(1, std::min<long long>((quads + 255) / 256, (long long)std::min(per_sm, 4) * sm_count()));
+            kern<<<grid, 256, 0, st>>>(f, ex);
+            return AMP_OK;
+        };
+        int rc = bucket->world <= 2 ? launch(finalize_exchange_kernel<2>) : bucket->world <= 4 ? launch(finalize_exchange_kernel<4>) : launch(finalize_exchange_kernel<8>);
+        if (rc != AMP_OK) return rc;
+    } else {
+        finalize_kernel<<<sm_count() * 4, 256, 0, st>>>(f);
+    }
     AMP_CUDA_TRY(cudaGetLastError());
     for (int i = 0; i < 3; ++i) t->staged_rows[i] = -1;
     return AMP_OK;
+}
+
+extern "C" {
+
+int amp_disc_train_step(amp_disc_train_t *t, const float *W1, const float *b1, const float *W2, const float *b2, const float *W3,
+                        const float *b3, int64_t batch_rows, float loss_scale, float logit_regularization_scale,
+                        float gradient_penalty_scale, float weight_decay_scale, float *gW1, float *gb1, float *gW2, float *gb2,
+                        float *gW3, float *gb3, float *terms, float *logits, void *stream) {
+    return train_step_impl(t, W1, b1, W2, b2, W3, b3, batch_rows, loss_scale, logit_regularization_scale, gradient_penalty_scale,
+                           weight_decay_scale, gW1, gb1, gW2, gb2, gW3, gb3, terms, logits, nullptr, stream);
+}
+
+int amp_disc_train_step_exchange(amp_disc_train_t *t, const float *W1, const float *b1, const float *W2, const float *b2, const float *W3,
+                                 const float *b3, int64_t batch_rows, float loss_scale, float logit_regularization_scale,
+                                 float gradient_penalty_scale, float weight_decay_scale, float *gW1, float *gb1, float *gW2, float *gb2,
+                                 float *gW3, float *gb3, float *terms, float *logits, amp_bucket_t *bucket, void *stream) {
+    AMP_REQUIRE(bucket, "amp_disc_train_step_exchange: NULL bucket");
+    return train_step_impl(t, W1, b1, W2, b2, W3, b3, batch_rows, loss_scale, logit_regularization_scale, gradient_penalty_scale,
+                           weight_decay_scale, gW1, gb1, gW2, gb2, gW3, gb3, terms, logits, bucket, stream);
 }
 
 }  // extern "C"

@@ -84,10 +84,15 @@ class AmpDiscriminatorUpdate:
     # ---- the step --------------------------------------------------------------------------------------------------
     def loss_and_grads(self, weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor],
                        grad_weights: Optional[Sequence[torch.Tensor]] = None, grad_biases: Optional[Sequence[torch.Tensor]] = None,
-                       return_logits: bool = False):
+                       return_logits: bool = False, bucket=None):
         """Returns ``(terms, grad_weights, grad_biases[, logits])``: ``terms`` is a float32 device tensor of 6 values named by
         ``TERM_NAMES`` (``terms[5]`` = the scaled discriminator loss); the gradient lists mirror ``weights`` / ``biases``
-        (``[W1 (h1,in), W2 (h2,h1), W3 (1,h2)]``, ``[b1, b2, b3]``) and are overwritten in place when given."""
+        (``[W1 (h1,in), W2 (h2,h1), W3 (1,h2)]``, ``[b1, b2, b3]``) and are overwritten in place when given.
+
+        With ``bucket`` (a :class:`humanoid_amp_b200.distributed.GradientBucket`; the gradient tensors must be six consecutive
+        views of it, e.g. ``bucket.carve``) the step's last kernel also runs the gradient exchange: the tensors come back holding
+        the MEAN over the ranks, exactly what ``bucket.all_reduce_mean`` over that range would have made of them, without the
+        second launch.  Collective: every rank calls it at the same point."""
         if self._batch_rows is None:
             raise RuntimeError("stage() the three batches before loss_and_grads()")
         dev = self.device
@@ -108,24 +113,29 @@ class AmpDiscriminatorUpdate:
         logits = torch.empty(3 * Bp, dtype=torch.float32, device=dev) if return_logits else None
         lib, stream = _lib.enter(dev)
         self._batch_rows = None  # whatever happens next, the following step starts from fresh staging
-        _lib.check(lib.amp_disc_train_step(
-            self._h, _lib.ptr(W[0]), _lib.ptr(b[0]), _lib.ptr(W[1]), _lib.ptr(b[1]), _lib.ptr(W[2]), _lib.ptr(b[2]), B,
-            self.discriminator_loss_scale, self.discriminator_logit_regularization_scale,
-            self.discriminator_gradient_penalty_scale, self.discriminator_weight_decay_scale,
-            _lib.ptr(gW[0]), _lib.ptr(gb[0]), _lib.ptr(gW[1]), _lib.ptr(gb[1]), _lib.ptr(gW[2]), _lib.ptr(gb[2]),
-            _lib.ptr(terms), _lib.ptr(logits), stream))
+        args = (self._h, _lib.ptr(W[0]), _lib.ptr(b[0]), _lib.ptr(W[1]), _lib.ptr(b[1]), _lib.ptr(W[2]), _lib.ptr(b[2]), B,
+                self.discriminator_loss_scale, self.discriminator_logit_regularization_scale,
+                self.discriminator_gradient_penalty_scale, self.discriminator_weight_decay_scale,
+                _lib.ptr(gW[0]), _lib.ptr(gb[0]), _lib.ptr(gW[1]), _lib.ptr(gb[1]), _lib.ptr(gW[2]), _lib.ptr(gb[2]),
+                _lib.ptr(terms), _lib.ptr(logits))
+        if bucket is not None:
+            if bucket.device != dev:
+                raise RuntimeError("the bucket lives on another device")
+            _lib.check(lib.amp_disc_train_step_exchange(*args, bucket._h, stream))
+        else:
+            _lib.check(lib.amp_disc_train_step(*args, stream))
         self._keep = [W, b]
         if return_logits:
             return terms, gW, gb, logits.view(3, Bp)[:, :B]
         return terms, gW, gb
 
     def __call__(self, weights, biases, amp_states, replay_states, motion_states, scaler: Optional[RunningStandardScaler] = None,
-                 train: bool = True, grad_weights=None, grad_biases=None, return_logits: bool = False):
+                 train: bool = True, grad_weights=None, grad_biases=None, return_logits: bool = False, bucket=None):
         """One discriminator update's loss + gradients from the three raw batches, in skrl's order."""
         self.stage(0, amp_states, scaler, train)
         self.stage(1, replay_states, scaler, train)
         self.stage(2, motion_states, scaler, train)
-        return self.loss_and_grads(weights, biases, grad_weights, grad_biases, return_logits)
+        return self.loss_and_grads(weights, biases, grad_weights, grad_biases, return_logits, bucket)
 
     def close(self):
         if getattr(self, "_h", None) is not None:

@@ -310,6 +310,20 @@ AMP_API int amp_bucket_poll_status(amp_bucket_t *b, void *stream, uint32_t *stat
  * barrier B passed.  Synchronises the stream.  For tools/bench_allreduce.py. */
 AMP_API int amp_bucket_last_timing(amp_bucket_t *b, void *stream, uint64_t *stamps4);
 
+/* amp_disc_train_step with the gradient exchange fused into its last kernel (replaces the discriminator's
+ * share of skrl Model.reduce_parameters, train.py:184-196): gW1 .. gb3 must be six views of `bucket` that lie side by side
+ * (any order, each starting on a multiple of 4 floats, the one-element gb3 last); on return of the stream they hold the MEAN
+ * over the ranks of d loss / d parameter -- bit for bit what amp_disc_train_step followed by amp_bucket_allreduce_mean over
+ * that range gives.  The kernel that sums the split-K slices pushes each quad straight into the owning rank's staging area
+ * (peer stores), the owner reduces and publishes; the local bucket is never written with un-reduced gradients and there is no
+ * second launch.  terms / logits stay per rank.  A collective: every rank calls it at the same point of its bucket's call
+ * sequence.  bucket world == 1: identical to amp_disc_train_step.  At most 8 ranks. */
+AMP_API int amp_disc_train_step_exchange(amp_disc_train_t *t, const float *W1, const float *b1, const float *W2, const float *b2,
+                                         const float *W3, const float *b3, int64_t batch_rows, float loss_scale,
+                                         float logit_regularization_scale, float gradient_penalty_scale,
+                                         float weight_decay_scale, float *gW1, float *gb1, float *gW2, float *gb2, float *gW3,
+                                         float *gb3, float *terms, float *logits, amp_bucket_t *bucket, void *stream);
+
 /* ---- offline dataset pipeline (reference motions/data_convert.py:161-379) ----------------------------- */
 /* CSV rows at 30 fps -> 2N-1 frames at 60 fps (scipy interp1d / Slerp semantics) -> forward kinematics over the URDF tree
  * (Pinocchio forwardKinematics + updateFramePlacements, Eigen matrix -> quaternion) -> velocities.  All pointers device. */
