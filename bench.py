@@ -623,7 +623,10 @@ def run_ours(args, name, spec, rank, world, local_rank):
         dist.broadcast(ref0, 0)
         same = torch.tensor([1 if torch.equal(ref0, bucket.flat[:EXCHANGE_FLOATS]) else 0], device=dev)
         dist.all_reduce(same, op=dist.ReduceOp.MIN)
-        collective = {"kernel": "allreduce_mean_bulk_kernel (csrc/amp_bucket.cu: two-shot, cp.async.bulk over NVLink peer memory, in place)",
+        kernel = ("allreduce_mean_switch_kernel (csrc/amp_bucket.cu: multimem.ld_reduce / multimem.st on an NVSwitch multicast mapping of the "
+                  "ranks' buckets, in place)" if bucket.in_switch else
+                  "allreduce_mean_bulk_kernel (csrc/amp_bucket.cu: two-shot, cp.async.bulk over NVLink peer memory, in place)")
+        collective = {"kernel": kernel, "in_switch": bucket.in_switch,
                       "replaces": "skrl Model.reduce_parameters: NCCL all_reduce(SUM) + divide (reference train.py:184-196)",
                       "floats": EXCHANGE_FLOATS, "max_abs_diff_vs_nccl": float(diff.item()), "bitwise_identical_on_all_ranks": bool(same.item())}  # fmt: skip
         bucket.flat[:EXCHANGE_FLOATS].copy_(src)

@@ -133,6 +133,10 @@ SIGNATURES = {
     "amp_dataset_interp_fk": (C.c_int, [C.POINTER(DatasetDesc), _P, _P, _P, _P, _P, _I64, _P]),
     "amp_dataset_velocities": (C.c_int, [_I32, _I32, _I32, C.c_double, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _P]),
     "amp_bucket_create": (C.c_int, [_I64, _I32, _I32, C.POINTER(_P)]),
+    "amp_bucket_create_shared": (C.c_int, [_I64, _I32, _I32, C.POINTER(_P)]),
+    "amp_bucket_export_shared": (C.c_int, [_P, _P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "amp_bucket_connect_shared": (C.c_int, [_P, _P, C.POINTER(C.c_int32), _I32]),
+    "amp_bucket_in_switch": (C.c_int, [_P]),
     "amp_bucket_destroy": (C.c_int, [_P]),
     "amp_bucket_floats": (C.c_int64, [_P]),
     "amp_bucket_data": (C.c_void_p, [_P]),

@@ -33,7 +33,8 @@ SOURCES = {
     "amp_motion.cu": ["-fmad=false"] + (["-DAMP_COLLECT_PROFILE"] if os.environ.get("AMP_COLLECT_PROFILE") == "1" else []),
     # AMP_DISC_PROFILE=1 (developer builds only) adds in-kernel cycle counters to the fused discriminator kernel
     "amp_disc.cu": ["-DAMP_DISC_PROFILE"] if os.environ.get("AMP_DISC_PROFILE") == "1" else [],
-    "amp_disc_train.cu": [],
+    # AMP_EXCHANGE_STAMPS=1|2 (developer builds only) moves the fused exchange kernel's time stamps inside its push / reduce phase
+    "amp_disc_train.cu": ["-DAMP_EXCHANGE_STAMPS=" + os.environ["AMP_EXCHANGE_STAMPS"]] if os.environ.get("AMP_EXCHANGE_STAMPS") else [],
     "amp_bucket.cu": [],
     # the float32 steps of the dataset tool mirror numpy: no contraction into FMA
     "amp_dataset.cu": ["-fmad=false"],

@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <type_traits>
 
 #include "amp_bucket.cuh"
 
@@ -276,6 +277,195 @@ __global__ void __launch_bounds__(kThreads) allreduce_mean_bulk_kernel(Peers pee
     }
 }
 
+// ---- in-switch variant (shared buckets) -------------------------------------------------------------------------------------
+// The data of every rank is bound to ONE NVSwitch multicast object; `mc` is its mapping on this device.  A multimem.ld_reduce
+// on mc + i makes the switch fetch element i from every rank and return the sum; a multimem.st on mc + i writes element i on
+// every rank.  Rank r does that for slice r, between the same two flag barriers as above: each GPU sends its bucket once and
+// receives it once (about half the two-shot kernel's bytes), and nothing is staged.  The sum is the switch's -- the same value
+// on every rank, but not the rank-ordered fp32 sum of the kernels above.
+template <int U>
+__global__ void __launch_bounds__(kThreads) allreduce_mean_switch_kernel(Peers peers, float *mc, int rank, int world, long long offset, long long count,
+                                                                         Control *ctl, volatile uint32_t *host_status, long long spin_limit,
+                                                                         unsigned long long *timing) {
+    __shared__ bool ok, last;
+    __shared__ uint32_t s_epoch;
+    unsigned long long t_start = 0, t_a = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+    uint32_t *local_flags = peers.flags[rank];
+    if (threadIdx.x == 0) s_epoch = *reinterpret_cast<volatile uint32_t *>(&ctl->epoch) + 1;  // device-resident epoch, see allreduce_mean_kernel
+    __syncthreads();
+    const uint32_t epoch = s_epoch;
+    // ---- barrier A ----
+    if (blockIdx.x == 0 && threadIdx.x < world) {
+        __threadfence_system();
+        st_release_sys(peers.flags[threadIdx.x] + rank, epoch);
+    }
+    if (threadIdx.x == 0) {
+        ok = wait_all(local_flags, world, epoch, spin_limit);
+        if (!ok && blockIdx.x == 0) report_failure(ctl, host_status, 1u, peers.data[rank], offset, count);
+    }
+    __syncthreads();
+    if (ok && blockIdx.x == 0 && threadIdx.x == 0) {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_a));
+        timing[0] = t_start;
+        timing[1] = t_a;
+    }
+    // ---- slice `rank`: reduce in the switch, broadcast through the switch ----
+    const long long quads = count / 4;
+    const long long per = (quads + world - 1) / world;
+    const long long q0 = (long long)rank * per, q1 = min(quads, q0 + per);
+    const float inv = 1.0f / (float)world;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    float *base = mc + offset;
+    for (long long q = q0 + blockIdx.x * (long long)blockDim.x + threadIdx.x; ok && q < q1; q += U * stride) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (q + u * stride < q1)
+                asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w)
+                             : "l"(base + 4 * (q + u * stride))
+                             : "memory");
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (q + u * stride < q1)
+                asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(base + 4 * (q + u * stride)), "f"(v[u].x * inv),
+                             "f"(v[u].y * inv), "f"(v[u].z * inv), "f"(v[u].w * inv)
+                             : "memory");
+    }
+    // ---- barrier B: one system fence per CTA, by the thread that signals (the CTA barrier orders the others' stores before it) ----
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        last = atomicAdd(&ctl->arrivals, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    if (threadIdx.x == 0) {
+        ctl->arrivals = 0;
+        ctl->epoch = epoch + 1;
+    }
+    if (threadIdx.x < world) {
+        __threadfence_system();
+        st_release_sys(peers.flags[threadIdx.x] + rank, epoch + 1);
+    }
+    if (threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        timing[2] = t;
+        if (ok && !wait_all(local_flags, world, epoch + 1, spin_limit)) report_failure(ctl, host_status, 2u, peers.data[rank], offset, count);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        timing[3] = t;
+    }
+}
+
+// ---- driver entry points of the virtual-memory-management / multicast API, resolved through the runtime so that the library
+// keeps loading on hosts without libcuda.so ----
+struct DriverApi {
+    decltype(&cuDeviceGet) DeviceGet;
+    decltype(&cuDeviceGetAttribute) DeviceGetAttribute;
+    decltype(&cuMemCreate) MemCreate;
+    decltype(&cuMemRelease) MemRelease;
+    decltype(&cuMemAddressReserve) MemAddressReserve;
+    decltype(&cuMemAddressFree) MemAddressFree;
+    decltype(&cuMemMap) MemMap;
+    decltype(&cuMemUnmap) MemUnmap;
+    decltype(&cuMemSetAccess) MemSetAccess;
+    decltype(&cuMemGetAllocationGranularity) MemGetAllocationGranularity;
+    decltype(&cuMemExportToShareableHandle) MemExportToShareableHandle;
+    decltype(&cuMemImportFromShareableHandle) MemImportFromShareableHandle;
+    decltype(&cuMulticastCreate) MulticastCreate;
+    decltype(&cuMulticastAddDevice) MulticastAddDevice;
+    decltype(&cuMulticastBindMem) MulticastBindMem;
+    decltype(&cuMulticastGetGranularity) MulticastGetGranularity;
+    decltype(&cuGetErrorString) GetErrorString;
+    bool ok;
+};
+
+static const DriverApi &driver() {
+    static DriverApi api = [] {
+        DriverApi a{};
+        bool all = true;
+        auto get = [&](const char *name, auto &fn) {
+            void *p = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess && p)
+                fn = reinterpret_cast<std::remove_reference_t<decltype(fn)>>(p);
+            else
+                all = false;
+        };
+        get("cuDeviceGet", a.DeviceGet);
+        get("cuDeviceGetAttribute", a.DeviceGetAttribute);
+        get("cuMemCreate", a.MemCreate);
+        get("cuMemRelease", a.MemRelease);
+        get("cuMemAddressReserve", a.MemAddressReserve);
+        get("cuMemAddressFree", a.MemAddressFree);
+        get("cuMemMap", a.MemMap);
+        get("cuMemUnmap", a.MemUnmap);
+        get("cuMemSetAccess", a.MemSetAccess);
+        get("cuMemGetAllocationGranularity", a.MemGetAllocationGranularity);
+        get("cuMemExportToShareableHandle", a.MemExportToShareableHandle);
+        get("cuMemImportFromShareableHandle", a.MemImportFromShareableHandle);
+        get("cuMulticastCreate", a.MulticastCreate);
+        get("cuMulticastAddDevice", a.MulticastAddDevice);
+        get("cuMulticastBindMem", a.MulticastBindMem);
+        get("cuMulticastGetGranularity", a.MulticastGetGranularity);
+        get("cuGetErrorString", a.GetErrorString);
+        a.ok = all;
+        return a;
+    }();
+    return api;
+}
+
+static int cu_fail(CUresult r, const char *what) {
+    const char *msg = nullptr;
+    if (driver().GetErrorString) driver().GetErrorString(r, &msg);
+    return fail(r == CUDA_ERROR_NOT_SUPPORTED || r == CUDA_ERROR_NOT_PERMITTED ? AMP_ENOTSUP : AMP_ECUDA, "%s failed: %s (CUresult %d)", what,
+                msg ? msg : "?", (int)r);
+}
+#define AMP_CU_TRY(expr)                                    \
+    do {                                                    \
+        CUresult _r = (expr);                               \
+        if (_r != CUDA_SUCCESS) return cu_fail(_r, #expr);  \
+    } while (0)
+
+static CUmemAllocationProp shared_alloc_prop(int device) {
+    CUmemAllocationProp ap{};
+    ap.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    ap.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    ap.location.id = device;
+    ap.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    return ap;
+}
+
+// reserve an address range on the current device and map `handle` (a local / imported allocation or the multicast object) there
+static int map_handle(CUmemGenericAllocationHandle handle, size_t bytes, size_t align, int device, float **out) {
+    const DriverApi &cu = driver();
+    CUdeviceptr va = 0;
+    AMP_CU_TRY(cu.MemAddressReserve(&va, bytes, align, 0, 0));
+    CUresult r = cu.MemMap(va, bytes, 0, handle, 0);
+    if (r == CUDA_SUCCESS) {
+        CUmemAccessDesc acc{};
+        acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+        acc.location.id = device;
+        acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+        r = cu.MemSetAccess(va, bytes, &acc, 1);
+        if (r != CUDA_SUCCESS) cu.MemUnmap(va, bytes);
+    }
+    if (r != CUDA_SUCCESS) {
+        cu.MemAddressFree(va, bytes);
+        return cu_fail(r, "cuMemMap / cuMemSetAccess");
+    }
+    *out = reinterpret_cast<float *>(va);
+    return AMP_OK;
+}
+
+static void unmap(float *p, size_t bytes) {
+    if (!p) return;
+    driver().MemUnmap(reinterpret_cast<CUdeviceptr>(p), bytes);
+    driver().MemAddressFree(reinterpret_cast<CUdeviceptr>(p), bytes);
+}
+
 }  // namespace bucket
 }  // namespace amp
 
@@ -289,6 +479,18 @@ int amp_bucket_destroy(amp_bucket_t *b) {
     if (!b) return AMP_OK;
     for (int i = 0; i < b->n_opened; ++i)
         if (b->opened[i]) cudaIpcCloseMemHandle(b->opened[i]);
+    if (b->vmm) {
+        cudaDeviceSynchronize();  // nothing may still be running on mappings that are about to go away
+        unmap(b->mc_data, b->map_bytes);
+        for (int p = 0; p < b->world; ++p) {
+            if (p != b->rank) unmap(b->peers.data[p], b->map_bytes);
+            if (b->peer_mem[p]) driver().MemRelease(b->peer_mem[p]);
+        }
+        unmap(b->data, b->map_bytes);
+        if (b->mc) driver().MemRelease(b->mc);  // the team's memory unbinds when the last reference to the object goes
+        if (b->mem) driver().MemRelease(b->mem);
+        b->data = nullptr;
+    }
     if (b->data) cudaFree(b->data);
     if (b->flags) cudaFree(b->flags);
     if (b->timing) cudaFree(b->timing);
@@ -297,7 +499,7 @@ int amp_bucket_destroy(amp_bucket_t *b) {
     return AMP_OK;
 }
 
-int amp_bucket_create(int64_t floats, int32_t world, int32_t rank, amp_bucket_t **out) {
+static int create_impl(int64_t floats, int32_t world, int32_t rank, bool shared, amp_bucket_t **out) {
     AMP_REQUIRE(out, "amp_bucket_create: NULL out");
     *out = nullptr;
     AMP_REQUIRE(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, "amp_bucket_create: bad world %d / rank %d (max %d ranks)",
@@ -314,12 +516,47 @@ int amp_bucket_create(int64_t floats, int32_t world, int32_t rank, amp_bucket_t 
     if (const char *ms = getenv("AMP_B200_BUCKET_TIMEOUT_MS")) b->spin_limit = std::max(1LL, atoll(ms)) * 2000000LL;  // ~2 GHz
     const char *bulk_env = getenv("AMP_B200_BUCKET_BULK");  // 0 selects the load/store kernel; read once per handle
     b->bulk = !(bulk_env && bulk_env[0] == '0') && world <= 8;
+    const char *switch_env = getenv("AMP_B200_BUCKET_IN_SWITCH");  // 0: even a shared bucket keeps the peer-memory kernels; read once per handle
+    b->in_switch = !(switch_env && switch_env[0] == '0');
     AMP_CUDA_TRY(cudaGetDevice(&b->device));
     // staging behind the bucket: `world` copies of the largest slice any range of the bucket can have (a whole quad more per
     // rank for the rounding of the slice length)
     b->stage_floats = world > 1 ? b->floats + 4 * (int64_t)world : 0;
-    cudaError_t e = cudaMalloc((void **)&b->data, (size_t)(b->floats + b->stage_floats) * 4);
-    if (e == cudaSuccess) e = cudaMemset(b->data, 0, (size_t)(b->floats + b->stage_floats) * 4);
+    cudaError_t e = cudaSuccess;
+    if (shared && world > 1) {
+        // a virtual-memory-management allocation that can travel as a POSIX fd and be bound to a multicast object
+        const DriverApi &cu = driver();
+        auto bail = [&](int rc) {
+            amp_bucket_destroy(b);
+            return rc;
+        };
+        if (!cu.ok) return bail(fail(AMP_ENOTSUP, "amp_bucket_create_shared: this driver has no virtual-memory-management / multicast entry points"));
+        CUdevice dev;
+        int mc_ok = 0, fd_ok = 0;
+        if (cu.DeviceGet(&dev, b->device) != CUDA_SUCCESS || cu.DeviceGetAttribute(&mc_ok, CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED, dev) != CUDA_SUCCESS ||
+            cu.DeviceGetAttribute(&fd_ok, CU_DEVICE_ATTRIBUTE_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR_SUPPORTED, dev) != CUDA_SUCCESS || !mc_ok || !fd_ok)
+            return bail(fail(AMP_ENOTSUP, "amp_bucket_create_shared: device %d has no NVSwitch multicast (%d) or no POSIX-fd memory handles (%d)", b->device,
+                             mc_ok, fd_ok));
+        const CUmemAllocationProp ap = shared_alloc_prop(b->device);
+        CUmulticastObjectProp mp{};
+        mp.numDevices = (unsigned)world;
+        mp.handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+        mp.size = (size_t)(b->floats + b->stage_floats) * 4;
+        size_t g_mem = 0, g_mc = 0;
+        CUresult r = cu.MemGetAllocationGranularity(&g_mem, &ap, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED);
+        if (r == CUDA_SUCCESS) r = cu.MulticastGetGranularity(&g_mc, &mp, CU_MULTICAST_GRANULARITY_MINIMUM);
+        if (r != CUDA_SUCCESS) return bail(cu_fail(r, "cuMemGetAllocationGranularity / cuMulticastGetGranularity"));
+        const size_t g = std::max(g_mem, g_mc);  // both are powers of two
+        b->map_bytes = ((size_t)(b->floats + b->stage_floats) * 4 + g - 1) / g * g;
+        b->vmm = true;
+        r = cu.MemCreate(&b->mem, b->map_bytes, &ap, 0);
+        if (r != CUDA_SUCCESS) return bail(cu_fail(r, "cuMemCreate"));
+        if (int rc = map_handle(b->mem, b->map_bytes, g, b->device, &b->data)) return bail(rc);
+        e = cudaMemset(b->data, 0, b->map_bytes);
+    } else {
+        e = cudaMalloc((void **)&b->data, (size_t)(b->floats + b->stage_floats) * 4);
+        if (e == cudaSuccess) e = cudaMemset(b->data, 0, (size_t)(b->floats + b->stage_floats) * 4);
+    }
     if (e == cudaSuccess) e = cudaMalloc((void **)&b->flags, kMaxWorld * sizeof(uint32_t) + sizeof(Control));
     if (e == cudaSuccess) e = cudaMemset(b->flags, 0, kMaxWorld * sizeof(uint32_t) + sizeof(Control));
     if (e == cudaSuccess) {
@@ -349,6 +586,71 @@ int amp_bucket_create(int64_t floats, int32_t world, int32_t rank, amp_bucket_t 
         b->connected = true;
     }
     *out = b;
+    return AMP_OK;
+}
+
+int amp_bucket_create(int64_t floats, int32_t world, int32_t rank, amp_bucket_t **out) { return create_impl(floats, world, rank, false, out); }
+
+int amp_bucket_create_shared(int64_t floats, int32_t world, int32_t rank, amp_bucket_t **out) { return create_impl(floats, world, rank, true, out); }
+
+int amp_bucket_in_switch(const amp_bucket_t *b) { return b && b->mc_data && b->connected && b->in_switch ? 1 : 0; }
+
+int amp_bucket_export_shared(amp_bucket_t *b, void *flags_handle64, int32_t *data_fd, int32_t *multicast_fd) {
+    AMP_REQUIRE(b && flags_handle64 && data_fd && multicast_fd, "amp_bucket_export_shared: NULL argument");
+    AMP_REQUIRE(b->vmm, "amp_bucket_export_shared: the bucket was not made by amp_bucket_create_shared (or has one rank)");
+    const DriverApi &cu = driver();
+    cudaIpcMemHandle_t h;
+    AMP_CUDA_TRY(cudaIpcGetMemHandle(&h, b->flags));
+    std::memcpy(flags_handle64, &h, 64);
+    int fd = -1;
+    AMP_CU_TRY(cu.MemExportToShareableHandle(&fd, b->mem, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0));
+    *data_fd = fd;
+    *multicast_fd = -1;
+    if (b->rank == 0) {  // one rank creates the multicast object; the others import it
+        CUmulticastObjectProp mp{};
+        mp.numDevices = (unsigned)b->world;
+        mp.handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+        mp.size = b->map_bytes;
+        if (!b->mc) AMP_CU_TRY(cu.MulticastCreate(&b->mc, &mp));
+        AMP_CU_TRY(cu.MemExportToShareableHandle(&fd, b->mc, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0));
+        *multicast_fd = fd;
+    }
+    return AMP_OK;
+}
+
+int amp_bucket_connect_shared(amp_bucket_t *b, const void *all_flags_handles, const int32_t *data_fds, int32_t multicast_fd) {
+    AMP_REQUIRE(b && all_flags_handles && data_fds, "amp_bucket_connect_shared: NULL argument");
+    AMP_REQUIRE(b->vmm, "amp_bucket_connect_shared: the bucket was not made by amp_bucket_create_shared (or has one rank)");
+    AMP_REQUIRE(!b->connected, "amp_bucket_connect_shared: already connected");
+    const DriverApi &cu = driver();
+    const cudaIpcMemHandle_t *fh = static_cast<const cudaIpcMemHandle_t *>(all_flags_handles);
+    for (int p = 0; p < b->world; ++p) {
+        if (p == b->rank) {
+            b->peers.data[p] = b->data;
+            b->peers.flags[p] = b->flags;
+            continue;
+        }
+        AMP_REQUIRE(data_fds[p] >= 0, "amp_bucket_connect_shared: no file descriptor for rank %d", p);
+        AMP_CU_TRY(cu.MemImportFromShareableHandle(&b->peer_mem[p], (void *)(uintptr_t)data_fds[p], CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));
+        if (int rc = map_handle(b->peer_mem[p], b->map_bytes, 1 << 21, b->device, &b->peers.data[p])) return rc;
+        void *f = nullptr;
+        AMP_CUDA_TRY(cudaIpcOpenMemHandle(&f, fh[p], cudaIpcMemLazyEnablePeerAccess));
+        b->opened[b->n_opened++] = f;
+        b->peers.flags[p] = static_cast<uint32_t *>(f);
+    }
+    if (b->rank != 0) {
+        AMP_REQUIRE(multicast_fd >= 0, "amp_bucket_connect_shared: no file descriptor for the multicast object");
+        AMP_CU_TRY(cu.MemImportFromShareableHandle(&b->mc, (void *)(uintptr_t)multicast_fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));
+    }
+    AMP_REQUIRE(b->mc, "amp_bucket_connect_shared: rank 0 has to call amp_bucket_export_shared first (it creates the multicast object)");
+    CUdevice dev;
+    AMP_CU_TRY(cu.DeviceGet(&dev, b->device));
+    AMP_CU_TRY(cu.MulticastAddDevice(b->mc, dev));
+    // blocks until every rank of the team has added its device (the call is a collective)
+    AMP_CU_TRY(cu.MulticastBindMem(b->mc, 0, b->mem, 0, b->map_bytes, 0));
+    b->mc_bound = true;
+    if (int rc = map_handle(b->mc, b->map_bytes, 1 << 21, b->device, &b->mc_data)) return rc;
+    b->connected = true;
     return AMP_OK;
 }
 
@@ -416,7 +718,12 @@ int amp_bucket_allreduce_mean(amp_bucket_t *b, int64_t offset_floats, int64_t co
     };
     // default: the bulk-copy kernel (2 GPUs, 2.65 M floats: 34.8 us against 39.3 us with per-thread peer loads / stores and
     // 51.5 us for NCCL all-reduce + divide); AMP_B200_BUCKET_BULK=0 selects the load/store kernel, which also serves > 8 ranks
-    if (b->bulk) {
+    if (b->mc_data && b->in_switch) {  // shared bucket: the NVSwitch reduces and broadcasts
+        constexpr int U = 2;
+        const int grid = (int)std::max<long long>(1, std::min<long long>((per + (long long)U * kThreads - 1) / ((long long)U * kThreads), 4LL * sm_count()));
+        allreduce_mean_switch_kernel<U><<<grid, kThreads, 0, as_stream(stream)>>>(b->peers, b->mc_data, b->rank, b->world, offset_floats, padded, ctl,
+                                                                                   b->host_status_dev, b->spin_limit, b->timing);
+    } else if (b->bulk) {
         const long long chunks = (per + kChunkQuads - 1) / kChunkQuads;
         const int grid = (int)std::max<long long>(1, std::min<long long>(chunks, 4LL * sm_count()));
         auto launch_bulk = [&](auto kern, int maxw) {

@@ -2,6 +2,8 @@
 // the handle itself.  amp_disc_train.cu uses them to run the exchange inside its last kernel (finalize_exchange_kernel).
 #pragma once
 
+#include <cuda.h>
+
 #include "amp_internal.h"
 
 namespace amp {
@@ -90,4 +92,13 @@ struct amp_bucket {
     uint32_t *host_status_dev;       // its device alias
     bool bulk;            // AMP_B200_BUCKET_BULK, read once at create
     bool connected;
+    // ---- shared form (amp_bucket_create_shared): the data is a VMM allocation bound to an NVSwitch multicast object ----
+    bool vmm;                               // data / peers.data[] are cuMemMap mappings, not cudaMalloc / legacy IPC
+    size_t map_bytes;                       // size of every mapping (data + staging, rounded to the granularities)
+    CUmemGenericAllocationHandle mem;       // local physical allocation
+    CUmemGenericAllocationHandle peer_mem[amp::bucket::kMaxWorld];  // imported peers' allocations (0: none)
+    CUmemGenericAllocationHandle mc;        // the multicast object (created by rank 0, imported elsewhere); 0: none
+    bool mc_bound;
+    bool in_switch;                         // AMP_B200_BUCKET_IN_SWITCH (default on), read once at create
+    float *mc_data;                         // multicast mapping of all ranks' data: multimem.ld_reduce / multimem.st address
 };

@@ -643,6 +643,9 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinalizeParams p) {
 // range as long as each starts on a quad (only the one-element dL/db3 is ragged, so it must come last).  All CTAs of the grid
 // must be resident at once (every CTA waits for flags that the peers' LAST CTAs send): the host sizes the grid from the
 // occupancy calculator.
+#ifndef AMP_EXCHANGE_STAMPS
+#define AMP_EXCHANGE_STAMPS 0  // developer builds: 1 = stamps inside the push phase, 2 = inside the reduce phase (tools/bench_fused_exchange.py)
+#endif
 struct ExchangeParams {
     bucket::Peers peers;
     int rank, world;
@@ -763,6 +766,9 @@ __global__ void __launch_bounds__(256) finalize_exchange_kernel(FinalizeParams p
         const float4 g = gradient_quad(p, x, 4 * q);
         st_peer(reinterpret_cast<float4 *>(x.peers.data[owner] + x.stage) + (long long)rank * per + (q - owner * per), g);
     }
+#if AMP_EXCHANGE_STAMPS == 1
+    if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); x.timing[0] = t_start; x.timing[1] = t; }
+#endif
     if (tid == 0 && p.terms) {  // the loss terms are local (skrl logs them per rank)
         const float bce_cat = p.acc[ACC_BCE_CAT] / (2.0f * (float)p.B), bce_motion = p.acc[ACC_BCE_MOTION] / (float)p.B;
         const float reg = p.acc[ACC_W3_SQ], gp = p.acc[ACC_GP_SQ] / (float)p.B, wd = p.acc[ACC_W_SQ] + p.acc[ACC_W3_SQ];
@@ -780,6 +786,9 @@ __global__ void __launch_bounds__(256) finalize_exchange_kernel(FinalizeParams p
     }
     __syncthreads();
     if (last) {
+#if AMP_EXCHANGE_STAMPS == 1
+        if (threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); x.timing[2] = t; }
+#endif
         if (threadIdx.x == 0) x.ctl->pushed = 0;  // every CTA has passed the counter
         if (threadIdx.x < world) {
             __threadfence_system();
@@ -795,8 +804,14 @@ __global__ void __launch_bounds__(256) finalize_exchange_kernel(FinalizeParams p
     if (ok && blockIdx.x == 0 && threadIdx.x == 0) {
         unsigned long long t_a;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_a));
+#if AMP_EXCHANGE_STAMPS == 1
+        x.timing[3] = t_a;
+#elif AMP_EXCHANGE_STAMPS == 2
+        x.timing[0] = t_a;
+#else
         x.timing[0] = t_start;
         x.timing[1] = t_a;
+#endif
     }
     // ---- reduce the own slice (local loads) and publish the mean to every rank's bucket ----
     const long long q0 = (long long)rank * per, q1 = min(quads, q0 + per);
@@ -826,6 +841,9 @@ __global__ void __launch_bounds__(256) finalize_exchange_kernel(FinalizeParams p
             }
         }
     }
+#if AMP_EXCHANGE_STAMPS == 2
+    if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); x.timing[1] = t; }
+#endif
     // ---- barrier B (amp_bucket.cu) ----
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -845,10 +863,14 @@ __global__ void __launch_bounds__(256) finalize_exchange_kernel(FinalizeParams p
     if (threadIdx.x == 0) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+#if AMP_EXCHANGE_STAMPS != 1
         x.timing[2] = t;
+#endif
         if (ok && !wait_all(local_flags, world, epoch + 1, x.spin_limit)) report_failure(x.ctl, x.host_status, 2u, bucket_local, x.hull, x.count);
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+#if AMP_EXCHANGE_STAMPS != 1
         x.timing[3] = t;
+#endif
     }
 }
 

@@ -10,6 +10,9 @@ models' gradients travel as ONE flat fp32 buffer per call (one NCCL launch over 
 from __future__ import annotations
 
 import ctypes as C
+import os
+import socket
+import struct
 from typing import Iterable, List, Optional, Sequence
 
 import torch
@@ -34,13 +37,18 @@ class _DevicePointer:
         self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f4", "data": (ptr, False), "version": 2}
 
 
+class _SharedUnavailable(Exception):
+    pass
+
+
 class GradientBucket:
     """One rank's flat fp32 gradient bucket, averaged over the node's ranks by ONE peer-memory kernel per rank.
 
     Replaces the collective inside skrl ``Model.reduce_parameters`` (``train.py:53-58, 184-196`` switch it on): instead of
     copy-in / NCCL all-reduce / divide / copy-out, gradient producers (``AmpDiscriminatorUpdate(grad_weights=...)``) write
-    straight into views of ``bucket.flat`` and ``all_reduce_mean()`` runs the two-shot NVLink kernel of
-    ``csrc/amp_bucket.cu`` in place.  Construction is collective (every rank of ``group`` must create its bucket at the
+    straight into views of ``bucket.flat`` and ``all_reduce_mean()`` runs one kernel of ``csrc/amp_bucket.cu`` per rank in
+    place: in the NVSwitch (``multimem.ld_reduce`` / ``multimem.st`` on a multicast mapping, ``bucket.in_switch``) from 4
+    ranks up when the node supports it, else two-shot over peer memory (``AMP_B200_BUCKET_IN_SWITCH`` = 0 / 1 overrides).  Construction is collective (every rank of ``group`` must create its bucket at the
     same point, with the same ``numel``): the CUDA IPC handles are exchanged through ``torch.distributed``.
     """
 
@@ -50,24 +58,126 @@ class GradientBucket:
         distributed = dist.is_available() and dist.is_initialized()
         self.world = dist.get_world_size(group) if distributed else 1
         self.rank = dist.get_rank(group) if distributed else 0
+        self.numel = int(numel)
+        self._h = None
+        # Shared form (the all-reduce runs in the NVSwitch) from 4 ranks up -- measured on 2.65 M floats: 52.9 us against 69.4 us
+        # over peer memory at 8 ranks, 54.0 against 55.6 at 4, but 56.4 against 40.3 at 2 (profiles/r02_allreduce_in_switch.md).
+        # Every rank must manage it, or every rank falls back to the peer-memory form.  AMP_B200_BUCKET_IN_SWITCH (read here,
+        # once): 0 never, 1 from 2 ranks up.
+        knob = os.environ.get("AMP_B200_BUCKET_IN_SWITCH", "")
+        if self.world > 1 and knob != "0" and (self.world >= 4 or knob == "1"):
+            self._h = self._create_shared()
+        if self._h is None:
+            self._h = self._create_peer()
+        lib, _stream = _lib.enter(self.device)
+        self.capacity = int(lib.amp_bucket_floats(self._h))
+        self.in_switch = bool(lib.amp_bucket_in_switch(self._h))
+        self.flat = torch.as_tensor(_DevicePointer(int(lib.amp_bucket_data(self._h)), self.capacity), device=self.device)
+
+    def _all_agree(self, ok: bool) -> bool:
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        return bool(flag.item())
+
+    def _gather_bytes(self, blob: bytes) -> bytes:
+        mine = torch.tensor(list(blob), dtype=torch.uint8, device=self.device)
+        gathered = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(gathered, mine, group=self.group)
+        return bytes(torch.cat(gathered).cpu().numpy().tobytes())
+
+    def _create_peer(self):
+        """cudaMalloc + legacy CUDA IPC: peer loads / stores over NVLink (``amp_bucket_create``)."""
         lib, _stream = _lib.enter(self.device)
         h = C.c_void_p()
-        _lib.check(lib.amp_bucket_create(int(numel), self.world, self.rank, C.byref(h)))
-        self._h = h
-        self.numel = int(numel)
-        self.capacity = int(lib.amp_bucket_floats(h))
-        self.flat = torch.as_tensor(_DevicePointer(int(lib.amp_bucket_data(h)), self.capacity), device=self.device)
+        _lib.check(lib.amp_bucket_create(self.numel, self.world, self.rank, C.byref(h)))
         if self.world > 1:
             blob = (C.c_ubyte * 128)()
-            lib, _stream = _lib.enter(self.device)
             _lib.check(lib.amp_bucket_export(h, blob))
-            mine = torch.tensor(list(blob), dtype=torch.uint8, device=self.device)
-            gathered = [torch.empty_like(mine) for _ in range(self.world)]
-            dist.all_gather(gathered, mine, group=group)
-            everyone = bytes(torch.cat(gathered).cpu().numpy().tobytes())
+            everyone = self._gather_bytes(bytes(blob))
             lib, _stream = _lib.enter(self.device)  # the peers' memory is mapped into THIS device's context
             _lib.check(lib.amp_bucket_connect(h, everyone))
-            dist.barrier(group)  # every rank has mapped every peer before the first all-reduce touches peer memory
+            dist.barrier(self.group)  # every rank has mapped every peer before the first all-reduce touches peer memory
+        return h
+
+    def _create_shared(self):
+        """VMM allocation shared as POSIX fds + one NVSwitch multicast object (``amp_bucket_create_shared``); ``None`` when
+        any rank cannot (no multicast support, fd passing refused): the caller then builds the peer-memory form."""
+        lib, _stream = _lib.enter(self.device)
+        h = C.c_void_p()
+        rc = lib.amp_bucket_create_shared(self.numel, self.world, self.rank, C.byref(h))
+        if not self._all_agree(rc == 0):
+            if rc == 0:
+                lib.amp_bucket_destroy(h)
+            return None
+        fds: List[int] = []
+        try:
+            blob = (C.c_ubyte * 64)()
+            data_fd, mc_fd = C.c_int32(-1), C.c_int32(-1)
+            rc = lib.amp_bucket_export_shared(h, blob, C.byref(data_fd), C.byref(mc_fd))
+            fds += [fd for fd in (data_fd.value, mc_fd.value) if fd >= 0]
+            if not self._all_agree(rc == 0):
+                raise _SharedUnavailable
+            everyone = self._gather_bytes(bytes(blob))
+            try:
+                peer_fds, peer_mc = self._swap_fds(data_fd.value, mc_fd.value)
+                ok = True
+            except OSError:
+                peer_fds, peer_mc, ok = [-1] * self.world, -1, False
+            fds += [fd for fd in peer_fds if fd >= 0] + ([peer_mc] if peer_mc >= 0 else [])
+            if not self._all_agree(ok):
+                raise _SharedUnavailable
+            lib, _stream = _lib.enter(self.device)
+            rc = lib.amp_bucket_connect_shared(h, everyone, (C.c_int32 * self.world)(*peer_fds), peer_mc if self.rank else mc_fd.value)
+            if rc != 0:  # the team is half built: nothing sane to fall back to
+                _lib.check(rc)
+            dist.barrier(self.group)
+            return h
+        except _SharedUnavailable:
+            lib.amp_bucket_destroy(h)
+            return None
+        finally:
+            for fd in fds:  # imports hold their own references
+                os.close(fd)
+
+    def _swap_fds(self, data_fd: int, mc_fd: int):
+        """Every rank hands the fd of its allocation (rank 0: also the multicast object's) to every other rank: SCM_RIGHTS over
+        unix sockets in the abstract namespace, named by a token rank 0 draws."""
+        token = torch.randint(0, 2**62, (1,), dtype=torch.int64, device=self.device)
+        src = dist.get_global_rank(self.group, 0) if self.group is not None else 0
+        dist.broadcast(token, src=src, group=self.group)
+        name = lambda r: f"\0amp_b200_bucket_{int(token.item()):x}_{r}"  # noqa: E731
+        server = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        got, mc = [-1] * self.world, -1
+        try:
+            bind_error = None
+            try:
+                server.bind(name(self.rank))
+                server.listen(self.world)
+                server.settimeout(60.0)
+            except OSError as e:  # still walk the barrier: the other ranks are waiting in it
+                bind_error = e
+            dist.barrier(self.group)  # everyone is listening
+            if bind_error is not None:
+                raise bind_error
+            for p in range(self.world):
+                if p == self.rank:
+                    continue
+                with socket.socket(socket.AF_UNIX, socket.SOCK_STREAM) as c:
+                    c.settimeout(60.0)
+                    c.connect(name(p))
+                    socket.send_fds(c, [struct.pack("i", self.rank)], [data_fd] + ([mc_fd] if self.rank == 0 else []))
+            for _ in range(self.world - 1):
+                conn, _addr = server.accept()
+                with conn:
+                    conn.settimeout(60.0)
+                    msg, received, _flags, _a = socket.recv_fds(conn, 4, 2)
+                    sender = struct.unpack("i", msg)[0]
+                    got[sender] = received[0]
+                    if sender == 0:
+                        mc = received[1]
+        finally:
+            server.close()
+        return got, mc
 
     def carve(self, shapes: Sequence[Sequence[int]]) -> List[torch.Tensor]:
         """Consecutive views of the bucket with the given shapes (e.g. the discriminator's six gradient tensors)."""

@@ -39,7 +39,8 @@ enum {
     AMP_ECUDA = -2,    /* a CUDA runtime call or launch failed; amp_last_error() carries cudaGetErrorString */
     AMP_ENODEV = -3,   /* no CUDA device / device is not sm_100 */
     AMP_ERANGE = -4,   /* a motion id was outside [0, num_trajectories) or a time was NaN (see amp_lib_poll_flags) */
-    AMP_ENOMEM = -5
+    AMP_ENOMEM = -5,
+    AMP_ENOTSUP = -6   /* the platform lacks a capability the call needs (NVSwitch multicast, POSIX-fd memory sharing) */
 };
 
 typedef struct amp_lib amp_lib_t;   /* a motion library staged on one device */
@@ -309,6 +310,21 @@ AMP_API int amp_bucket_poll_status(amp_bucket_t *b, void *stream, uint32_t *stat
 /* %globaltimer stamps (ns) of the last all-reduce on this rank: kernel start, barrier A passed, own slice published,
  * barrier B passed.  Synchronises the stream.  For tools/bench_allreduce.py. */
 AMP_API int amp_bucket_last_timing(amp_bucket_t *b, void *stream, uint64_t *stamps4);
+
+/* Shared form of the bucket: the same object, but its memory is a virtual-memory-management allocation that every rank maps
+ * (unicast, for the kernels above) AND that is bound to one NVSwitch multicast object, so that amp_bucket_allreduce_mean runs
+ * in the switch: rank r reduces slice r with multimem.ld_reduce (the switch adds the W copies) and broadcasts the mean with
+ * multimem.st -- every rank moves about half the bytes of the two-shot kernel and the sum is the switch's, identical on all
+ * ranks.  Everything else (flags, epochs, timeouts, amp_disc_train_step_exchange) is unchanged.
+ *   create_shared -> export_shared (64-byte IPC handle of the flags, a POSIX fd of the data, and on rank 0 the fd of the
+ *   multicast object; the caller owns the fds and closes them after connect) -> [pass the fds between the processes, e.g.
+ *   SCM_RIGHTS over a unix socket] -> connect_shared (collective: blocks until every rank has joined the multicast team).
+ * AMP_ENOTSUP when the device has no multicast support or no POSIX-fd handles: use amp_bucket_create then. */
+AMP_API int amp_bucket_create_shared(int64_t floats, int32_t world, int32_t rank, amp_bucket_t **out);
+AMP_API int amp_bucket_export_shared(amp_bucket_t *b, void *flags_handle64, int32_t *data_fd, int32_t *multicast_fd);
+AMP_API int amp_bucket_connect_shared(amp_bucket_t *b, const void *all_flags_handles, const int32_t *data_fds, int32_t multicast_fd);
+/* 1 when amp_bucket_allreduce_mean on this bucket runs in the switch (shared form, connected), else 0. */
+AMP_API int amp_bucket_in_switch(const amp_bucket_t *b);
 
 /* amp_disc_train_step with the gradient exchange fused into its last kernel (replaces the discriminator's
  * share of skrl Model.reduce_parameters, train.py:184-196): gW1 .. gb3 must be six views of `bucket` that lie side by side

@@ -58,17 +58,25 @@ def test_discriminator_gradients_land_in_the_bucket():
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs on the box (run with gpurun --gpus 2)")
-def test_peer_memory_allreduce_matches_nccl_world2():
+@pytest.mark.parametrize("in_switch", ["auto", "1"])
+def test_allreduce_matches_nccl_world2(in_switch):
+    """Both forms of the bucket under a 2-rank torchrun: peer memory (the default below 4 ranks) and, forced, the shared form
+    whose all-reduce runs in the NVSwitch (skipped where the node has no multicast support: the tool then reports the fallback)."""
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", str(port), os.path.join(ROOT, "tools", "bench_allreduce.py"), "--numel", "1376000", "--iters", "10"]  # fmt: skip
+           "--master-port", str(port), os.path.join(ROOT, "tools", "bench_allreduce.py"), "--numel", "1376000", "--iters", "10",
+           "--in-switch", in_switch]  # fmt: skip
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-3000:]
     rec = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
     assert rec["ok"], rec["notes"]
     assert rec["world"] == 2
+    if in_switch == "auto":
+        assert not rec["in_switch"]
+    elif not rec["in_switch"]:
+        pytest.skip("no NVSwitch multicast on this node: the bucket fell back to peer memory")
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs on the box (run with gpurun --gpus 2)")

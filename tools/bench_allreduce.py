@@ -43,7 +43,11 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--numel", type=int, default=2_650_000)  # policy + value + discriminator of the G1 dance config
     ap.add_argument("--iters", type=int, default=50)
+    ap.add_argument("--in-switch", choices=["auto", "0", "1"], default="auto",
+                    help="AMP_B200_BUCKET_IN_SWITCH for the bucket under test: auto = from 4 ranks up, 1 = also at 2 ranks, 0 = never")
     a = ap.parse_args()
+    if a.in_switch != "auto":
+        os.environ["AMP_B200_BUCKET_IN_SWITCH"] = a.in_switch
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
@@ -147,12 +151,35 @@ def main():
     if bucket.poll_status() != 0:
         ok = False
         notes.append("device status word set after timing")
+    # the other form of the bucket (peer memory when the default came up in the switch): same checks in short, and its time
+    ms_other = None
+    if bucket.in_switch:
+        before = os.environ.get("AMP_B200_BUCKET_IN_SWITCH")
+        os.environ["AMP_B200_BUCKET_IN_SWITCH"] = "0"
+        other = amp.GradientBucket(a.numel, dev)
+        if before is None:
+            del os.environ["AMP_B200_BUCKET_IN_SWITCH"]
+        else:
+            os.environ["AMP_B200_BUCKET_IN_SWITCH"] = before
+        src = torch.randn(a.numel, device=dev, generator=g) * (1.0 + rank)
+        other.flat[: a.numel].copy_(src)
+        want = src.clone()
+        dist.all_reduce(want, op=dist.ReduceOp.SUM)
+        want /= world
+        other.all_reduce_mean(0, a.numel)
+        err = float((other.flat[: a.numel] - want).abs().max())
+        if other.in_switch or not err <= 1e-5 * max(1.0, float(want.abs().max())):
+            ok = False
+            notes.append(f"peer-memory form: in_switch={other.in_switch}, max err {err:.3e}")
+        ms_other = timed(lambda: other.all_reduce_mean(0, a.numel), a.iters, dev)
+        other.close()
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         bytes_moved = 2.0 * (world - 1) / world * a.numel * 4
         print(json.dumps({"what": "gradient all-reduce (mean) of one flat fp32 bucket", "world": world, "numel": a.numel,
-                          "ok": bool(flag.item()), "notes": notes, "ms_nccl_allreduce_plus_div": ms_nccl, "ms_peer_memory_kernel": ms_bucket,
+                          "ok": bool(flag.item()), "notes": notes, "in_switch": bucket.in_switch, "ms_nccl_allreduce_plus_div": ms_nccl,
+                          "ms_bucket_kernel": ms_bucket, "ms_peer_memory_form": ms_other if bucket.in_switch else ms_bucket,
                           "speedup": ms_nccl / ms_bucket, "phases_us_rank0_last_call": phases, "nvlink_gbs_per_rank_each_way": bytes_moved / ms_bucket / 1e6}))
     dist.barrier()
     dist.destroy_process_group()

@@ -32,7 +32,10 @@ def main():
     ap.add_argument("--in-features", type=int, nargs="+", default=[166, 830])
     ap.add_argument("--batch", type=int, default=4096)  # agents/skrl_g1_dance_amp_cfg.yaml:94 discriminator_batch_size
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--in-switch", choices=["auto", "0", "1"], default="auto", help="AMP_B200_BUCKET_IN_SWITCH for the buckets (see bench_allreduce.py)")
     a = ap.parse_args()
+    if a.in_switch != "auto":
+        os.environ["AMP_B200_BUCKET_IN_SWITCH"] = a.in_switch
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
@@ -114,9 +117,11 @@ def main():
             bad(f"in={inf}: device status word set")
         ms_plain = timed(g_plain.replay, a.iters, dev)
         ms_fused = timed(g_fused.replay, a.iters, dev)
-        fused()
+        for _ in range(5):  # a few replays put the ranks in lock step before the stamps are read
+            g_fused.replay()
         phases = bucket.last_timing_us()
-        rows.append({"in_features": inf, "batch_rows": a.batch, "gradient_floats": n_disc, "us_step_plus_allreduce": ms_plain * 1e3,
+        rows.append({"in_features": inf, "batch_rows": a.batch, "gradient_floats": n_disc, "all_reduce_in_switch": bucket.in_switch,
+                     "us_step_plus_allreduce": ms_plain * 1e3,
                      "us_fused_step": ms_fused * 1e3, "phases_us_rank0_last_fused_call": phases})
         del g_plain, g_fused
         upd.close()
