@@ -135,7 +135,8 @@ SIGNATURES = {
     "amp_bucket_create": (C.c_int, [_I64, _I32, _I32, C.POINTER(_P)]),
     "amp_bucket_create_shared": (C.c_int, [_I64, _I32, _I32, C.POINTER(_P)]),
     "amp_bucket_export_shared": (C.c_int, [_P, _P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
-    "amp_bucket_connect_shared": (C.c_int, [_P, _P, C.POINTER(C.c_int32), _I32]),
+    "amp_bucket_join_shared": (C.c_int, [_P, _I32]),
+    "amp_bucket_connect_shared": (C.c_int, [_P, _P, C.POINTER(C.c_int32)]),
     "amp_bucket_in_switch": (C.c_int, [_P]),
     "amp_bucket_destroy": (C.c_int, [_P]),
     "amp_bucket_floats": (C.c_int64, [_P]),

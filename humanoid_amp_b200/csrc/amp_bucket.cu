@@ -618,9 +618,27 @@ int amp_bucket_export_shared(amp_bucket_t *b, void *flags_handle64, int32_t *dat
     return AMP_OK;
 }
 
-int amp_bucket_connect_shared(amp_bucket_t *b, const void *all_flags_handles, const int32_t *data_fds, int32_t multicast_fd) {
+int amp_bucket_join_shared(amp_bucket_t *b, int32_t multicast_fd) {
+    AMP_REQUIRE(b, "amp_bucket_join_shared: NULL handle");
+    AMP_REQUIRE(b->vmm, "amp_bucket_join_shared: the bucket was not made by amp_bucket_create_shared (or has one rank)");
+    AMP_REQUIRE(!b->joined, "amp_bucket_join_shared: already joined");
+    const DriverApi &cu = driver();
+    if (b->rank != 0) {
+        AMP_REQUIRE(multicast_fd >= 0, "amp_bucket_join_shared: no file descriptor for the multicast object");
+        AMP_CU_TRY(cu.MemImportFromShareableHandle(&b->mc, (void *)(uintptr_t)multicast_fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));
+    }
+    AMP_REQUIRE(b->mc, "amp_bucket_join_shared: rank 0 has to call amp_bucket_export_shared first (it creates the multicast object)");
+    CUdevice dev;
+    AMP_CU_TRY(cu.DeviceGet(&dev, b->device));
+    AMP_CU_TRY(cu.MulticastAddDevice(b->mc, dev));
+    b->joined = true;
+    return AMP_OK;
+}
+
+int amp_bucket_connect_shared(amp_bucket_t *b, const void *all_flags_handles, const int32_t *data_fds) {
     AMP_REQUIRE(b && all_flags_handles && data_fds, "amp_bucket_connect_shared: NULL argument");
     AMP_REQUIRE(b->vmm, "amp_bucket_connect_shared: the bucket was not made by amp_bucket_create_shared (or has one rank)");
+    AMP_REQUIRE(b->joined, "amp_bucket_connect_shared: amp_bucket_join_shared has not been called");
     AMP_REQUIRE(!b->connected, "amp_bucket_connect_shared: already connected");
     const DriverApi &cu = driver();
     const cudaIpcMemHandle_t *fh = static_cast<const cudaIpcMemHandle_t *>(all_flags_handles);
@@ -638,15 +656,8 @@ int amp_bucket_connect_shared(amp_bucket_t *b, const void *all_flags_handles, co
         b->opened[b->n_opened++] = f;
         b->peers.flags[p] = static_cast<uint32_t *>(f);
     }
-    if (b->rank != 0) {
-        AMP_REQUIRE(multicast_fd >= 0, "amp_bucket_connect_shared: no file descriptor for the multicast object");
-        AMP_CU_TRY(cu.MemImportFromShareableHandle(&b->mc, (void *)(uintptr_t)multicast_fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));
-    }
-    AMP_REQUIRE(b->mc, "amp_bucket_connect_shared: rank 0 has to call amp_bucket_export_shared first (it creates the multicast object)");
-    CUdevice dev;
-    AMP_CU_TRY(cu.DeviceGet(&dev, b->device));
-    AMP_CU_TRY(cu.MulticastAddDevice(b->mc, dev));
-    // blocks until every rank of the team has added its device (the call is a collective)
+    // would block until every rank of the team has added its device -- which is why joining is a call of its own: the caller
+    // gets here only after EVERY rank has reported a successful join
     AMP_CU_TRY(cu.MulticastBindMem(b->mc, 0, b->mem, 0, b->map_bytes, 0));
     b->mc_bound = true;
     if (int rc = map_handle(b->mc, b->map_bytes, 1 << 21, b->device, &b->mc_data)) return rc;

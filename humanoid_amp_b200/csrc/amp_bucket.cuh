@@ -98,6 +98,7 @@ struct amp_bucket {
     CUmemGenericAllocationHandle mem;       // local physical allocation
     CUmemGenericAllocationHandle peer_mem[amp::bucket::kMaxWorld];  // imported peers' allocations (0: none)
     CUmemGenericAllocationHandle mc;        // the multicast object (created by rank 0, imported elsewhere); 0: none
+    bool joined;                            // this rank's device has been added to the multicast team
     bool mc_bound;
     bool in_switch;                         // AMP_B200_BUCKET_IN_SWITCH (default on), read once at create
     float *mc_data;                         // multicast mapping of all ranks' data: multimem.ld_reduce / multimem.st address

@@ -127,10 +127,13 @@ class GradientBucket:
             if not self._all_agree(ok):
                 raise _SharedUnavailable
             lib, _stream = _lib.enter(self.device)
-            rc = lib.amp_bucket_connect_shared(h, everyone, (C.c_int32 * self.world)(*peer_fds), peer_mc if self.rank else mc_fd.value)
-            if rc != 0:  # the team is half built: nothing sane to fall back to
-                _lib.check(rc)
-            dist.barrier(self.group)
+            rc = lib.amp_bucket_join_shared(h, peer_mc if self.rank else mc_fd.value)
+            if not self._all_agree(rc == 0):  # binding blocks until the whole team has joined: go on only if everyone has
+                raise _SharedUnavailable
+            lib, _stream = _lib.enter(self.device)
+            rc = lib.amp_bucket_connect_shared(h, everyone, (C.c_int32 * self.world)(*peer_fds))
+            if not self._all_agree(rc == 0):
+                raise _SharedUnavailable
             return h
         except _SharedUnavailable:
             lib.amp_bucket_destroy(h)

@@ -318,11 +318,14 @@ AMP_API int amp_bucket_last_timing(amp_bucket_t *b, void *stream, uint64_t *stam
  * ranks.  Everything else (flags, epochs, timeouts, amp_disc_train_step_exchange) is unchanged.
  *   create_shared -> export_shared (64-byte IPC handle of the flags, a POSIX fd of the data, and on rank 0 the fd of the
  *   multicast object; the caller owns the fds and closes them after connect) -> [pass the fds between the processes, e.g.
- *   SCM_RIGHTS over a unix socket] -> connect_shared (collective: blocks until every rank has joined the multicast team).
- * AMP_ENOTSUP when the device has no multicast support or no POSIX-fd handles: use amp_bucket_create then. */
+ *   SCM_RIGHTS over a unix socket] -> join_shared (adds this rank's device to the multicast team) -> [make sure EVERY rank
+ *   has joined: binding memory blocks until the team is complete] -> connect_shared (maps the peers, binds, maps the team).
+ * AMP_ENOTSUP when the device has no multicast support or no POSIX-fd handles: use amp_bucket_create then.  A rank that fails
+ * at any step destroys its handle; when the ranks agree on that after each step, nobody is left waiting. */
 AMP_API int amp_bucket_create_shared(int64_t floats, int32_t world, int32_t rank, amp_bucket_t **out);
 AMP_API int amp_bucket_export_shared(amp_bucket_t *b, void *flags_handle64, int32_t *data_fd, int32_t *multicast_fd);
-AMP_API int amp_bucket_connect_shared(amp_bucket_t *b, const void *all_flags_handles, const int32_t *data_fds, int32_t multicast_fd);
+AMP_API int amp_bucket_join_shared(amp_bucket_t *b, int32_t multicast_fd);
+AMP_API int amp_bucket_connect_shared(amp_bucket_t *b, const void *all_flags_handles, const int32_t *data_fds);
 /* 1 when amp_bucket_allreduce_mean on this bucket runs in the switch (shared form, connected), else 0. */
 AMP_API int amp_bucket_in_switch(const amp_bucket_t *b);
 
