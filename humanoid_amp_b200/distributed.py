@@ -37,6 +37,54 @@ class _DevicePointer:
         self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f4", "data": (ptr, False), "version": 2}
 
 
+def swap_fds(own_fd: int, root_fd: int, rank: int, world: int, group=None, device=None, timeout: float = 60.0):
+    """Every rank hands a file descriptor (``own_fd``) to every other rank, and rank 0 a second one (``root_fd``) on top:
+    ``SCM_RIGHTS`` over unix sockets in the abstract namespace, named by a token rank 0 draws.  Returns ``(fds, root)``: ``fds[p]``
+    is this process's descriptor for rank p's ``own_fd`` (-1 for itself), ``root`` the one for rank 0's ``root_fd`` (-1 on rank 0).
+    Collective; any failure surfaces as ``OSError`` AFTER the rendezvous barrier, so the ranks stay in step.  The descriptors of
+    :class:`GradientBucket`'s shared form travel this way (CUDA VMM allocations and the multicast object export as POSIX fds,
+    which mean nothing in another process until the kernel has duplicated them into it)."""
+    token = torch.randint(0, 2**62, (1,), dtype=torch.int64)
+    if device is not None and dist.get_backend(group) == "nccl":
+        token = token.to(device)
+    src = dist.get_global_rank(group, 0) if group is not None else 0
+    dist.broadcast(token, src=src, group=group)
+    tag = int(token.item())
+    name = lambda r: f"\0amp_b200_bucket_{tag:x}_{r}"  # noqa: E731
+    server = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+    got, root = [-1] * world, -1
+    try:
+        bind_error = None
+        try:
+            server.bind(name(rank))
+            server.listen(world)
+            server.settimeout(timeout)
+        except OSError as e:  # still walk the barrier: the other ranks are waiting in it
+            bind_error = e
+        dist.barrier(group)  # everyone is listening
+        if bind_error is not None:
+            raise bind_error
+        for p in range(world):
+            if p == rank:
+                continue
+            with socket.socket(socket.AF_UNIX, socket.SOCK_STREAM) as c:
+                c.settimeout(timeout)
+                c.connect(name(p))
+                socket.send_fds(c, [struct.pack("i", rank)], [own_fd] + ([root_fd] if rank == 0 else []))
+        for _ in range(world - 1):
+            conn, _addr = server.accept()
+            with conn:
+                conn.settimeout(timeout)
+                msg, received, _flags, _a = socket.recv_fds(conn, 4, 2)
+                sender = struct.unpack("i", msg)[0]
+                got[sender] = received[0]
+                if sender == 0:
+                    root = received[1]
+    finally:
+        server.close()
+    return got, root
+
+
 class _SharedUnavailable(Exception):
     pass
 
@@ -119,7 +167,7 @@ class GradientBucket:
                 raise _SharedUnavailable
             everyone = self._gather_bytes(bytes(blob))
             try:
-                peer_fds, peer_mc = self._swap_fds(data_fd.value, mc_fd.value)
+                peer_fds, peer_mc = swap_fds(data_fd.value, mc_fd.value, self.rank, self.world, self.group, self.device)
                 ok = True
             except OSError:
                 peer_fds, peer_mc, ok = [-1] * self.world, -1, False
@@ -141,46 +189,6 @@ class GradientBucket:
         finally:
             for fd in fds:  # imports hold their own references
                 os.close(fd)
-
-    def _swap_fds(self, data_fd: int, mc_fd: int):
-        """Every rank hands the fd of its allocation (rank 0: also the multicast object's) to every other rank: SCM_RIGHTS over
-        unix sockets in the abstract namespace, named by a token rank 0 draws."""
-        token = torch.randint(0, 2**62, (1,), dtype=torch.int64, device=self.device)
-        src = dist.get_global_rank(self.group, 0) if self.group is not None else 0
-        dist.broadcast(token, src=src, group=self.group)
-        name = lambda r: f"\0amp_b200_bucket_{int(token.item()):x}_{r}"  # noqa: E731
-        server = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
-        got, mc = [-1] * self.world, -1
-        try:
-            bind_error = None
-            try:
-                server.bind(name(self.rank))
-                server.listen(self.world)
-                server.settimeout(60.0)
-            except OSError as e:  # still walk the barrier: the other ranks are waiting in it
-                bind_error = e
-            dist.barrier(self.group)  # everyone is listening
-            if bind_error is not None:
-                raise bind_error
-            for p in range(self.world):
-                if p == self.rank:
-                    continue
-                with socket.socket(socket.AF_UNIX, socket.SOCK_STREAM) as c:
-                    c.settimeout(60.0)
-                    c.connect(name(p))
-                    socket.send_fds(c, [struct.pack("i", self.rank)], [data_fd] + ([mc_fd] if self.rank == 0 else []))
-            for _ in range(self.world - 1):
-                conn, _addr = server.accept()
-                with conn:
-                    conn.settimeout(60.0)
-                    msg, received, _flags, _a = socket.recv_fds(conn, 4, 2)
-                    sender = struct.unpack("i", msg)[0]
-                    got[sender] = received[0]
-                    if sender == 0:
-                        mc = received[1]
-        finally:
-            server.close()
-        return got, mc
 
     def carve(self, shapes: Sequence[Sequence[int]]) -> List[torch.Tensor]:
         """Consecutive views of the bucket with the given shapes (e.g. the discriminator's six gradient tensors)."""

@@ -72,6 +72,49 @@ def test_reduce_parameters_world2_gloo(tmp_path):
     assert r[0]["shard"] == (0, 2049) and r[1]["shard"] == (2049, 4097)
 
 
+def _fd_worker(rank, world, port, result_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    from humanoid_amp_b200.distributed import swap_fds
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # every rank owns a pipe whose write end travels to the others; rank 0 a second one ("the multicast object")
+        r_own, w_own = os.pipe()
+        r_root, w_root = os.pipe() if rank == 0 else (-1, -1)
+        fds, root = swap_fds(w_own, w_root, rank, world)
+        assert fds[rank] == -1 and all(fd >= 0 for p, fd in enumerate(fds) if p != rank)
+        assert (root == -1) == (rank == 0)
+        for p, fd in enumerate(fds):  # write into every peer's pipe through the descriptor that was handed over
+            if p != rank:
+                os.write(fd, bytes([rank]))
+                os.close(fd)
+        if rank != 0:
+            os.write(root, bytes([100 + rank]))
+            os.close(root)
+        dist.barrier()
+        os.close(w_own)
+        own = sorted(os.read(r_own, 64))
+        extra = sorted(os.read(r_root, 64)) if rank == 0 else None
+        if rank == 0:
+            os.close(w_root)
+        with open(os.path.join(result_dir, f"fd{rank}.json"), "w") as f:
+            json.dump({"own": own, "extra": extra}, f)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_swap_fds_world3_gloo(tmp_path):
+    """The descriptor exchange behind the shared gradient bucket (SCM_RIGHTS over abstract unix sockets): every rank must end up
+    with a working descriptor for every other rank's object and for rank 0's extra one."""
+    world, port = 3, _free_port()
+    mp.spawn(_fd_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    for rank in range(world):
+        rec = json.load(open(tmp_path / f"fd{rank}.json"))
+        assert rec["own"] == [p for p in range(world) if p != rank]
+        assert rec["extra"] == ([101, 102] if rank == 0 else None)
+
+
 def test_reduce_parameters_is_noop_without_process_group():
     from humanoid_amp_b200.distributed import reduce_parameters
 
