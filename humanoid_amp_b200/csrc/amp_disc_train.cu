@@ -648,6 +648,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinalizeParams p) {
 #endif
 struct ExchangeParams {
     bucket::Peers peers;
+    float *mc;             // multicast mapping of every rank's bucket (shared buckets whose all-reduce runs in the switch), or NULL
     int rank, world;
     long long hull;        // float offset of the exchanged range inside the bucket (multiple of 4)
     long long count;       // floats in the range (all six tensors)
@@ -743,8 +744,11 @@ __device__ __forceinline__ float4 gradient_quad(const FinalizeParams &p, const E
     return make_float4(p.acc[ACC_GB3], 0.0f, 0.0f, 0.0f);  // dL/db3 (the ragged last quad)
 }
 
-template <int MAXW>
-__global__ void __launch_bounds__(256) finalize_exchange_kernel(FinalizeParams p, ExchangeParams x) {
+// SWITCH = true (shared buckets): the push phase writes the local bucket instead, and the reduce phase is the in-switch pair of
+// allreduce_mean_switch_kernel (multimem.ld_reduce / multimem.st on the multicast mapping) -- finalize_kernel and that kernel in
+// one launch, with the switch's sum.
+template <int MAXW, bool SWITCH>
+__global__ void __launch_bounds__(256, 4) finalize_exchange_kernel(FinalizeParams p, ExchangeParams x) {
     using namespace amp::bucket;
     __shared__ bool ok, last;
     __shared__ uint32_t s_epoch;
@@ -761,10 +765,17 @@ __global__ void __launch_bounds__(256) finalize_exchange_kernel(FinalizeParams p
     // ---- push: local gradients -> the owners' staging (slot `rank` of the owner's W slots of `per` quads) ----
     // No barrier in front: the peers stopped reading their staging before they passed barrier B of the previous call, and this
     // rank passed that barrier before its stream reached this launch.
+    float *bucket_local = x.peers.data[rank];
     for (long long q = tid; q < quads; q += stride) {
-        const int owner = (int)q / (int)per;  // the range is a few million floats: 32-bit arithmetic
         const float4 g = gradient_quad(p, x, 4 * q);
-        st_peer(reinterpret_cast<float4 *>(x.peers.data[owner] + x.stage) + (long long)rank * per + (q - owner * per), g);
+        if (SWITCH) {
+            float *dst = bucket_local + x.hull + 4 * q;
+            if (x.count - 4 * q >= 4) *reinterpret_cast<float4 *>(dst) = g;
+            else dst[0] = g.x;  // the ragged last quad holds dL/db3 alone
+        } else {
+            const int owner = (int)q / (int)per;  // the range is a few million floats: 32-bit arithmetic
+            st_peer(reinterpret_cast<float4 *>(x.peers.data[owner] + x.stage) + (long long)rank * per + (q - owner * per), g);
+        }
     }
 #if AMP_EXCHANGE_STAMPS == 1
     if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); x.timing[0] = t_start; x.timing[1] = t; }
@@ -795,7 +806,6 @@ __global__ void __launch_bounds__(256) finalize_exchange_kernel(FinalizeParams p
             st_release_sys(x.peers.flags[threadIdx.x] + rank, epoch);
         }
     }
-    float *bucket_local = x.peers.data[rank];
     if (threadIdx.x == 0) {
         ok = wait_all(local_flags, world, epoch, x.spin_limit);
         if (!ok && blockIdx.x == 0) report_failure(x.ctl, x.host_status, 1u, bucket_local, x.hull, x.count);
@@ -817,7 +827,19 @@ __global__ void __launch_bounds__(256) finalize_exchange_kernel(FinalizeParams p
     const long long q0 = (long long)rank * per, q1 = min(quads, q0 + per);
     const float inv = 1.0f / (float)world;
     const float4 *staged = reinterpret_cast<const float4 *>(bucket_local + x.stage);
-    for (long long q = q0 + tid; ok && q < q1; q += stride) {
+    for (long long q = q0 + tid; SWITCH && ok && q < q1; q += stride) {
+        float *at = x.mc + x.hull + 4 * q;
+        if (x.count - 4 * q >= 4) {
+            float4 v;
+            asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(at) : "memory");
+            asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(at), "f"(v.x * inv), "f"(v.y * inv), "f"(v.z * inv), "f"(v.w * inv) : "memory");
+        } else {  // dL/db3: one float, the rest of the quad belongs to somebody else
+            float v;
+            asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f32 %0, [%1];" : "=f"(v) : "l"(at) : "memory");
+            asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(at), "f"(v * inv) : "memory");
+        }
+    }
+    for (long long q = q0 + tid; !SWITCH && ok && q < q1; q += stride) {
         float4 v[MAXW];
 #pragma unroll
         for (int r = 0; r < MAXW; ++r)
@@ -1040,6 +1062,7 @@ static int plan_exchange(amp_disc_train_t *t, amp_bucket_t *bk, float *const g[6
     const long long quads = (x->count + 3) / 4, per = (quads + bk->world - 1) / bk->world;
     AMP_REQUIRE(bk->world == 1 || per * 4 * bk->world <= bk->stage_floats, "amp_disc_train_step_exchange: staging area too small");  // sized from the bucket
     x->peers = bk->peers;
+    x->mc = bk->connected && bk->in_switch ? bk->mc_data : nullptr;
     x->rank = bk->rank;
     x->world = bk->world;
     x->stage = bk->floats;
@@ -1186,7 +1209,10 @@ static int train_step_impl(amp_disc_train_t *t, const float *W1, const float *b1
             kern<<<grid, 256, 0, st>>>(f, ex);
             return AMP_OK;
         };
-        int rc = bucket->world <= 2 ? launch(finalize_exchange_kernel<2>) : bucket->world <= 4 ? launch(finalize_exchange_kernel<4>) : launch(finalize_exchange_kernel<8>);
+        int rc = ex.mc ? launch(finalize_exchange_kernel<2, true>)
+                 : bucket->world <= 2 ? launch(finalize_exchange_kernel<2, false>)
+                 : bucket->world <= 4 ? launch(finalize_exchange_kernel<4, false>)
+                                      : launch(finalize_exchange_kernel<8, false>);
         if (rc != AMP_OK) return rc;
     } else {
         finalize_kernel<<<sm_count() * 4, 256, 0, st>>>(f);
