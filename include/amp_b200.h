@@ -332,10 +332,11 @@ AMP_API int amp_bucket_in_switch(const amp_bucket_t *b);
 /* amp_disc_train_step with the gradient exchange fused into its last kernel (replaces the discriminator's
  * share of skrl Model.reduce_parameters, train.py:184-196): gW1 .. gb3 must be six views of `bucket` that lie side by side
  * (any order, each starting on a multiple of 4 floats, the one-element gb3 last); on return of the stream they hold the MEAN
- * over the ranks of d loss / d parameter -- bit for bit what amp_disc_train_step followed by amp_bucket_allreduce_mean over
- * that range gives.  The kernel that sums the split-K slices pushes each quad straight into the owning rank's staging area
- * (peer stores), the owner reduces and publishes; the local bucket is never written with un-reduced gradients and there is no
- * second launch.  terms / logits stay per rank.  A collective: every rank calls it at the same point of its bucket's call
+ * over the ranks of d loss / d parameter -- the reduction amp_bucket_allreduce_mean over that range would have made after
+ * amp_disc_train_step (same summation: fixed rank order over peer memory, the switch's sum on a shared bucket), identical on
+ * every rank.  The kernel that sums the split-K slices pushes each quad straight into the owning rank's staging area (peer
+ * stores), the owner reduces and publishes; on a shared bucket it writes the local bucket and reduces its slice in the
+ * switch.  No second launch.  terms / logits stay per rank.  A collective: every rank calls it at the same point of its bucket's call
  * sequence.  bucket world == 1: identical to amp_disc_train_step.  At most 8 ranks. */
 AMP_API int amp_disc_train_step_exchange(amp_disc_train_t *t, const float *W1, const float *b1, const float *W2, const float *b2,
                                          const float *W3, const float *b3, int64_t batch_rows, float loss_scale,
