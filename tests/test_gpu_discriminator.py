@@ -146,6 +146,26 @@ def test_one_launch_for_large_batches_and_many_tiles_per_cta():
     assert torch.equal(disc.style_reward(x[:mid]), whole[:mid])
 
 
+def test_one_million_rows_properties():
+    """BASELINE configs[3] size (1 M rows x 166, the bench's reward stage) through size-independent properties: the reward of a
+    row does not depend on where the row sits in the batch (a permuted batch gives the permuted rewards, bit for bit: other tile,
+    other CTA, other half of a CTA pair), the call is deterministic, and a random subset agrees with the oracle."""
+    disc, ora, inputs = build(166, 5.0)
+    M = 1_000_000
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = inputs(4096, 3).cuda().repeat(245, 1)[:M].contiguous()
+    x += 0.25 * torch.randn(M, 166, device="cuda", generator=g)
+    whole, logits = disc.style_reward(x, return_logits=True)
+    assert torch.equal(disc.style_reward(x), whole)
+    perm = torch.randperm(M, device="cuda", generator=g)
+    assert torch.equal(disc.style_reward(x[perm].contiguous()), whole[perm])
+    assert torch.equal(disc.style_reward_sampled(x, perm[:300_000]), whole[perm[:300_000]])
+    assert torch.isfinite(whole).all() and float(whole.min()) >= 0.0
+    pick = torch.randperm(M, generator=torch.Generator().manual_seed(1))[:2048]
+    want = ora.logits(x[pick.cuda()].cpu())
+    assert (logits[pick.cuda()].cpu() - want).abs().max() <= 1e-2 * max(1.0, float(want.abs().max()))
+
+
 def test_wide_input_chunks_and_gather_give_the_same_bits():
     """K*A = 830 takes the cast-kernel path (x_hat of a chunk prepared by normalise_cast_kernel): a batch larger than the
     chunk capacity (max_rows) is cut into chunks and gives the same bits as independent calls; the gathered form agrees."""
